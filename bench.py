@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native adaptive-factorization hot path.
+
+Metric (BASELINE.json): Bull-head QL λ-points/s  — `ql(A - λI).L[1,1]` over the 1024 x 1024 complex λ grid of
+config C3 (per GPU; weak scaling: with N ranks the global grid is 1024 x 1024·N, rank r owns a 1024-row slab), and
+adaptive-QR columns/s on the 4096 batched Bessel solves of config C2 (reported under "secondary").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-secondary]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL only for the barrier / max-over-ranks of the timings: the path
+has no exchange step).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BULLHEAD_COLUMN = np.array([2j, 0.0, 0.0, 1.0, 0.7])      # BandedMatrix(-3=>7/10, -2=>1, 1=>2im) data column
+NX = NY = 1024
+BYTES_PER_POINT = 36            # 16 (λ) + 16 (L11) + 4 (status): SURVEY §8d
+FLOPS_PER_POINT = 6.9e3         # LAPACK-style count of the reference's per-λ work
+BYTES_PER_COLUMN = 72           # Bessel (l=u=1): SURVEY §8d
+FLOPS_PER_COLUMN = 42
+
+
+def grid_slab(rank: int, world: int) -> np.ndarray:
+    """Rows [rank*NY, (rank+1)*NY) of the global 1024 x (1024*world) λ grid over the C3 window."""
+    x = np.linspace(-10.0, 7.0, NX)
+    y = np.linspace(-7.0, 8.0, NY * world)[rank * NY:(rank + 1) * NY]
+    return (x[None, :] + 1j * y[:, None]).reshape(-1)
+
+
+def c2_z():
+    return 1e3 + (1e5 - 1e3) * np.arange(4096) / 4095
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [s.strip() for s in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle (numpy -> LAPACK zgeev + restated tail_de/ql_X!), all host threads
+# ---------------------------------------------------------------------------------------------------------
+
+def cpu_bullhead(lam: np.ndarray, threads: int):
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import toeplitz_ql as tq
+    chunks = np.array_split(lam, max(threads * 4, 1))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(lambda c: tq.ql_toeplitz_l11(BULLHEAD_COLUMN, c), chunks))
+    dt = time.perf_counter() - t0
+    return dt, res
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = 128                                       # bounded sample: 128 of the 1024 rows of the rank-0 slab
+    lam = grid_slab(0, max(world, 1))[:rows * NX]
+    for _ in range(max(args.warmup, 1)):
+        cpu_bullhead(lam[:NX * 8], threads)
+    times = []
+    for _ in range(args.steps):
+        dt, _ = cpu_bullhead(lam, threads)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = lam.size / (ms * 1e-3)
+    line = {
+        "metric": "bullhead_ql_lambda_points_per_s", "value": val, "unit": "lambda-points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "C3 Bull-head ql(A-λI).L[1,1], 1024x1024 λ grid (bands -3,-2,+1), per-GPU slab",
+                   "sample": f"{rows} of 1024 grid rows per step"},
+        "cpu_baseline": {"value": val, "unit": "lambda-points/s", "cores": threads, "kind": "port",
+                         "sample": f"{rows}x{NX} λ-points per step, numpy/LAPACK zgeev oracle, {threads} threads"},
+        "e2e": {"value": val, "unit": "lambda-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import ila_b200
+    from ila_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.check(ila_b200.lib().ila_set_device(local_rank))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    def timed(fn, steps, warmup):
+        """K steps, each bracketed by CUDA events on the current stream, L2 flushed (untimed) between steps."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        tot = 0.0
+        for _ in range(steps):
+            flush_l2()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        barrier()
+        return max_over_ranks(tot)          # ms for all K steps, max over ranks
+
+    lib = ila_b200.lib()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    # ---------------- C3: Bull-head λ grid, device resident ----------------
+    lam_h = grid_slab(rank, world)
+    n = lam_h.size
+    d_lam = torch.from_numpy(lam_h).to(dev)
+    d_L = torch.empty(n, dtype=torch.complex128, device=dev)
+    d_st = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def step_dev():
+        ila_b200.ql_toeplitz_l11_dev(BULLHEAD_COLUMN, d_lam, d_L, d_st, stream=stream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = lib.ila_kernel_launches()
+    ms_total = timed(step_dev, args.steps, args.warmup)
+    launches = lib.ila_kernel_launches() - l0 - args.warmup
+    ms_step = ms_total / args.steps
+    value = n * world / (ms_step * 1e-3)
+
+    # ---------------- e2e: host API, pinned host buffers, H2D + kernel + D2H inside the timed region --------
+    h_lam = torch.from_numpy(lam_h).pin_memory()
+    h_L = torch.empty(n, dtype=torch.complex128).pin_memory()
+    h_st = torch.empty(n, dtype=torch.int32).pin_memory()
+    col = np.ascontiguousarray(BULLHEAD_COLUMN, dtype=np.complex128)
+
+    def step_e2e():
+        _lib.check(lib.ila_ql_toeplitz_l11_c64(3, 1, _lib.ptr(col), _lib.ptr(h_lam), n, 1, _lib.ptr(h_L), None,
+                                               _lib.ptr(h_st), 1))
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t_e2e = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_e2e()                          # synchronous: returns after the D2H copies completed
+        t_e2e += time.perf_counter() - t0
+    barrier()
+    e2e_ms = max_over_ranks(t_e2e * 1e3) / args.steps
+    e2e_value = n * world / (e2e_ms * 1e-3)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    # cross-check device and host paths agree bit for bit
+    same = bool(torch.equal(torch.view_as_real(d_L.cpu()).nan_to_num(0.0), torch.view_as_real(h_L).nan_to_num(0.0)))
+
+    hbm_peak, peak_kind = measured_peaks()
+    achieved_gbs = BYTES_PER_POINT * n / (ms_step * 1e-3) / 1e9
+    fp64_peak = ila_b200.fp64_peak_tflops()
+    line = {
+        "metric": "bullhead_ql_lambda_points_per_s", "value": value, "unit": "lambda-points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": "C3 Bull-head ql(A-λI).L[1,1], 1024x1024 λ grid (bands -3,-2,+1), per-GPU slab",
+                   "points_per_gpu": n, "l2": "flushed between timed steps (256 MiB fill)", "parallelism":
+                   f"shift-grid sharding x{world}, no collective on the data path"},
+        "e2e": {"value": e2e_value, "unit": "lambda-points/s", "h2d_bytes_per_step": 16 * n,
+                "d2h_bytes_per_step": 20 * n, "ms_per_step": e2e_ms, "host_equals_device": same},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                     "kernel": "ql_toeplitz_l11_kernel<4,false,false>", "bytes_per_unit": BYTES_PER_POINT,
+                     "note": "FP64-pipe bound, not HBM bound: see roofline_fp64"},
+        "roofline_fp64": {"bound": "fp64", "achieved": FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12,
+                          "peak": fp64_peak, "unit": "TFLOP/s",
+                          "frac": FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12 / fp64_peak,
+                          "flops_per_unit": FLOPS_PER_POINT, "peak_kind": "measured DFMA probe (this run)"},
+        "clocks": sampler.summary(),
+    }
+
+    # ---------------- secondary: C2 batched Bessel adaptive-QR solves ----------------
+    if not args.no_secondary:
+        from scipy.special import jv
+        zs = c2_z()
+        p, q, r = ila_b200.bessel_operator(zs)
+        caps = np.ceil(1.06 * zs + 3000).astype(np.int64)
+        plan = ila_b200.QrBandedPlan(1, 1, p, q, r, b=jv(1, zs)[:, None], ncap_per=caps, device=dev)
+        k2 = max(1, min(args.steps, 5))
+        ms2 = timed(plan.run, k2, 1) / k2
+        cols = float(plan.d_nswept.sum().item())
+        cols_ref = float(plan.d_ncols.sum().item())
+        gbs2 = BYTES_PER_COLUMN * cols / (ms2 * 1e-3) / 1e9
+        line["secondary"] = {
+            "metric": "adaptive_qr_columns_per_s", "value": cols * world / (ms2 * 1e-3), "unit": "columns/s",
+            "ms_per_step": ms2, "config": {"workload": "C2 4096 Bessel solves, z in [1e3,1e5] (per GPU)",
+                                           "columns_swept": cols, "columns_reference_datasize": cols_ref},
+            "roofline": {"bound": "hbm", "achieved": gbs2, "peak": hbm_peak, "unit": "GB/s", "frac": gbs2 / hbm_peak,
+                         "traffic": None, "peak_kind": peak_kind, "bytes_per_unit": BYTES_PER_COLUMN,
+                         "note": "latency bound: 4096 serial recurrences = 128 warps on 148 SMs"},
+            "gpu_launches_per_step": 3,
+        }
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rows = 256
+        sample = lam_h[:rows * NX]
+        dt, res = cpu_bullhead(sample, threads)
+        line["cpu_baseline"] = {"value": sample.size / dt, "unit": "lambda-points/s", "cores": threads, "kind": "port",
+                                "sample": f"{rows}x{NX} λ-points once, numpy/LAPACK zgeev oracle on {threads} threads "
+                                          "(Julia absent: reference cannot run; it is single-threaded)"}
+        if "secondary" in line:
+            from oracle import banded as ob
+            from scipy.special import jv
+            zsub = c2_z()[::64]
+            p, q, r = ob.bessel_operator(zsub)
+            t0 = time.perf_counter()
+            o = ob.qr_banded_solve(1, 1, p, q, r, b=jv(1, zsub)[:, None], ncap=int(1.06 * 1e5 + 3000), nthreads=threads)
+            dt2 = time.perf_counter() - t0
+            line["secondary"]["cpu_baseline"] = {"value": float(o["ncols"].sum()) / dt2, "unit": "columns/s",
+                                                 "cores": threads, "kind": "port",
+                                                 "sample": "every 64th z of C2 (64 solves), C oracle, OpenMP"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

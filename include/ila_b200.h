@@ -1,0 +1,121 @@
+/* ila_b200.h — C ABI of the B200-native adaptive-factorization hot path.
+ *
+ * The reference (InfiniteLinearAlgebra.jl v0.10.3) is pure Julia and has NO FFI; its "boundary" is
+ * multiple dispatch.  Each entry point below replaces the narrow waist named beside it
+ * and is what a `ccall` shim would bind (see INTEGRATION.md and julia/ILAB200.jl).  All citations are
+ * relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / C++ types.  Host entry points take HOST pointers, own all
+ *     device memory and streams, are synchronous, and shard the batch over `ngpus` devices of this
+ *     process (ngpus <= 0: all visible devices; under one-process-per-GPU launches pass 1).
+ *   - `_dev` entry points take DEVICE pointers valid on the current CUDA device and enqueue on
+ *     `stream` (a cudaStream_t passed as void*; NULL = default stream) without synchronising.
+ *   - return value: 0 on success, negative ILA_ERR_* on a library error (ila_last_error() has text).
+ *     Per-instance outcomes (the reference's exceptions) go to status[]:
+ *       0 ILA_OK
+ *       1 ILA_NO_QL          DomainError "QL factorization does not exist"   (src/banded/infqltoeplitz.jl:13,23)
+ *       2 ILA_NOT_REAL       DomainError "Real-valued QL ... does not exist" (src/banded/infqltoeplitz.jl:12)
+ *       3 ILA_NOT_CONVERGED  ncap reached / "Did not converge"               (src/infql.jl:181)
+ *       4 ILA_NOT_POSDEF     pbtrf info > 0 (the reference discards it,        src/infcholesky.jl:49)
+ *       5 ILA_NAN            "Not-a-number encounted"                        (src/infqr.jl:324)
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns ILA_ERR_NOGPU.
+ */
+#ifndef ILA_B200_H
+#define ILA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } ila_c64;
+
+enum { ILA_OK = 0, ILA_NO_QL = 1, ILA_NOT_REAL = 2, ILA_NOT_CONVERGED = 3, ILA_NOT_POSDEF = 4, ILA_NAN = 5 };
+enum { ILA_ERR_CUDA = -1, ILA_ERR_ARG = -2, ILA_ERR_NOGPU = -3, ILA_ERR_UNSUPPORTED = -4, ILA_ERR_CAPACITY = -5 };
+
+/* ---- library ------------------------------------------------------------------------------- */
+int ila_version(void);                 /* 10000*major + 100*minor + patch */
+int ila_device_count(void);            /* number of visible CUDA devices (0 without a GPU) */
+const char *ila_last_error(void);      /* text of the last error on the calling thread */
+int ila_set_device(int dev);           /* select the CUDA device single-GPU calls (ngpus == 1, `_dev`) run on */
+int ila_get_device(void);
+int64_t ila_kernel_launches(void);     /* number of kernels this library launched so far (process-wide) */
+/* DFMA throughput probe: runs a register-resident FP64 FMA loop on the current device and returns the
+ * achieved TFLOP/s (2 flop per FMA) — the FP64 roofline denominator (MEASURED_PEAKS.json has none). */
+int ila_fp64_peak_probe(double *tflops_out, double *ms_out);
+/* dependent-chain latencies on one warp, in SM cycles per op: out4[0] DFMA, [1] DMUL+DADD pair, [2] DSQRT+DADD,
+ * [3] DDIV+DADD — what bounds the serial recurrences of K1/K2/K5. */
+int ila_fp64_latency_probe(double *out4);
+
+/* ---- K3: Toeplitz-tail QL, u == 1 -----------------------------------------------------------
+ * L11[i] = ql(A - lambda[i]*I).L[1,1] for the pure Toeplitz operator A with bandwidths (l, 1).
+ * Replaces, per shift: `A - λ*I` + ql(::InfToeplitz) -> _inf_ql -> ql_hessenberg(::InfToeplitz)
+ * (src/banded/infqltoeplitz.jl:56-65,182-191) = tail_de (:7-27) + ql_X! (:31-39) + L[1,1] read (src/infql.jl:96).
+ *   a          l+u+1 coefficients in BandedMatrices data-column order: a_{+1}, a_0, a_{-1}, ..., a_{-l}
+ *   lambda     n shifts;  branch_rank 1 = `findmax` (default), k = k-th largest |mu|^2 (examples/toeplitz.jl:22-27)
+ *   L11        n results (NaN where status != 0)
+ *   tail_opt   NULL or n x (2m+2) values, m = l+2:  X[1,1..m], X[2,1..m], tau[1], tau[2]  after ql_X!
+ *              (first L column = [X[1,m-1]; X[2,m-1:-1:1]], tail L column = X[2,m:-1:1], 2x2 Q = QLPackedQ(X[:,m-1:m],tau))
+ * _f64 is the `T<:Real` method (tail_de :7-16): real dominant eigenvalue required (else ILA_NOT_REAL).
+ */
+int ila_ql_toeplitz_l11_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank,
+                            ila_c64 *L11, ila_c64 *tail_opt, int32_t *status, int ngpus);
+int ila_ql_toeplitz_l11_f64(int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank,
+                            double *L11, double *tail_opt, int32_t *status, int ngpus);
+/* device-resident forms: `a` stays a HOST pointer (l+u+1 values, passed by value to the kernel) */
+int ila_ql_toeplitz_l11_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d_lambda, int64_t n, int branch_rank,
+                                ila_c64 *d_L11, ila_c64 *d_tail_opt, int32_t *d_status, void *stream);
+int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank,
+                                double *d_L11, double *d_tail_opt, int32_t *d_status, void *stream);
+
+/* ---- K1+K2: adaptive banded QR solve  x_i = A_i \ b_i ----------------------------------------
+ * Replaces qr(A) -> adaptiveqr (src/infqr.jl:163-174) and `\` = ldiv!(F.R, F.Q'*b) (src/infqr.jl:370-374):
+ * AdaptiveQRData/partialqr! (:2-13,32-48) -> _banded_qr!, the Q'b adaptive driver (:236-274) and the
+ * back-substitution (:350-355), fused per instance with on-device convergence detection.
+ *
+ * Operator i (bandwidths l,u shared by the batch) is described by generators, one per diagonal, in
+ * BandedMatrices data-row order rr = 0..l+u  <->  diagonal d = u - rr (d = col - row):
+ *     entry at position t (0-based, along the diagonal, as in `BandedMatrix(d => v)`)
+ *         = head[rr*hp + t]                          for t < hp      (shared explicit head, may be NULL/hp = 0)
+ *         = (p[i][rr] + q[i][rr]*t) / r[i][rr]       otherwise       (r == NULL means 1)
+ *     and shift[i] (NULL = 0) is subtracted on the main diagonal (A_i - shift_i*I).
+ *   b          batch x nb (instance-major): the non-zero prefix of the right-hand sides
+ *   tol        convergence tolerance on max|(Q'b)[j : j+l]| (reference default floatmin, infqr.jl:236)
+ *   colgrowth  the reference's COLGROWTH = 1000 (infqr.jl:238): the test runs at columns 1, 1+cg, 1+2cg, ...
+ *   ncap       per-instance column capacity (uniform) — or ncap_per[batch] when non-NULL
+ *   x, xoff    ragged output: x[xoff[i] .. xoff[i+1]) = solution prefix of instance i, length ncols[i]
+ *              (= the reference's B.datasize: n_conv + colgrowth - 1 + l); xcap = capacity of x in doubles.
+ *              If the total exceeds xcap the call returns ILA_ERR_CAPACITY and xoff[batch] holds the need.
+ *   nconv      1-based column at which the convergence test passed (0 if it never ran / l == 0)
+ *   factors_opt NULL or ragged (2l+u+1) x ncols[i] column-major band storage (R above, reflectors below;
+ *              bandwidths (l, l+u), src/infqr.jl:11) at offset (2l+u+1)*xoff[i]; tau_opt, qtb_opt ragged like x.
+ */
+int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const double *q, const double *r,
+                            const double *shift, int hp, const double *head, int nb, const double *b, double tol,
+                            int colgrowth, int64_t ncap, const int64_t *ncap_per, double *x, int64_t xcap,
+                            int64_t *xoff, int64_t *ncols, int64_t *nconv, double *factors_opt, double *tau_opt,
+                            double *qtb_opt, int32_t *status, int ngpus);
+
+/* device-resident two-phase form (no host round trip between the phases; the caller owns all buffers):
+ *   phase 1 `_factor_dev`: forward sweep + Q'b + convergence; writes d_ncols, d_nconv, d_status, d_xoff (scan).
+ *   phase 2 `_backsolve_dev`: back-substitution into ragged d_x using d_xoff.
+ * d_work: ila_qr_banded_work_bytes(l,u,batch,ncap,ncap_per) bytes.  d_woff: batch+1 int64 workspace offsets
+ * (in columns), filled by the host helper ila_qr_banded_work_offsets. */
+int64_t ila_qr_banded_work_bytes(int l, int u, int64_t batch, int64_t ncap, const int64_t *ncap_per);
+int ila_qr_banded_work_offsets(int64_t batch, int64_t ncap, const int64_t *ncap_per, int64_t *woff_host);
+int ila_qr_banded_factor_f64_dev(int l, int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                 const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
+                                 double tol, int colgrowth, const int64_t *d_woff, double *d_work, int64_t *d_ncols,
+                                 int64_t *d_nconv, int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status,
+                                 int want_reflectors, void *stream);
+int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *d_woff, const double *d_work,
+                                    const int64_t *d_ncols, const int64_t *d_nswept, const int64_t *d_xoff,
+                                    const int32_t *d_status, double *d_x, int64_t xcap, int want_reflectors,
+                                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ILA_B200_H */

@@ -1,0 +1,17 @@
+"""infinitelinearalgebra.jl_b200 — B200-native adaptive-factorization hot path of InfiniteLinearAlgebra.jl.
+
+The directory name contains a dot, so import it through the top-level alias module:
+
+    import ila_b200                                  # loads this package as `ila_b200`
+    L11, status = ila_b200.ql_toeplitz_l11(col, lambdas)
+
+Contents: `csrc/` (hand-written sm_100a CUDA + the C ABI of include/ila_b200.h), `_lib` (ctypes binding),
+`batched` (batched numpy/torch-pointer entry points), `api` (host-side mirror of the reference's Julia interface).
+"""
+from . import _lib
+from ._lib import IlaError, SO_PATH, build, lib
+from .batched import (FLOATMIN, QrBandedPlan, bessel_operator, fp64_peak_tflops, ql_toeplitz_l11,
+                      ql_toeplitz_l11_dev, qr_banded_solve)
+
+__all__ = ["IlaError", "SO_PATH", "build", "lib", "FLOATMIN", "QrBandedPlan", "bessel_operator", "fp64_peak_tflops",
+           "ql_toeplitz_l11", "ql_toeplitz_l11_dev", "qr_banded_solve"]

@@ -1,0 +1,210 @@
+"""Batched host-side entry points over the C ABI (numpy in / numpy out), plus device-resident plans.
+
+These are the "batched form over a vector of shifts" of the north star: thin argument marshalling around
+`ila_ql_toeplitz_l11_*` and `ila_qr_banded_solve_f64`.  All arithmetic happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib, ptr
+
+FLOATMIN = float(np.finfo(np.float64).tiny)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3: Toeplitz-tail QL
+# ------------------------------------------------------------------------------------------------
+
+def ql_toeplitz_l11(data_column, lambdas, branch_rank: int = 1, want_tail: bool = False, ngpus: int = 1,
+                    real_path: bool | None = None, out=None, status_out=None):
+    """L[1,1] of ql(A - λI) for the pure Toeplitz A (bandwidths (l,1)) with BandedMatrices data column
+    `data_column` = [a_{+1}, a_0, a_{-1}, …, a_{-l}], over all shifts `lambdas`
+    (reference: src/banded/infqltoeplitz.jl:56-65,191 and `.L[1,1]`, src/infql.jl:96).
+
+    Returns (L11, status[, tail]); entries with status != 0 are NaN (the reference throws DomainError there).
+    """
+    col = np.asarray(data_column)
+    lam = np.asarray(lambdas)
+    if real_path is None:
+        real_path = not (np.iscomplexobj(col) or np.iscomplexobj(lam))
+    dt = np.float64 if real_path else np.complex128
+    col = np.ascontiguousarray(col, dtype=dt)
+    shape = lam.shape
+    lam = np.ascontiguousarray(lam, dtype=dt).reshape(-1)
+    n = lam.size
+    l = col.size - 2
+    m = l + 2
+    L11 = out if out is not None else np.empty(n, dtype=dt)
+    status = status_out if status_out is not None else np.empty(n, dtype=np.int32)
+    tail = np.empty((n, 2 * m + 2), dtype=dt) if want_tail else None
+    fn = lib().ila_ql_toeplitz_l11_f64 if real_path else lib().ila_ql_toeplitz_l11_c64
+    check(fn(l, 1, ptr(col), ptr(lam), n, branch_rank, ptr(L11), ptr(tail), ptr(status), ngpus))
+    res = (L11.reshape(shape), status.reshape(shape))
+    if want_tail:
+        res = res + (tail.reshape(shape + (2 * m + 2,)),)
+    return res
+
+
+def ql_toeplitz_l11_dev(data_column, d_lambda, d_L11, d_status, branch_rank: int = 1, d_tail=None, stream=None,
+                        real_path: bool = False):
+    """Device-resident form: `d_*` are torch CUDA tensors (complex128 / float64 / int32) on the current device."""
+    dt = np.float64 if real_path else np.complex128
+    col = np.ascontiguousarray(np.asarray(data_column), dtype=dt)
+    l = col.size - 2
+    n = d_lambda.numel()
+    fn = lib().ila_ql_toeplitz_l11_f64_dev if real_path else lib().ila_ql_toeplitz_l11_c64_dev
+    s = C.c_void_p(stream) if stream else None
+    check(fn(l, 1, ptr(col), ptr(d_lambda), n, branch_rank, ptr(d_L11), ptr(d_tail), ptr(d_status), s))
+
+
+# ------------------------------------------------------------------------------------------------
+# K1+K2: adaptive banded QR solve
+# ------------------------------------------------------------------------------------------------
+
+def _op_arrays(nd, batch, p, q, r, shift, head):
+    p = np.ascontiguousarray(np.broadcast_to(np.asarray(p, dtype=np.float64), (batch, nd)))
+    q = np.ascontiguousarray(np.broadcast_to(np.asarray(q, dtype=np.float64), (batch, nd)))
+    r = None if r is None else np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64), (batch, nd)))
+    shift = None if shift is None else np.ascontiguousarray(
+        np.broadcast_to(np.asarray(shift, dtype=np.float64), (batch,)))
+    hp = 0
+    if head is not None:
+        head = np.ascontiguousarray(np.asarray(head, dtype=np.float64))
+        if head.shape[0] != nd:
+            raise ValueError("head must have l+u+1 rows")
+        hp = head.shape[1]
+    return p, q, r, shift, hp, head
+
+
+def qr_banded_solve(l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=FLOATMIN, colgrowth=1000,
+                    ncap=200_000, ncap_per=None, batch=None, want_factors=False, ngpus=1, xcap=None, x_out=None):
+    """Batched `A_i \\ b_i` by adaptive banded QR (reference src/infqr.jl:236-274,350-355,370-374).
+
+    Operator description: see include/ila_b200.h (generators per diagonal, BandedMatrices data-row order).
+    Returns dict(x=list of per-instance solution prefixes (views), xflat, xoff, ncols, nconv, status
+    [, factors, tau, qtb as per-instance lists]).
+    """
+    nd = l + u + 1
+    if batch is None:
+        batch = int(np.asarray(p).reshape(-1, nd).shape[0])
+    p, q, r, shift, hp, head = _op_arrays(nd, batch, p, q, r, shift, head)
+    b = np.asarray(b, dtype=np.float64)
+    if b.ndim == 1:
+        b = np.broadcast_to(b, (batch, b.shape[0]))
+    b = np.ascontiguousarray(b)
+    nb = b.shape[1]
+    caps = None
+    if ncap_per is not None:
+        caps = np.ascontiguousarray(np.asarray(ncap_per, dtype=np.int64))
+    if xcap is None:
+        xcap = int(caps.sum()) if caps is not None else int(batch) * int(ncap)
+    x = x_out if x_out is not None else np.empty(xcap, dtype=np.float64)
+    xcap = x.size
+    xoff = np.zeros(batch + 1, dtype=np.int64)
+    ncols = np.zeros(batch, dtype=np.int64)
+    nconv = np.zeros(batch, dtype=np.int64)
+    status = np.zeros(batch, dtype=np.int32)
+    LD = 2 * l + u + 1
+    fac = np.empty(xcap * LD) if want_factors else None
+    tau = np.empty(xcap) if want_factors else None
+    qtb = np.empty(xcap) if want_factors else None
+    check(lib().ila_qr_banded_solve_f64(l, u, batch, ptr(p), ptr(q), ptr(r), ptr(shift), hp, ptr(head), nb, ptr(b),
+                                        float(tol), int(colgrowth), int(ncap), ptr(caps), ptr(x), xcap, ptr(xoff),
+                                        ptr(ncols), ptr(nconv), ptr(fac), ptr(tau), ptr(qtb), ptr(status), ngpus))
+    out = dict(xflat=x[:xoff[batch]], xoff=xoff, ncols=ncols, nconv=nconv, status=status,
+               x=[x[xoff[i]:xoff[i + 1]] for i in range(batch)])
+    if want_factors:
+        out["factors"] = [fac[xoff[i] * LD:xoff[i + 1] * LD].reshape(-1, LD) for i in range(batch)]
+        out["tau"] = [tau[xoff[i]:xoff[i + 1]] for i in range(batch)]
+        out["qtb"] = [qtb[xoff[i]:xoff[i + 1]] for i in range(batch)]
+    return out
+
+
+class QrBandedPlan:
+    """Device-resident two-phase adaptive QR solve (torch tensors as plain device memory).
+
+    All inputs live in HBM before `run()`; `run()` enqueues forward sweep, offset scan and back-substitution on
+    the current torch stream without any host synchronisation — the timed region of bench.py's `value`.
+    """
+
+    def __init__(self, l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=FLOATMIN, colgrowth=1000,
+                 ncap=200_000, ncap_per=None, device=None, xcap=None, want_reflectors=False):
+        import torch
+        self.torch = torch
+        nd = l + u + 1
+        batch = int(np.asarray(p).reshape(-1, nd).shape[0])
+        p, q, r, shift, hp, head = _op_arrays(nd, batch, p, q, r, shift, head)
+        b = np.asarray(b, dtype=np.float64)
+        if b.ndim == 1:
+            b = np.broadcast_to(b, (batch, b.shape[0]))
+        b = np.ascontiguousarray(b)
+        self.l, self.u, self.batch, self.hp, self.nb = l, u, batch, hp, b.shape[1]
+        self.tol, self.colgrowth = float(tol), int(colgrowth)
+        self.refl = 1 if want_reflectors else 0
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        caps = None if ncap_per is None else np.ascontiguousarray(np.asarray(ncap_per, dtype=np.int64))
+        woff = np.zeros(batch + 1, dtype=np.int64)
+        check(lib().ila_qr_banded_work_offsets(batch, int(ncap), ptr(caps), ptr(woff)))
+        wbytes = lib().ila_qr_banded_work_bytes(l, u, batch, int(ncap), ptr(caps))
+        t = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+        self.d_p, self.d_q, self.d_r, self.d_shift, self.d_head, self.d_b = t(p), t(q), t(r), t(shift), t(head), t(b)
+        self.d_woff = t(woff)
+        self.d_work = torch.empty(wbytes // 8, dtype=torch.float64, device=dev)
+        self.d_ncols = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.d_nconv = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.d_nswept = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.d_xoff = torch.zeros(batch + 1, dtype=torch.int64, device=dev)
+        self.d_status = torch.zeros(batch, dtype=torch.int32, device=dev)
+        if xcap is None:
+            xcap = int(caps.sum()) if caps is not None else batch * int(ncap)
+        self.xcap = int(xcap)
+        self.d_x = torch.empty(self.xcap, dtype=torch.float64, device=dev)
+
+    def _stream(self):
+        lib().ila_set_device(self.device.index or 0)
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def run(self):
+        self.run_factor()
+        self.run_backsolve()
+        return 3   # kernels launched: forward, scan, back-substitution
+
+    def run_factor(self):
+        s = self._stream()
+        check(lib().ila_qr_banded_factor_f64_dev(
+            self.l, self.u, self.batch, ptr(self.d_p), ptr(self.d_q), ptr(self.d_r), ptr(self.d_shift), self.hp,
+            ptr(self.d_head), self.nb, ptr(self.d_b), self.tol, self.colgrowth, ptr(self.d_woff), ptr(self.d_work),
+            ptr(self.d_ncols), ptr(self.d_nconv), ptr(self.d_nswept), ptr(self.d_xoff), ptr(self.d_status),
+            self.refl, s))
+        return 2
+
+    def run_backsolve(self):
+        s = self._stream()
+        check(lib().ila_qr_banded_backsolve_f64_dev(
+            self.l, self.u, self.batch, ptr(self.d_woff), ptr(self.d_work), ptr(self.d_ncols), ptr(self.d_nswept),
+            ptr(self.d_xoff), ptr(self.d_status), ptr(self.d_x), self.xcap, self.refl, s))
+        return 1
+
+
+def bessel_operator(z):
+    """Generator description of A = BandedMatrix(0 => -2*(0:∞)/z, 1 => Ones(∞), -1 => Ones(∞))
+    (README.md:41, test/test_infqr.jl:95); data-row order: diagonal +1, 0, -1."""
+    z = np.atleast_1d(np.asarray(z, dtype=np.float64))
+    batch = z.shape[0]
+    p = np.tile(np.array([1.0, 0.0, 1.0]), (batch, 1))
+    q = np.tile(np.array([0.0, -2.0, 0.0]), (batch, 1))
+    r = np.ones((batch, 3))
+    r[:, 1] = z
+    return p, q, r
+
+
+def fp64_peak_tflops():
+    t = C.c_double(0.0)
+    ms = C.c_double(0.0)
+    check(lib().ila_fp64_peak_probe(C.byref(t), C.byref(ms)))
+    return t.value

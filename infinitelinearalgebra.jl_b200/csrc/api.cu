@@ -1,0 +1,514 @@
+// api.cu — the C ABI of libila_b200 (include/ila_b200.h): host-pointer entry points that own device memory,
+// streams and the multi-GPU sharding, plus the device-pointer (`_dev`) forms.  No torch types, no CPU fallback.
+#include <mutex>
+#include <vector>
+
+#include "ila_common.cuh"
+
+namespace ila {
+
+thread_local char g_last_error[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+// from ql_toeplitz.cu
+int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
+                       int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream);
+
+// from qr_banded.cu
+struct QrFwdArgs {
+    int64_t batch;
+    const double *p, *q, *r, *shift, *head, *b;
+    int hp, nb, colgrowth;
+    double tol;
+    const int64_t *woff;
+    double *work;
+    int64_t *ncols, *nconv, *nswept;
+    int32_t *status;
+};
+struct QrBwdArgs {
+    int64_t batch;
+    const int64_t *woff;
+    const double *work;
+    const int64_t *ncols, *nswept, *xoff;
+    const int32_t *status;
+    double *x;
+    int64_t xcap;
+};
+int qr_record_doubles(int l, int u, bool refl);
+int launch_qr_forward(int l, int u, const QrFwdArgs &a, bool refl, cudaStream_t s);
+int launch_qr_scan(const int64_t *d_ncols, int64_t batch, int64_t *d_xoff, cudaStream_t s);
+int launch_qr_backsolve(int l, int u, const QrBwdArgs &a, bool refl, cudaStream_t s);
+int launch_qr_export(int l, int u, int64_t batch, const int64_t *d_woff, const double *d_work, const int64_t *d_ncols,
+                     const int64_t *d_nswept, const int64_t *d_xoff, double *d_factors, double *d_tau, double *d_qtb,
+                     cudaStream_t s);
+
+// ---- per-device grow-only buffer pool (host entry points only) ---------------------------------------
+constexpr int kMaxDev = 16;
+constexpr int kSlots = 24;
+struct DevState {
+    bool init = false;
+    cudaStream_t stream = nullptr;
+    void *buf[kSlots] = {};
+    size_t cap[kSlots] = {};
+};
+static DevState g_dev[kMaxDev];
+static std::mutex g_mutex;
+
+static int dev_init(int d)
+{
+    ILA_CUDA_CHECK(cudaSetDevice(d));
+    if (!g_dev[d].init) {
+        ILA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_dev[d].stream, cudaStreamNonBlocking));
+        g_dev[d].init = true;
+    }
+    return 0;
+}
+static int dev_buf(int d, int slot, size_t bytes, void **out)
+{
+    DevState &S = g_dev[d];
+    if (bytes == 0) bytes = 8;
+    if (S.cap[slot] < bytes) {
+        if (S.buf[slot]) ILA_CUDA_CHECK(cudaFree(S.buf[slot]));
+        S.buf[slot] = nullptr;
+        S.cap[slot] = 0;
+        ILA_CUDA_CHECK(cudaMalloc(&S.buf[slot], bytes));
+        S.cap[slot] = bytes;
+    }
+    *out = S.buf[slot];
+    return 0;
+}
+template <class T>
+static int dev_buf_t(int d, int slot, size_t count, T **out)
+{
+    void *p = nullptr;
+    int rc = dev_buf(d, slot, count * sizeof(T), &p);
+    *out = static_cast<T *>(p);
+    return rc;
+}
+
+// logical shard d -> physical device: a single-GPU call runs on the CURRENT device (one process per GPU under
+// torchrun selects it with ila_set_device); a multi-GPU call uses devices 0..G-1 of this process.
+static int g_base_dev = 0;
+static inline int phys(int d, int G) { return G == 1 ? g_base_dev : d; }
+
+static int resolve_ngpus(int ngpus, int *out)
+{
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt <= 0) {
+        cudaGetLastError();
+        return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    }
+    if (cnt > kMaxDev) cnt = kMaxDev;
+    if (ngpus <= 0 || ngpus > cnt) ngpus = cnt;
+    *out = ngpus;
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = 0; }
+    g_base_dev = cur;
+    return 0;
+}
+
+// ---- FP64 peak probe ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// dependent-chain latency probe (one warp): cycles per dependent DFMA / DMUL+DADD pair / sqrt / div
+__global__ void latency_probe_kernel(double *out, double seed)
+{
+    const int iters = 4096;
+    double a = seed + threadIdx.x * 1e-9;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i++) a = fma(a, 0.999999, 1e-7);
+    long long t1 = clock64();
+    double b = a;
+    for (int i = 0; i < iters; i++) b = __dadd_rn(__dmul_rn(b, 0.999999), 1e-7);
+    long long t2 = clock64();
+    double c = fabs(b) + 2.0;
+    for (int i = 0; i < iters; i++) c = __dsqrt_rn(c) + 1.5;
+    long long t3 = clock64();
+    double d = c;
+    for (int i = 0; i < iters; i++) d = __ddiv_rn(3.0, d) + 0.5;
+    long long t4 = clock64();
+    if (threadIdx.x == 0) {
+        out[0] = (double)(t1 - t0) / iters;
+        out[1] = (double)(t2 - t1) / iters;
+        out[2] = (double)(t3 - t2) / iters;
+        out[3] = (double)(t4 - t3) / iters;
+        out[4] = a + b + c + d;
+    }
+}
+
+} // namespace ila
+
+using namespace ila;
+
+extern "C" {
+
+int ila_version(void) { return 100; }
+
+int ila_device_count(void)
+{
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return cnt;
+}
+
+const char *ila_last_error(void) { return g_last_error; }
+
+int ila_set_device(int dev)
+{
+    ILA_CUDA_CHECK(cudaSetDevice(dev));
+    return 0;
+}
+
+int ila_get_device(void)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
+
+int64_t ila_kernel_launches(void) { return g_launches.load(); }
+
+int ila_fp64_peak_probe(double *tflops_out, double *ms_out)
+{
+    int cnt = ila_device_count();
+    if (cnt <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible");
+    int dev = 0, sms = 0;
+    ILA_CUDA_CHECK(cudaGetDevice(&dev));
+    ILA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+    double *d = nullptr;
+    ILA_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    ILA_CUDA_CHECK(cudaEventCreate(&e0));
+    ILA_CUDA_CHECK(cudaEventCreate(&e1));
+    dfma_probe_kernel<<<blocks, threads>>>(d, 1 << 10);   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        ILA_CUDA_CHECK(cudaEventRecord(e0));
+        dfma_probe_kernel<<<blocks, threads>>>(d, iters);
+        ILA_CUDA_CHECK(cudaEventRecord(e1));
+        ILA_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        ILA_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    count_launch(4);
+    ILA_CUDA_CHECK(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+    if (tflops_out) *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return 0;
+}
+
+/* cycles per dependent op on one warp: out[0] DFMA, out[1] DMUL+DADD, out[2] DSQRT+DADD, out[3] DDIV+DADD */
+int ila_fp64_latency_probe(double *out4)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible");
+    double *d = nullptr;
+    ILA_CUDA_CHECK(cudaMalloc(&d, sizeof(double) * 8));
+    latency_probe_kernel<<<1, 32>>>(d, 1.0);
+    latency_probe_kernel<<<1, 32>>>(d, 1.0);
+    count_launch(2);
+    ILA_CUDA_CHECK(cudaDeviceSynchronize());
+    double h[8];
+    ILA_CUDA_CHECK(cudaMemcpy(h, d, sizeof(double) * 5, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    for (int i = 0; i < 4; i++) out4[i] = h[i];
+    return 0;
+}
+
+// ================================ K3: Toeplitz-tail QL =================================================
+
+static int ql_toeplitz_host(bool real_path, int l, int u, const double *a, const double *lambda, int64_t n,
+                            int branch_rank, double *L11, double *tail_opt, int32_t *status, int ngpus)
+{
+    if (n < 0 || !a || (n > 0 && (!lambda || !L11 || !status))) return set_error(ILA_ERR_ARG, "ql_toeplitz: null pointer / negative n");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    const int w = real_path ? 1 : 2;             // doubles per scalar
+    const int m = l + 2, tl = 2 * m + 2;
+    if (G > n) G = (int)n;
+    const int64_t per = (n + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= n ? per : n - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        double *d_lam, *d_L, *d_tail = nullptr;
+        int32_t *d_st;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt * w, &d_lam))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt * w, &d_L))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
+        if (tail_opt && (rc = dev_buf_t(pd, 3, (size_t)cnt * tl * w, &d_tail))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam, lambda + lo * w, sizeof(double) * cnt * w, cudaMemcpyHostToDevice, s));
+        if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam, cnt, d_L, d_tail, d_st, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + lo * w, d_L, sizeof(double) * cnt * w, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+        if (tail_opt)
+            ILA_CUDA_CHECK(cudaMemcpyAsync(tail_opt + lo * tl * w, d_tail, sizeof(double) * cnt * tl * w, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
+int ila_ql_toeplitz_l11_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank,
+                            ila_c64 *L11, ila_c64 *tail_opt, int32_t *status, int ngpus)
+{
+    return ql_toeplitz_host(false, l, u, (const double *)a, (const double *)lambda, n, branch_rank, (double *)L11,
+                            (double *)tail_opt, status, ngpus);
+}
+
+int ila_ql_toeplitz_l11_f64(int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank,
+                            double *L11, double *tail_opt, int32_t *status, int ngpus)
+{
+    return ql_toeplitz_host(true, l, u, a, lambda, n, branch_rank, L11, tail_opt, status, ngpus);
+}
+
+int ila_ql_toeplitz_l11_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d_lambda, int64_t n, int branch_rank,
+                                ila_c64 *d_L11, ila_c64 *d_tail_opt, int32_t *d_status, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    return launch_ql_toeplitz(false, l, u, (const double *)a, branch_rank, (const double *)d_lambda, n, (double *)d_L11,
+                              (double *)d_tail_opt, d_status, (cudaStream_t)stream);
+}
+
+int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank,
+                                double *d_L11, double *d_tail_opt, int32_t *d_status, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    return launch_ql_toeplitz(true, l, u, a, branch_rank, d_lambda, n, d_L11, d_tail_opt, d_status, (cudaStream_t)stream);
+}
+
+// ================================ K1+K2: adaptive banded QR solve =======================================
+
+int ila_qr_banded_work_offsets(int64_t batch, int64_t ncap, const int64_t *ncap_per, int64_t *woff_host)
+{
+    if (batch < 0 || !woff_host) return set_error(ILA_ERR_ARG, "qr_banded_work_offsets: bad arguments");
+    int64_t acc = 0;
+    for (int64_t i = 0; i < batch; i++) {
+        woff_host[i] = acc;
+        int64_t c = ncap_per ? ncap_per[i] : ncap;
+        if (c < 0) c = 0;
+        acc += (c + 3) & ~(int64_t)3;   // keep every instance's records 32 B aligned
+    }
+    woff_host[batch] = acc;
+    return 0;
+}
+
+int64_t ila_qr_banded_work_bytes(int l, int u, int64_t batch, int64_t ncap, const int64_t *ncap_per)
+{
+    int64_t acc = 0;
+    for (int64_t i = 0; i < batch; i++) {
+        int64_t c = ncap_per ? ncap_per[i] : ncap;
+        if (c < 0) c = 0;
+        acc += (c + 3) & ~(int64_t)3;
+    }
+    // sized for the widest record (with reflectors) so one buffer serves both modes
+    return acc * (int64_t)sizeof(double) * qr_record_doubles(l, u, true);
+}
+
+int ila_qr_banded_factor_f64_dev(int l, int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                 const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
+                                 double tol, int colgrowth, const int64_t *d_woff, double *d_work, int64_t *d_ncols,
+                                 int64_t *d_nconv, int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status,
+                                 int want_reflectors, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0) return set_error(ILA_ERR_ARG, "qr_banded: bad sizes");
+    QrFwdArgs a{batch, d_p, d_q, d_r, d_shift, d_head, d_b, hp, nb, colgrowth, tol, d_woff, d_work, d_ncols, d_nconv, d_nswept, d_status};
+    int rc = launch_qr_forward(l, u, a, want_reflectors != 0, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_qr_scan(d_ncols, batch, d_xoff, (cudaStream_t)stream);
+}
+
+int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *d_woff, const double *d_work,
+                                    const int64_t *d_ncols, const int64_t *d_nswept, const int64_t *d_xoff,
+                                    const int32_t *d_status, double *d_x, int64_t xcap, int want_reflectors, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    QrBwdArgs a{batch, d_woff, d_work, d_ncols, d_nswept, d_xoff, d_status, d_x, xcap};
+    return launch_qr_backsolve(l, u, a, want_reflectors != 0, (cudaStream_t)stream);
+}
+
+int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const double *q, const double *r,
+                            const double *shift, int hp, const double *head, int nb, const double *b, double tol,
+                            int colgrowth, int64_t ncap, const int64_t *ncap_per, double *x, int64_t xcap,
+                            int64_t *xoff, int64_t *ncols, int64_t *nconv, double *factors_opt, double *tau_opt,
+                            double *qtb_opt, int32_t *status, int ngpus)
+{
+    if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0 || !p || !q || !b || !xoff || !ncols || !nconv || !status || (hp > 0 && !head))
+        return set_error(ILA_ERR_ARG, "qr_banded_solve: bad arguments");
+    if (l < 1) return set_error(ILA_ERR_UNSUPPORTED, "qr_banded_solve: l == 0 (triangular operator, Q = I) is not on the accelerated path");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (batch == 0) { xoff[0] = 0; return 0; }
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int nd = l + u + 1, LD = 2 * l + u + 1;
+    const bool refl = factors_opt || tau_opt;
+    const int REC = qr_record_doubles(l, u, refl);
+
+    // round-robin sharding: instance i -> device i % G, local index i / G
+    struct Shard {
+        int64_t cnt = 0;
+        std::vector<double> p, q, r, shift, b;
+        std::vector<int64_t> woff, ncols, nconv, nswept, xoff;
+        std::vector<int32_t> status;
+        double *d_p, *d_q, *d_r, *d_shift, *d_head, *d_b, *d_work, *d_x, *d_fac, *d_tau, *d_qtb;
+        int64_t *d_woff, *d_ncols, *d_nconv, *d_nswept, *d_xoff;
+        int32_t *d_status;
+        int64_t total = 0;
+    };
+    std::vector<Shard> sh(G);
+    for (int d = 0; d < G; d++) {
+        Shard &S = sh[d];
+        S.cnt = (batch - d + G - 1) / G;
+        S.p.resize(S.cnt * nd); S.q.resize(S.cnt * nd); S.b.resize(S.cnt * nb);
+        if (r) S.r.resize(S.cnt * nd);
+        if (shift) S.shift.resize(S.cnt);
+        std::vector<int64_t> caps(S.cnt);
+        for (int64_t j = 0; j < S.cnt; j++) {
+            const int64_t i = j * G + d;
+            memcpy(&S.p[j * nd], p + i * nd, sizeof(double) * nd);
+            memcpy(&S.q[j * nd], q + i * nd, sizeof(double) * nd);
+            if (r) memcpy(&S.r[j * nd], r + i * nd, sizeof(double) * nd);
+            if (shift) S.shift[j] = shift[i];
+            memcpy(&S.b[j * nb], b + i * nb, sizeof(double) * nb);
+            caps[j] = ncap_per ? ncap_per[i] : ncap;
+        }
+        S.woff.resize(S.cnt + 1);
+        ila_qr_banded_work_offsets(S.cnt, 0, caps.data(), S.woff.data());
+        S.ncols.resize(S.cnt); S.nconv.resize(S.cnt); S.nswept.resize(S.cnt); S.status.resize(S.cnt); S.xoff.resize(S.cnt + 1);
+    }
+    // phase 1 on every device
+    for (int d = 0; d < G; d++) {
+        Shard &S = sh[d];
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        if ((rc = dev_buf_t(pd, 4, S.p.size(), &S.d_p))) return rc;
+        if ((rc = dev_buf_t(pd, 5, S.q.size(), &S.d_q))) return rc;
+        S.d_r = nullptr; S.d_shift = nullptr; S.d_head = nullptr;
+        if (r && (rc = dev_buf_t(pd, 6, S.r.size(), &S.d_r))) return rc;
+        if (shift && (rc = dev_buf_t(pd, 7, S.shift.size(), &S.d_shift))) return rc;
+        if (hp > 0 && (rc = dev_buf_t(pd, 8, (size_t)nd * hp, &S.d_head))) return rc;
+        if ((rc = dev_buf_t(pd, 9, S.b.size(), &S.d_b))) return rc;
+        if ((rc = dev_buf_t(pd, 10, (size_t)S.cnt + 1, &S.d_woff))) return rc;
+        if ((rc = dev_buf_t(pd, 11, (size_t)S.cnt, &S.d_ncols))) return rc;
+        if ((rc = dev_buf_t(pd, 12, (size_t)S.cnt, &S.d_nconv))) return rc;
+        if ((rc = dev_buf_t(pd, 13, (size_t)S.cnt, &S.d_nswept))) return rc;
+        if ((rc = dev_buf_t(pd, 14, (size_t)S.cnt + 1, &S.d_xoff))) return rc;
+        if ((rc = dev_buf_t(pd, 15, (size_t)S.cnt, &S.d_status))) return rc;
+        if ((rc = dev_buf_t(pd, 16, (size_t)S.woff[S.cnt] * REC, &S.d_work))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_p, S.p.data(), sizeof(double) * S.p.size(), cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_q, S.q.data(), sizeof(double) * S.q.size(), cudaMemcpyHostToDevice, s));
+        if (r) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_r, S.r.data(), sizeof(double) * S.r.size(), cudaMemcpyHostToDevice, s));
+        if (shift) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_shift, S.shift.data(), sizeof(double) * S.shift.size(), cudaMemcpyHostToDevice, s));
+        if (hp > 0) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_head, head, sizeof(double) * nd * hp, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_b, S.b.data(), sizeof(double) * S.b.size(), cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_woff, S.woff.data(), sizeof(int64_t) * (S.cnt + 1), cudaMemcpyHostToDevice, s));
+        rc = ila_qr_banded_factor_f64_dev(l, u, S.cnt, S.d_p, S.d_q, S.d_r, S.d_shift, hp, S.d_head, nb, S.d_b, tol, colgrowth,
+                                          S.d_woff, S.d_work, S.d_ncols, S.d_nconv, S.d_nswept, S.d_xoff, S.d_status, refl, s);
+        if (rc) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.ncols.data(), S.d_ncols, sizeof(int64_t) * S.cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.nconv.data(), S.d_nconv, sizeof(int64_t) * S.cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.status.data(), S.d_status, sizeof(int32_t) * S.cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.xoff.data(), S.d_xoff, sizeof(int64_t) * (S.cnt + 1), cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        ILA_CUDA_CHECK(cudaSetDevice(phys(d, G)));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[phys(d, G)].stream));
+    }
+    // the one host round trip per call (not per column): sizes of the ragged result
+    int64_t acc = 0;
+    for (int64_t i = 0; i < batch; i++) {
+        const Shard &S = sh[i % G];
+        const int64_t j = i / G;
+        xoff[i] = acc;
+        ncols[i] = S.ncols[j];
+        nconv[i] = S.nconv[j];
+        status[i] = S.status[j];
+        acc += S.ncols[j];
+    }
+    xoff[batch] = acc;
+    if (acc > xcap || !x) {
+        ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+        return set_error(ILA_ERR_CAPACITY, "qr_banded_solve: x capacity too small; xoff[batch] holds the required number of doubles");
+    }
+    // phase 2
+    for (int d = 0; d < G; d++) {
+        Shard &S = sh[d];
+        const int pd = phys(d, G);
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        cudaStream_t s = g_dev[pd].stream;
+        S.total = S.xoff[S.cnt];
+        if ((rc = dev_buf_t(pd, 17, (size_t)S.total, &S.d_x))) return rc;
+        rc = ila_qr_banded_backsolve_f64_dev(l, u, S.cnt, S.d_woff, S.d_work, S.d_ncols, S.d_nswept, S.d_xoff, S.d_status, S.d_x,
+                                             S.total, refl, s);
+        if (rc) return rc;
+        S.d_fac = S.d_tau = S.d_qtb = nullptr;
+        if (refl || qtb_opt) {
+            if (factors_opt) {
+                if ((rc = dev_buf_t(pd, 18, (size_t)S.total * LD, &S.d_fac))) return rc;
+                ILA_CUDA_CHECK(cudaMemsetAsync(S.d_fac, 0, sizeof(double) * S.total * LD, s));
+            }
+            if (tau_opt && (rc = dev_buf_t(pd, 19, (size_t)S.total, &S.d_tau))) return rc;
+            if (qtb_opt && (rc = dev_buf_t(pd, 20, (size_t)S.total, &S.d_qtb))) return rc;
+            if (refl) {
+                if ((rc = launch_qr_export(l, u, S.cnt, S.d_woff, S.d_work, S.d_ncols, S.d_nswept, S.d_xoff, S.d_fac, S.d_tau, S.d_qtb, s))) return rc;
+            } else {
+                return set_error(ILA_ERR_UNSUPPORTED, "qr_banded_solve: qtb_opt requires factors_opt or tau_opt");
+            }
+        }
+        if (G == 1) {
+            ILA_CUDA_CHECK(cudaMemcpyAsync(x, S.d_x, sizeof(double) * S.total, cudaMemcpyDeviceToHost, s));
+            if (factors_opt) ILA_CUDA_CHECK(cudaMemcpyAsync(factors_opt, S.d_fac, sizeof(double) * S.total * LD, cudaMemcpyDeviceToHost, s));
+            if (tau_opt) ILA_CUDA_CHECK(cudaMemcpyAsync(tau_opt, S.d_tau, sizeof(double) * S.total, cudaMemcpyDeviceToHost, s));
+            if (qtb_opt) ILA_CUDA_CHECK(cudaMemcpyAsync(qtb_opt, S.d_qtb, sizeof(double) * S.total, cudaMemcpyDeviceToHost, s));
+        } else {
+            for (int64_t j = 0; j < S.cnt; j++) {
+                const int64_t i = j * G + d, nn = S.ncols[j];
+                if (nn <= 0) continue;
+                ILA_CUDA_CHECK(cudaMemcpyAsync(x + xoff[i], S.d_x + S.xoff[j], sizeof(double) * nn, cudaMemcpyDeviceToHost, s));
+                if (factors_opt) ILA_CUDA_CHECK(cudaMemcpyAsync(factors_opt + xoff[i] * LD, S.d_fac + S.xoff[j] * LD, sizeof(double) * nn * LD, cudaMemcpyDeviceToHost, s));
+                if (tau_opt) ILA_CUDA_CHECK(cudaMemcpyAsync(tau_opt + xoff[i], S.d_tau + S.xoff[j], sizeof(double) * nn, cudaMemcpyDeviceToHost, s));
+                if (qtb_opt) ILA_CUDA_CHECK(cudaMemcpyAsync(qtb_opt + xoff[i], S.d_qtb + S.xoff[j], sizeof(double) * nn, cudaMemcpyDeviceToHost, s));
+            }
+        }
+    }
+    for (int d = 0; d < G; d++) {
+        ILA_CUDA_CHECK(cudaSetDevice(phys(d, G)));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[phys(d, G)].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
+} // extern "C"

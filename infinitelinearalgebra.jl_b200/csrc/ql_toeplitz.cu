@@ -1,0 +1,354 @@
+// ql_toeplitz.cu — K3: Toeplitz-tail QL for Hessenberg (u == 1) Toeplitz symbols, one thread per shift λ.
+//
+// Reference path replaced (InfiniteLinearAlgebra.jl v0.10.3):
+//   ql(A - λ*I)  ->  _inf_ql              src/banded/infqltoeplitz.jl:182-191
+//                ->  ql_hessenberg         src/banded/infqltoeplitz.jl:56-65
+//                      tail_de             src/banded/infqltoeplitz.jl:7-27   (companion eigenproblem -> (d,e))
+//                      ql_X!               src/banded/infqltoeplitz.jl:31-39  (2 x m Householder QL + sign fix)
+//   .L[1,1]      ->  factors[1,1] = X[1,m-1]   src/infql.jl:96, infqltoeplitz.jl:63
+//
+// B200-first design (not a translation): the reference builds the (m-1)x(m-1) companion matrix and calls
+// LAPACK geevx for ALL eigenpairs, then keeps one.  Here each thread keeps the m coefficients in registers,
+// normalises the characteristic polynomial by the super-diagonal coefficient β (w = μ/β, so that
+// "QL exists" <=> |w| >= 1), finds all roots simultaneously with a Gauss–Seidel Aberth–Ehrlich iteration
+// (cubic convergence, one complex division per root per sweep), selects the branch, and recovers the
+// eigenvector in closed form from the companion structure (V_1 = 1, V_{i+1} = g_i - w V_i).
+// Everything is FP64/ComplexF64 on the CUDA cores; 36 B of HBM traffic per shift, so the kernel is FP64-pipe bound.
+#include "ila_common.cuh"
+
+namespace ila {
+
+constexpr int kMaxDeg = 8;   // l + 1 <= 8
+constexpr int kAberthMaxIt = 48;
+
+template <int N>
+struct TzParams {
+    cplx a[N + 1];     // reversed data column: a[0] = a_{-l}, ..., a[N-1] = a_0, a[N] = a_{+1} = β
+    cplx ginv;         // 1/β
+    cplx unit[N];      // initial directions exp(i(θ0 + 2πj/N))
+    double beta2;      // |β|^2
+    int branch_rank;
+};
+
+__device__ __forceinline__ double dsign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
+
+// Horner: P(w) and P'(w) for the monic polynomial with coefficients cf[1..N]
+template <int N>
+__device__ __forceinline__ void horner2(const cplx (&cf)[N + 1], cplx w, cplx &pv, cplx &dv)
+{
+    pv = mk(1.0, 0.0);
+    dv = mk(0.0, 0.0);
+#pragma unroll
+    for (int k = 1; k <= N; k++) {
+        dv = dv * w + pv;
+        pv = pv * w + cf[k];
+    }
+}
+
+template <int N, bool REAL_PATH, bool WANT_TAIL>
+__global__ void __launch_bounds__(128)
+ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t n, double *__restrict__ L11,
+                       double *__restrict__ tail, int32_t *__restrict__ status)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    constexpr int M = N + 1;   // number of symbol coefficients (reference's m)
+
+    cplx lam;
+    if (REAL_PATH) {
+        lam = mk(lambda[idx], 0.0);
+    } else {
+        const double2 t = reinterpret_cast<const double2 *>(lambda)[idx];
+        lam = mk(t.x, t.y);
+    }
+    // A - λI: only the diagonal coefficient moves (InfToeplitz - UniformScaling)
+    const cplx adiag = P.a[N - 1] - lam;
+
+    // normalised symbol coefficients g_k = a_{m-k}/β, k = 1..N  (c_k of SURVEY A.2 divided by β)
+    cplx g[N + 1];
+    g[0] = mk(1.0, 0.0);
+    g[1] = adiag * P.ginv;
+#pragma unroll
+    for (int k = 2; k <= N; k++) g[k] = P.a[N - k] * P.ginv;
+    // monic characteristic polynomial of C/β:  P(w) = sum_k (-1)^k g_k w^{N-k}
+    cplx cf[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; k++) cf[k] = (k & 1) ? -g[k] : g[k];
+
+    // ---- initial guesses: circle around the centroid with the geometric-mean radius |P(c)|^(1/N)
+    cplx w[N];
+    {
+        const cplx c = (1.0 / N) * g[1];
+        cplx pc, dc;
+        horner2<N>(cf, c, pc, dc);
+        double rad;   // |P(c)|^(1/N)
+        if (N == 2) rad = sqrt(sqrt(abs2(pc)));
+        else if (N == 4) rad = sqrt(sqrt(sqrt(abs2(pc))));
+        else if (N == 8) rad = sqrt(sqrt(sqrt(sqrt(abs2(pc)))));
+        else rad = pow(abs2(pc), 0.5 / N);
+        if (!(rad > 1e-8)) {
+            double mx = 0.0;
+#pragma unroll
+            for (int k = 1; k <= N; k++) mx = fmax(mx, abs2(g[k]));
+            rad = 1.0 + sqrt(mx);
+        }
+#pragma unroll
+        for (int j = 0; j < N; j++) w[j] = c + rad * P.unit[j];
+    }
+
+    // ---- Aberth–Ehrlich, Gauss–Seidel sweeps
+    for (int it = 0; it < kAberthMaxIt; it++) {
+        bool done = true;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            cplx pv, dv;
+            horner2<N>(cf, w[j], pv, dv);
+            // sum_k 1/(w_j - w_k) kept as num/den to spend a single division per root
+            cplx num = mk(0.0, 0.0), den = mk(1.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                if (k == j) continue;
+                const cplx d = w[j] - w[k];
+                num = num * d + den;
+                den = den * d;
+            }
+            const cplx top = pv * den;
+            const cplx bot = dv * den - pv * num;
+            const double b2 = abs2(bot);
+            cplx corr = mk(0.0, 0.0);
+            if (b2 > 0.0) corr = (1.0 / b2) * (top * conj(bot));
+            w[j] = w[j] - corr;
+            if (abs2(corr) > 1e-18 * abs2(w[j])) done = false;
+        }
+        if (done) break;
+    }
+
+    // ---- branch selection on |μ|^2 = |β w|^2 (findmax / k-th largest; ties: Julia's (re, im) eigenvalue order)
+    int jsel = 0;
+    {
+        double n2[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) n2[j] = abs2(w[j]);
+        int want = P.branch_rank - 1;   // number of roots strictly "larger" than the selected one
+        if (want < 0) want = 0;
+        if (want > N - 1) want = N - 1;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            int larger = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                if (k == j) continue;
+                const cplx mj = w[j] , mk_ = w[k];
+                bool gt = n2[k] > n2[j];
+                if (n2[k] == n2[j]) {
+                    // tie: the reference keeps the first maximum in (real, imag)-sorted order
+                    gt = (mk_.re < mj.re) || (mk_.re == mj.re && mk_.im < mj.im) || (mk_.re == mj.re && mk_.im == mj.im && k < j);
+                }
+                larger += gt ? 1 : 0;
+            }
+            if (larger == want) jsel = j;
+        }
+    }
+    cplx ws = w[0];
+#pragma unroll
+    for (int j = 1; j < N; j++)
+        if (j == jsel) ws = w[j];
+
+    int32_t st = ILA_OK;
+    if (REAL_PATH) {
+        // isreal(λ[j]) (infqltoeplitz.jl:12): a complex-conjugate pair cannot be a real root
+        if (!(fabs(ws.im) <= 1e-9 * fabs(ws.re))) st = ILA_NOT_REAL;
+        ws.im = 0.0;
+    }
+    // one Newton polish of the selected root (the last Aberth correction already is one; this removes
+    // any dependence on the other iterates)
+    {
+        cplx pv, dv;
+        horner2<N>(cf, ws, pv, dv);
+        const double d2 = abs2(dv);
+        if (d2 > 0.0) {
+            cplx corr = (1.0 / d2) * (pv * conj(dv));
+            if (REAL_PATH) corr.im = 0.0;
+            if (abs2(corr) < 1e-6 * abs2(ws)) ws = ws - corr;
+        }
+    }
+
+    // μ = β w ; n2 = |μ|^2 ; existence test n2 >= |β|^2 (infqltoeplitz.jl:13,23)
+    const cplx beta = P.a[N];
+    const cplx mu = beta * ws;
+    const double n2 = abs2(mu);
+    if (st == ILA_OK && !(n2 >= P.beta2)) st = ILA_NO_QL;
+
+    // eigenvector of the companion matrix in closed form (V_1 = 1): V_{i+1} = g_i - w V_i
+    cplx V[N];
+    V[0] = mk(1.0, 0.0);
+#pragma unroll
+    for (int i = 1; i < N; i++) V[i] = g[i] - ws * V[i - 1];
+
+    // de = c_sgn c_abs V[end:-1:1]; with V_1 = 1 the reference's c_sgn is exactly -1 (complex branch,
+    // infqltoeplitz.jl:24-26, since V_1 a_{m-1} - V_2 a_m = μ V_1).  Real branch: see below.
+    const double c_abs = sqrt(n2 - P.beta2);
+
+    // X = [a^T; 0 de^T]  (2 x m)
+    cplx X1[M], X2[M];
+#pragma unroll
+    for (int j = 0; j < M; j++) X1[j] = P.a[j];
+    X1[N - 1] = adiag;
+    X2[0] = mk(0.0, 0.0);
+#pragma unroll
+    for (int k = 1; k <= N; k++) X2[k] = (-c_abs) * V[N - k];
+
+    // ---- ql_X! : k = 2 reflector on (X[2,m], X[1,m]) applied to columns 1..m-1
+    cplx tau1 = mk(0.0, 0.0), tau2 = mk(0.0, 0.0);
+    {
+        cplx xi1 = X2[N];
+        const double normu = sqrt(abs2(X2[N]) + abs2(X1[N]));
+        if (normu != 0.0) {
+            const double nu = copysign(normu, xi1.re);
+            xi1.re += nu;
+            X2[N] = mk(-nu, 0.0);
+            X1[N] = X1[N] / xi1;
+            tau2 = xi1 / nu;
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                cplx vA = X2[j] + conj(X1[N]) * X1[j];
+                vA = conj(tau2) * vA;
+                X2[j] = X2[j] - vA;
+                X1[j] = X1[j] - X1[N] * vA;
+            }
+        }
+    }
+    double s;   // sign(real(X[2,end])) taken BEFORE ql! in the reference
+    if (REAL_PATH) {
+        // T<:Real (infqltoeplitz.jl:7-16): de = c * real(V[end:-1:1, j]) with LAPACK's eigenvector sign.  Row 1 of X
+        // after the reflector does not depend on that sign, row 2 flips with it; the sign LAPACK returns in every
+        // case the reference tests (test_infql.jl:12-19) is the one for which ql_X! needs no flip, i.e.
+        // sign(de[end]) == sign(X[1,m-1]).  We pick that sign.
+        double t = dsign(X1[N - 1].re);
+        if (t == 0.0) t = 1.0;
+        // X2 was built with sign -1: de_N = -c_abs.  Flip row 2 when t = +1.
+        if (t > 0.0) {
+#pragma unroll
+            for (int j = 0; j < M; j++) X2[j] = -X2[j];
+            X1[N] = -X1[N];   // v = X[1,m]/(ξ1+ν) flips with ξ1, ν
+        }
+        s = (c_abs == 0.0) ? 0.0 : t;
+        // real eltype: ql! skips k = 1 (the (T<:Real) lower bound, examples/jacobi.jl:63)
+    } else {
+        s = dsign(-c_abs);
+        // k = 1 (complex only): length-1 reflector making X[1,m-1] real
+        cplx xi1 = X1[N - 1];
+        const double normu = sqrt(abs2(xi1));
+        if (normu != 0.0) {
+            const double nu = copysign(normu, xi1.re);
+            xi1.re += nu;
+            X1[N - 1] = mk(-nu, 0.0);
+            tau1 = xi1 / nu;
+#pragma unroll
+            for (int j = 0; j < N - 1; j++) X1[j] = X1[j] - conj(tau1) * X1[j];
+        }
+    }
+    // sign normalisation (infqltoeplitz.jl:34-37)
+    if (s != dsign(X1[N - 1].re)) {
+        tau1 = mk(2.0, 0.0) - tau1;
+#pragma unroll
+        for (int j = 0; j < N; j++) X1[j] = -X1[j];
+    }
+
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (st != ILA_OK) {
+#pragma unroll
+        for (int j = 0; j < M; j++) { X1[j] = mk(qnan, qnan); X2[j] = mk(qnan, qnan); }
+        tau1 = tau2 = mk(qnan, qnan);
+    }
+    status[idx] = st;
+    if (REAL_PATH) {
+        L11[idx] = X1[N - 1].re;
+        if (WANT_TAIL) {
+            double *t = tail + idx * (2 * M + 2);
+#pragma unroll
+            for (int j = 0; j < M; j++) { t[j] = X1[j].re; t[M + j] = X2[j].re; }
+            t[2 * M] = tau1.re;
+            t[2 * M + 1] = tau2.re;
+        }
+    } else {
+        reinterpret_cast<double2 *>(L11)[idx] = make_double2(X1[N - 1].re, st == ILA_OK ? X1[N - 1].im : qnan);
+        if (WANT_TAIL) {
+            double2 *t = reinterpret_cast<double2 *>(tail) + idx * (2 * M + 2);
+#pragma unroll
+            for (int j = 0; j < M; j++) {
+                t[j] = make_double2(X1[j].re, X1[j].im);
+                t[M + j] = make_double2(X2[j].re, X2[j].im);
+            }
+            t[2 * M] = make_double2(tau1.re, tau1.im);
+            t[2 * M + 1] = make_double2(tau2.re, tau2.im);
+        }
+    }
+}
+
+// ---- host-side launcher -------------------------------------------------------------------------
+template <int N, bool REAL_PATH>
+static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, int64_t n, double *d_L11,
+                    double *d_tail, int32_t *d_status, cudaStream_t stream)
+{
+    TzParams<N> P;
+    for (int j = 0; j <= N; j++) P.a[j] = a_rev[j];
+    const cplx beta = a_rev[N];
+    const double b2 = beta.re * beta.re + beta.im * beta.im;
+    P.ginv = cplx{beta.re / b2, -beta.im / b2};
+    P.beta2 = b2;
+    P.branch_rank = branch_rank;
+    const double theta0 = 0.7;   // asymmetric start: a conjugate-symmetric start cannot split real root pairs
+    for (int j = 0; j < N; j++) {
+        const double th = theta0 + 2.0 * 3.14159265358979323846 * j / N;
+        P.unit[j] = cplx{cos(th), sin(th)};
+    }
+    if (n <= 0) return 0;
+    const int threads = 128;
+    const int64_t blocks = (n + threads - 1) / threads;
+    if (d_tail)
+        ql_toeplitz_l11_kernel<N, REAL_PATH, true><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, d_L11, d_tail, d_status);
+    else
+        ql_toeplitz_l11_kernel<N, REAL_PATH, false><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, d_L11, d_tail, d_status);
+    count_launch();
+    ILA_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+template <bool REAL_PATH>
+static int launch_any(int l, const cplx *a_rev, int branch_rank, const double *d_lambda, int64_t n, double *d_L11,
+                      double *d_tail, int32_t *d_status, cudaStream_t stream)
+{
+    switch (l + 1) {
+    case 2: return launch_n<2, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+    case 3: return launch_n<3, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+    case 4: return launch_n<4, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+    case 5: return launch_n<5, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+    case 6: return launch_n<6, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+    case 7: return launch_n<7, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+    case 8: return launch_n<8, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+    default: return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz: lower bandwidth l must be in 1..7");
+    }
+}
+
+// Exposed to api.cu.  `a` is in BandedMatrices data-column order (a_{+1}, a_0, ..., a_{-l}); `reverse` (infqltoeplitz.jl:59)
+// is done here.
+int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
+                       int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream)
+{
+    if (u != 1) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz: only u == 1 (Hessenberg) symbols are supported (ql_pruneband is undefined upstream)");
+    if (l < 1 || l + 1 > kMaxDeg) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz: lower bandwidth l must be in 1..7");
+    if (branch_rank < 1 || branch_rank > l + 1) return set_error(ILA_ERR_ARG, "ql_toeplitz: branch_rank out of range");
+    const int m = l + 2;
+    cplx a_rev[kMaxDeg + 1];
+    for (int j = 0; j < m; j++) {
+        const int src = m - 1 - j;
+        a_rev[j] = real_path ? cplx{a_host[src], 0.0} : cplx{a_host[2 * src], a_host[2 * src + 1]};
+    }
+    if (a_rev[m - 1].re == 0.0 && a_rev[m - 1].im == 0.0)
+        return set_error(ILA_ERR_ARG, "ql_toeplitz: super-diagonal coefficient is zero (u would be 0)");
+    return real_path ? launch_any<true>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream)
+                     : launch_any<false>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+}
+
+} // namespace ila

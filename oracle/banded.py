@@ -1,0 +1,143 @@
+"""ctypes front-end of the C oracle (oracle/ila_oracle.c) — TEST INFRASTRUCTURE ONLY.
+
+Adaptive banded QR solve (reference src/infqr.jl:8-13,32-48,236-274,350-355) and adaptive banded
+Cholesky solve (src/infcholesky.jl:42-59,94-140), restated in plain C with the reference's operation
+order.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libila_oracle.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int64)
+_sp = C.POINTER(C.c_int32)
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the recipe in oracle/Makefile."""
+    src = [os.path.join(_HERE, f) for f in ("ila_oracle.c", "ila_oracle_impl.h", "Makefile")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def _ptr(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def _prep_op(nd, batch, p, q, r, shift, head):
+    p = np.ascontiguousarray(np.broadcast_to(np.asarray(p, dtype=np.float64), (batch, nd)))
+    q = np.ascontiguousarray(np.broadcast_to(np.asarray(q, dtype=np.float64), (batch, nd)))
+    r = None if r is None else np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64), (batch, nd)))
+    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=np.float64), (batch,)))
+    hp = 0
+    if head is not None:
+        head = np.ascontiguousarray(np.asarray(head, dtype=np.float64))
+        assert head.shape[0] == nd
+        hp = head.shape[1]
+    return p, q, r, shift, hp, head
+
+
+def qr_banded_solve(l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=np.finfo(np.float64).tiny,
+                    colgrowth=1000, ncap=200_000, batch=None, want_factors=False, quad=False, nthreads=0):
+    """Batched adaptive QR solve through the oracle; returns dict(x, ncols, nconv, status[, factors, tau, qtb])."""
+    nd = l + u + 1
+    if batch is None:
+        batch = int(np.asarray(p).reshape(-1, nd).shape[0])
+    p, q, r, shift, hp, head = _prep_op(nd, batch, p, q, r, shift, head)
+    b = np.asarray(b, dtype=np.float64)
+    if b.ndim == 1:
+        b = np.broadcast_to(b, (batch, b.shape[0]))
+    b = np.ascontiguousarray(b)
+    nb = b.shape[1]
+    ldx = ncap
+    x = np.zeros((batch, ldx))
+    ncols = np.zeros(batch, dtype=np.int64)
+    nconv = np.zeros(batch, dtype=np.int64)
+    status = np.zeros(batch, dtype=np.int32)
+    out = dict(x=x, ncols=ncols, nconv=nconv, status=status)
+    L = lib()
+    if quad:
+        L.ila_oracle_qr_banded_solve_f128(
+            C.c_int(l), C.c_int(u), C.c_int64(batch), _ptr(p, _dp), _ptr(q, _dp), _ptr(r, _dp), _ptr(shift, _dp),
+            C.c_int(hp), _ptr(head, _dp), C.c_int(nb), _ptr(b, _dp), C.c_double(tol), C.c_int(colgrowth),
+            C.c_int64(ncap), C.c_int64(ldx), _ptr(x, _dp), _ptr(ncols, _ip), _ptr(nconv, _ip), _ptr(status, _sp),
+            C.c_int(nthreads))
+        return out
+    fac = tau = qtb = None
+    if want_factors:
+        fac = np.zeros((batch, ldx, 2 * l + u + 1))
+        tau = np.zeros((batch, ldx))
+        qtb = np.zeros((batch, ldx))
+        out.update(factors=fac, tau=tau, qtb=qtb)
+    L.ila_oracle_qr_banded_solve_f64(
+        C.c_int(l), C.c_int(u), C.c_int64(batch), _ptr(p, _dp), _ptr(q, _dp), _ptr(r, _dp), _ptr(shift, _dp),
+        C.c_int(hp), _ptr(head, _dp), C.c_int(nb), _ptr(b, _dp), C.c_double(tol), C.c_int(colgrowth),
+        C.c_int64(ncap), C.c_int64(ldx), _ptr(x, _dp), _ptr(ncols, _ip), _ptr(nconv, _ip), _ptr(fac, _dp),
+        _ptr(tau, _dp), _ptr(qtb, _dp), _ptr(status, _sp), C.c_int(nthreads))
+    return out
+
+
+def chol_banded_solve(u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=np.finfo(np.float64).tiny,
+                      colgrowth=1000, ncap=20_000, batch=None, want_factors=False, nthreads=0):
+    """Batched adaptive Cholesky solve through the oracle (upper bands, data-row order +u … 0)."""
+    nd = u + 1
+    if batch is None:
+        batch = int(np.asarray(p).reshape(-1, nd).shape[0])
+    p, q, r, shift, hp, head = _prep_op(nd, batch, p, q, r, shift, head)
+    b = np.asarray(b, dtype=np.float64)
+    if b.ndim == 1:
+        b = np.broadcast_to(b, (batch, b.shape[0]))
+    b = np.ascontiguousarray(b)
+    nb = b.shape[1]
+    ldx = ncap
+    x = np.zeros((batch, ldx))
+    ncols = np.zeros(batch, dtype=np.int64)
+    nconv = np.zeros(batch, dtype=np.int64)
+    status = np.zeros(batch, dtype=np.int32)
+    out = dict(x=x, ncols=ncols, nconv=nconv, status=status)
+    fac = y = None
+    if want_factors:
+        fac = np.zeros((batch, ldx, u + 1))
+        y = np.zeros((batch, ldx))
+        out.update(factors=fac, y=y)
+    lib().ila_oracle_chol_banded_solve_f64(
+        C.c_int(u), C.c_int64(batch), _ptr(p, _dp), _ptr(q, _dp), _ptr(r, _dp), _ptr(shift, _dp), C.c_int(hp),
+        _ptr(head, _dp), C.c_int(nb), _ptr(b, _dp), C.c_double(tol), C.c_int(colgrowth), C.c_int64(ncap),
+        C.c_int64(ldx), _ptr(x, _dp), _ptr(ncols, _ip), _ptr(nconv, _ip), _ptr(fac, _dp), _ptr(y, _dp),
+        _ptr(status, _sp), C.c_int(nthreads))
+    return out
+
+
+def num_threads() -> int:
+    return int(lib().ila_oracle_num_threads())
+
+
+# -- operator descriptions of the reference's fixtures --------------------------------------------
+
+def bessel_operator(z):
+    """A = BandedMatrix(0 => -2*(0:∞)/z, 1 => Ones(∞), -1 => Ones(∞)) (README.md:41, test_infqr.jl:95).
+    Rows of (p,q,r) follow BandedMatrices data-row order: diagonal +1, 0, -1."""
+    z = np.atleast_1d(np.asarray(z, dtype=np.float64))
+    batch = z.shape[0]
+    p = np.tile(np.array([1.0, 0.0, 1.0]), (batch, 1))
+    q = np.tile(np.array([0.0, -2.0, 0.0]), (batch, 1))
+    r = np.ones((batch, 3))
+    r[:, 1] = z
+    return p, q, r

@@ -1,0 +1,270 @@
+"""CPU oracle for the Toeplitz-tail QL (TEST INFRASTRUCTURE — never imported by the product path).
+
+numpy restatement of the reference's `tail_de`, `ql_X!` and `ql_hessenberg(::InfToeplitz)`
+(reference: src/banded/infqltoeplitz.jl:7-65) plus the perturbed-Toeplitz head
+`ql_hessenberg!` (src/infql.jl:60-93).  The eigen-decomposition goes through
+`numpy.linalg.eig`, i.e. LAPACK `?geev` — the same routine family Julia's `eigen`
+(`geevx`) reaches — and mirrors Julia's default `sortby` ordering of the eigenvalues
+(lexicographic on (real, imag)) before `branch` is applied.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline legs may import this.
+
+Parity status: pinned by the reference's known answers for this path
+(test/test_reduceql.jl:41-45 constants, test/test_infql.jl:12-67 reconstruction identities,
+test/test_infql.jl:147-153 `(Q'b)[1]`) — see tests/test_oracle_toeplitz.py.
+The *sign* of the real-typed path follows LAPACK's eigenvector sign (infqltoeplitz.jl:14-15) and is
+therefore "parity unpinned" beyond the cases the reference tests hold.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+STATUS_OK = 0
+STATUS_NO_QL = 1          # DomainError: |mu|^2 < |a_u|^2 (infqltoeplitz.jl:13,23)
+STATUS_NOT_REAL = 2       # DomainError: dominant eigenvalue not real (infqltoeplitz.jl:12)
+
+
+def _csign(z):
+    """Julia's sign(z) for complex z: z/|z| (0 for 0)."""
+    z = np.asarray(z)
+    az = np.abs(z)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.where(az == 0, 0, z / np.where(az == 0, 1, az))
+
+
+def companion(a):
+    """C of infqltoeplitz.jl:9/20 for a batch of coefficient rows a[..., m].
+
+    First column (a[m-1], ..., a[1]) (1-based), then -a[m]*I_{m-2} stacked over a zero row.
+    """
+    a = np.asarray(a)
+    m = a.shape[-1]
+    n = m - 1
+    C = np.zeros(a.shape[:-1] + (n, n), dtype=a.dtype)
+    C[..., :, 0] = a[..., m - 2::-1]
+    for i in range(n - 1):
+        C[..., i, i + 1] = -a[..., m - 1]
+    return C
+
+
+def _julia_sorted_eig(C):
+    """eigen(C) with Julia's default ordering: eigenvalues sorted by (real, imag)."""
+    lam, V = np.linalg.eig(C)
+    # lexsort: last key is primary
+    order = np.lexsort((lam.imag, lam.real), axis=-1) if lam.ndim == 1 else \
+        np.stack([np.lexsort((li.imag, li.real)) for li in lam.reshape(-1, lam.shape[-1])]).reshape(lam.shape)
+    lam = np.take_along_axis(lam, order, axis=-1)
+    V = np.take_along_axis(V, order[..., None, :], axis=-1)
+    return lam, V
+
+
+def _select(n2, branch_rank):
+    """branch: rank 1 = findmax (first maximum); rank k = k-th largest |mu|^2
+    (examples/toeplitz.jl:22-27: sortperm(n2)[end-k+1])."""
+    if branch_rank == 1:
+        return np.argmax(n2, axis=-1)
+    order = np.argsort(n2, axis=-1, kind="stable")
+    return order[..., -branch_rank]
+
+
+def tail_de(a, branch_rank=1, real_path=None):
+    """Batched `tail_de` (infqltoeplitz.jl:7-27).
+
+    a: (..., m) coefficients [a_{-l}, ..., a_0, a_{+1}] (i.e. reverse of the Toeplitz data column).
+    Returns (de (..., m-1), status (...), mu (...)).  Rows with status != 0 hold NaN.
+    real_path: True → the `T<:Real` method; default: a is real dtype.
+    """
+    a = np.asarray(a)
+    if real_path is None:
+        real_path = not np.iscomplexobj(a)
+    batch_shape = a.shape[:-1]
+    m = a.shape[-1]
+    C = companion(a)
+    lam, V = _julia_sorted_eig(C)
+    n2 = lam.real ** 2 + lam.imag ** 2
+    j = _select(n2, branch_rank)
+    n2j = np.take_along_axis(n2, j[..., None], axis=-1)[..., 0]
+    muj = np.take_along_axis(lam, j[..., None], axis=-1)[..., 0]
+    Vj = np.take_along_axis(V, j[..., None, None], axis=-1)[..., 0]       # (..., m-1)
+    au = a[..., m - 1]
+    status = np.zeros(batch_shape, dtype=np.int32)
+    if real_path:
+        notreal = np.iscomplexobj(lam) and (muj.imag != 0)
+        if np.iscomplexobj(lam):
+            status = np.where(muj.imag != 0, STATUS_NOT_REAL, status)
+        au2 = np.real(au) ** 2
+        status = np.where((status == 0) & ~(n2j >= au2), STATUS_NO_QL, status)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            c = np.sqrt((n2j - au2) / np.real(Vj[..., 0]) ** 2)
+            de = c[..., None] * np.real(Vj[..., ::-1])
+        de = np.where((status == 0)[..., None], de, np.nan)
+        return de, status.astype(np.int32), muj
+    au2 = au.real ** 2 + au.imag ** 2 if np.iscomplexobj(au) else au ** 2
+    status = np.where(~(n2j >= au2), STATUS_NO_QL, status)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        v1 = Vj[..., 0]
+        c_abs = np.sqrt((n2j - au2) / (v1.real ** 2 + v1.imag ** 2))
+        c_sgn = -_csign(muj) / _csign(v1 * a[..., m - 2] - Vj[..., 1] * au)
+        de = (c_sgn * c_abs)[..., None] * Vj[..., ::-1]
+    de = np.where((status == 0)[..., None], de, np.nan)
+    return de, status.astype(np.int32), muj
+
+
+def _reflector(x):
+    """LinearAlgebra.reflector! on the leading axis of x (shape (n, ...)); returns tau, mutates x.
+
+    xi1 = x[0]; normu = ||x||; nu = copysign(normu, real(xi1)); xi1 += nu; x[0] = -nu; x[1:] /= xi1;
+    tau = xi1/nu  (0 when normu == 0).
+    """
+    xi1 = x[0].copy()
+    normu = np.sqrt(np.sum(x.real ** 2 + x.imag ** 2, axis=0)) if np.iscomplexobj(x) \
+        else np.sqrt(np.sum(x * x, axis=0))
+    zero = normu == 0
+    nu = np.copysign(normu, xi1.real)
+    nu_safe = np.where(zero, 1, nu)
+    xi1n = xi1 + nu
+    xi1n_safe = np.where(zero, 1, xi1n)
+    x[0] = np.where(zero, x[0], -nu)
+    if x.shape[0] > 1:
+        x[1:] = np.where(zero, x[1:], x[1:] / xi1n_safe)
+    tau = np.where(zero, 0, xi1n / nu_safe)
+    return tau
+
+
+def _reflector_apply(x, tau, A):
+    """LinearAlgebra.reflectorApply!(x, tau, A): A (n, ncols, ...) <- (I - conj(tau) v v')A, v=[1;x[1:]]."""
+    vA = A[0].copy()
+    for i in range(1, x.shape[0]):
+        vA = vA + np.conj(x[i])[None] * A[i]
+    vA = np.conj(tau)[None] * vA
+    A[0] = A[0] - vA
+    for i in range(1, x.shape[0]):
+        A[i] = A[i] - x[i][None] * vA
+
+
+def ql_X(X):
+    """`ql_X!` (infqltoeplitz.jl:31-39) on a batch X[..., 2, m]; returns (X_factored, tau[..., 2]).
+
+    `ql!` of a 2×m matrix (MatrixFactorizations; the loop is restated in src/infql.jl:10-22 and
+    examples/jacobi.jl:61-74): k = 2: reflector on (X[2,m], X[1,m]) applied to columns 1..m-1;
+    k = 1 (complex only): length-1 reflector on X[1,m-1] applied to X[1,1:m-2]; then the sign fix.
+    """
+    X = np.array(X, copy=True)
+    cplx = np.iscomplexobj(X)
+    m = X.shape[-1]
+    s = np.sign(X[..., 1, m - 1].real)
+    tau = np.zeros(X.shape[:-2] + (2,), dtype=X.dtype)
+    # k = 2 : x = (X[2,m], X[1,m]); rows reversed (view(A, 2:-1:1, m))
+    Xt = np.moveaxis(X, (-2, -1), (0, 1))        # (2, m, ...)
+    x = np.stack([Xt[1, m - 1], Xt[0, m - 1]])
+    t2 = _reflector(x)
+    Xt[1, m - 1], Xt[0, m - 1] = x[0], x[1]
+    A = np.stack([Xt[1, :m - 1], Xt[0, :m - 1]])   # (2, m-1, ...)
+    _reflector_apply(x, t2, A)
+    Xt[1, :m - 1], Xt[0, :m - 1] = A[0], A[1]
+    tau[..., 1] = t2
+    if cplx:
+        x1 = Xt[0, m - 2][None].copy()
+        t1 = _reflector(x1)
+        Xt[0, m - 2] = x1[0]
+        if m > 2:
+            A1 = Xt[0, :m - 2][None].copy()
+            _reflector_apply(x1, t1, A1)
+            Xt[0, :m - 2] = A1[0]
+        tau[..., 0] = t1
+    X = np.moveaxis(Xt, (0, 1), (-2, -1))
+    flip = s != np.sign(X[..., 0, m - 2].real)
+    tau[..., 0] = np.where(flip, 2 - tau[..., 0], tau[..., 0])
+    X[..., 0, :m - 1] = np.where(flip[..., None], -X[..., 0, :m - 1], X[..., 0, :m - 1])
+    return X, tau
+
+
+def ql_toeplitz_tail(a, branch_rank=1, real_path=None):
+    """`ql_hessenberg(::InfToeplitz)` data (infqltoeplitz.jl:56-65) for a batch of symbols.
+
+    a: (..., m) = reverse(A.data.args[1]) = [a_{-l}, ..., a_0, a_{+1}].
+    Returns dict with L11 (...), X (..., 2, m) factored, tau (..., 2), de, status, mu.
+      first L column  = [X[1,m-1]; X[2,m-1:-1:1]]   (band rows u+1 ..)
+      tail  L column  = X[2,m:-1:1]
+      2×2 Q block     = QLPackedQ(X[:, m-1:m], tau)
+    """
+    a = np.asarray(a)
+    de, status, mu = tail_de(a, branch_rank, real_path)
+    m = a.shape[-1]
+    dt = de.dtype if np.iscomplexobj(de) or np.iscomplexobj(a) else np.float64
+    dt = np.result_type(a.dtype, de.dtype)
+    X = np.zeros(a.shape[:-1] + (2, m), dtype=dt)
+    X[..., 0, :] = a
+    X[..., 1, 1:] = de
+    with np.errstate(invalid="ignore", divide="ignore"):
+        Xf, tau = ql_X(X)
+    L11 = Xf[..., 0, m - 2]
+    return dict(L11=L11, X=Xf, tau=tau, de=de, status=status, mu=mu)
+
+
+def ql_toeplitz_l11(coeffs_data_column, lambdas, branch_rank=1, real_path=None):
+    """L[1,1] of ql(A - lambda*I) for the pure Toeplitz A whose BandedMatrices data column is
+    `coeffs_data_column` = [a_{+u}, ..., a_0, ..., a_{-l}] with u == 1 (infqltoeplitz.jl:56-65, 191).
+
+    lambdas: array of shifts.  Returns (L11, status).
+    """
+    col = np.asarray(coeffs_data_column)
+    lambdas = np.asarray(lambdas)
+    dt = np.result_type(col.dtype, lambdas.dtype)
+    a = np.empty(lambdas.shape + (col.shape[0],), dtype=dt)
+    a[...] = col[::-1]
+    m = col.shape[0]
+    a[..., m - 2] = col[1] - lambdas          # diagonal coefficient a_0 - lambda
+    out = ql_toeplitz_tail(a, branch_rank, real_path)
+    return out["L11"], out["status"]
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers used by the tests (dense finite sections; restated from src/infql.jl:10-22)
+# ----------------------------------------------------------------------------------------------
+
+def dense_ql(A):
+    """Householder QL of a dense square/tall matrix, loop of src/infql.jl:10-22 with
+    the `(T<:Real)` lower bound of examples/jacobi.jl:63 (the convention MatrixFactorizations.ql! uses).
+
+    Returns (factors, tau): L in the lower triangle (for m == n), reflector vectors above.
+    """
+    A = np.array(A, copy=True)
+    cplx = np.iscomplexobj(A)
+    m, n = A.shape
+    mn = min(m, n)
+    tau = np.zeros(mn, dtype=A.dtype)
+    kmin = 1 if cplx else 2
+    for k in range(mn, kmin - 1, -1):
+        mu = m - mn + k
+        nu = n - mn + k
+        x = A[mu - 1::-1, nu - 1].copy() if mu - 1 >= 0 else None
+        x = A[:mu, nu - 1][::-1].copy()
+        t = _reflector(x)
+        A[:mu, nu - 1] = x[::-1]
+        tau[k - 1] = t
+        if nu - 1 > 0:
+            B = A[:mu, :nu - 1][::-1].copy()
+            _reflector_apply(x, np.asarray(t), B)
+            A[:mu, :nu - 1] = B[::-1]
+    return A, tau
+
+
+def ql_packed_Q(factors, tau):
+    """Dense Q of a packed QL (square factors): Q = H_n ... H_1?  Built by applying to the identity.
+
+    Q = prod_k H_k with H_k = I - tau_k v_k v_k', v_k = [factors[0:k-1, nu]; 1; 0...]. A = Q L.
+    """
+    m, n = factors.shape
+    mn = min(m, n)
+    Q = np.eye(m, dtype=factors.dtype)
+    # A = Q L  with  Q' = H_1' ... H_mn'  applied in order k = mn, ..., 1 to A; so Q = H_mn H_{mn-1} ... H_1
+    for k in range(1, mn + 1):
+        mu = m - mn + k
+        nu = n - mn + k
+        v = np.zeros(m, dtype=factors.dtype)
+        v[:mu - 1] = factors[:mu - 1, nu - 1]
+        v[mu - 1] = 1
+        H = np.eye(m, dtype=factors.dtype) - tau[k - 1] * np.outer(v, np.conj(v))
+        Q = H @ Q
+    return Q

@@ -1,0 +1,56 @@
+"""The C-ABI library builds, loads and exports every symbol include/ila_b200.h declares (no GPU compute)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "ila_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ila_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(ila):
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    L = ctypes.CDLL(ila.SO_PATH)
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/ila_b200.h but not exported"
+    # the ctypes table covers the header and nothing else
+    from ila_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == syms
+
+
+def test_version_and_no_cpu_fallback(ila):
+    L = ila.lib()
+    assert L.ila_version() >= 100
+    if L.ila_device_count() == 0:
+        with pytest.raises(ila.IlaError) as e:
+            ila.ql_toeplitz_l11([2j, 0, 0, 1, 0.7], np.array([5.0 + 0j]))
+        assert e.value.code == -3
+        with pytest.raises(ila.IlaError):
+            ila.qr_banded_solve(1, 1, [[1, 1, 1]], [[0, 1, 0]], b=[1.0], ncap=3000)
+
+
+def test_product_path_never_imports_oracle():
+    """The shipped package must not reference oracle/ (prompt ③): grep the package sources."""
+    pkg = os.path.join(ROOT, "infinitelinearalgebra.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in src and "from oracle" not in src and "libila_oracle" not in src, f
+
+
+def test_work_offsets_host_helper(ila):
+    from ila_b200 import _lib
+    woff = np.zeros(4, dtype=np.int64)
+    caps = np.array([5, 8, 13], dtype=np.int64)
+    _lib.check(ila.lib().ila_qr_banded_work_offsets(3, 0, _lib.ptr(caps), _lib.ptr(woff)))
+    assert list(woff) == [0, 8, 16, 32]
+    assert ila.lib().ila_qr_banded_work_bytes(1, 1, 3, 0, _lib.ptr(caps)) == 32 * 8 * 6
