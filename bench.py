@@ -271,10 +271,12 @@ def run_ours(args, rank, local_rank, world):
         from scipy.special import jv
         zs = c2_z()
         p, q, r = ila_b200.bessel_operator(zs)
-        caps = np.ceil(1.06 * zs + 3000).astype(np.int64)
+        caps = ila_b200.bessel_ncap(zs)
         plan = ila_b200.QrBandedPlan(1, 1, p, q, r, b=jv(1, zs)[:, None], ncap_per=caps, device=dev)
         k2 = max(1, min(args.steps, 5))
         ms2 = timed(plan.run, k2, 1) / k2
+        if int((plan.d_status != 0).sum().item()) != 0:
+            raise SystemExit("bench.py: C2 instances did not converge within ncap")
         cols = float(plan.d_nswept.sum().item())
         cols_ref = float(plan.d_ncols.sum().item())
         gbs2 = BYTES_PER_COLUMN * cols / (ms2 * 1e-3) / 1e9

@@ -98,6 +98,11 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
                             int64_t *xoff, int64_t *ncols, int64_t *nconv, double *factors_opt, double *tau_opt,
                             double *qtb_opt, int32_t *status, int ngpus);
 
+/* Arithmetic of the sweeps: 0 (default) = branch-free division / square-root sequences that reproduce the IEEE
+ * results bit for bit inside an exponent box (redo with intrinsics outside it); 1 = plain __ddiv_rn/__dsqrt_rn
+ * (validation mode: both must give identical bits). */
+int ila_qr_set_arith_mode(int mode);
+
 /* device-resident two-phase form (no host round trip between the phases; the caller owns all buffers):
  *   phase 1 `_factor_dev`: forward sweep + Q'b + convergence; writes d_ncols, d_nconv, d_status, d_xoff (scan).
  *   phase 2 `_backsolve_dev`: back-substitution into ragged d_x using d_xoff.

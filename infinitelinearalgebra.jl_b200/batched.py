@@ -203,6 +203,14 @@ def bessel_operator(z):
     return p, q, r
 
 
+def bessel_ncap(z, colgrowth=1000):
+    """Column capacity that lets the Bessel solve converge: |(Q'b)_k| drops below floatmin at
+    k ≈ z + 83 z^(1/3) (Debye asymptotics of J_k(z), k > z); the reference then factorizes up to two more
+    COLGROWTH chunks."""
+    z = np.atleast_1d(np.asarray(z, dtype=np.float64))
+    return np.ceil(z + 90.0 * np.cbrt(z) + 2 * colgrowth + 100).astype(np.int64)
+
+
 def fp64_peak_tflops():
     t = C.c_double(0.0)
     ms = C.c_double(0.0)

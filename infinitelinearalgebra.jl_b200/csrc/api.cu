@@ -35,6 +35,8 @@ struct QrBwdArgs {
     int64_t xcap;
 };
 int qr_record_doubles(int l, int u, bool refl);
+void qr_set_arith_mode(int mode);
+int qr_get_arith_mode();
 int launch_qr_forward(int l, int u, const QrFwdArgs &a, bool refl, cudaStream_t s);
 int launch_qr_scan(const int64_t *d_ncols, int64_t batch, int64_t *d_xoff, cudaStream_t s);
 int launch_qr_backsolve(int l, int u, const QrBwdArgs &a, bool refl, cudaStream_t s);
@@ -306,6 +308,13 @@ int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_l
 }
 
 // ================================ K1+K2: adaptive banded QR solve =======================================
+
+int ila_qr_set_arith_mode(int mode)
+{
+    if (mode != 0 && mode != 1) return set_error(ILA_ERR_ARG, "qr arith mode must be 0 (branch-free exact) or 1 (IEEE intrinsics)");
+    qr_set_arith_mode(mode);
+    return 0;
+}
 
 int ila_qr_banded_work_offsets(int64_t batch, int64_t ncap, const int64_t *ncap_per, int64_t *woff_host)
 {

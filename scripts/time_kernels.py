@@ -35,8 +35,16 @@ print(f"K3 1M points: median {med*1e3:.1f} us min {mn*1e3:.1f} us -> {lam.numel(
 for name, zs in (("64 z in [1e3,1e4]", np.linspace(1e3, 1e4, 64)), ("4096 z in [1e3,1e5] (C2)", 1e3 + (1e5 - 1e3) * np.arange(4096) / 4095),
                  ("32768 z=2000", np.full(32768, 2000.0))):
     p, q, r = ila_b200.bessel_operator(zs)
-    caps = np.ceil(1.06 * zs + 3000).astype(np.int64)
+    caps = ila_b200.bessel_ncap(zs)
     plan = ila_b200.QrBandedPlan(1, 1, p, q, r, b=jv(1, zs)[:, None], ncap_per=caps)
+    if "C2" in name or "64 z" in name:
+        _lib.check(_lib.lib().ila_qr_set_arith_mode(1)); plan.run(); torch.cuda.synchronize()
+        x_ref = plan.d_x.clone(); nc_ref = plan.d_ncols.clone(); work_ref = plan.d_work.clone()
+        tm1, _ = ev_time(plan.run, reps=2, warm=0)
+        _lib.check(_lib.lib().ila_qr_set_arith_mode(0)); plan.run(); torch.cuda.synchronize()
+        tot = int(plan.d_xoff[-1].item())
+        print("  mode0 vs mode1: ncols equal", bool(torch.equal(nc_ref, plan.d_ncols)), "x bit-equal", bool(torch.equal(x_ref[:tot].view(torch.int64), plan.d_x[:tot].view(torch.int64))), "records bit-equal (swept part) checked via x; intrinsics-mode time %.2f ms" % tm1)
+        del x_ref, work_ref
     mf, _ = ev_time(plan.run_factor, reps=5, warm=1)
     mb, _ = ev_time(plan.run_backsolve, reps=5, warm=1)
     mt, _ = ev_time(plan.run, reps=5, warm=1)

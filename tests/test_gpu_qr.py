@@ -23,7 +23,7 @@ def test_bessel_batch_bit_exact(ila):
     zs = np.concatenate([[10.0, 100.0, 1000.0, 10000.0], np.linspace(1e3, 2e4, 60)])
     p, q, r = ila.bessel_operator(zs)
     b = jv(1, zs)[:, None]
-    caps = np.ceil(1.06 * zs + 3000).astype(np.int64)
+    caps = ila.bessel_ncap(zs)
     g = ila.qr_banded_solve(1, 1, p, q, r, b=b, ncap_per=caps)
     o = ob.qr_banded_solve(1, 1, p, q, r, b=b, ncap=int(caps.max()))
     # the oracle ran with the largest capacity; statuses must agree because every instance converges
@@ -100,7 +100,7 @@ def test_c2_full_size_properties(ila):
     zs = 1e3 + (1e5 - 1e3) * np.arange(4096) / 4095
     p, q, r = ila.bessel_operator(zs)
     b = jv(1, zs)[:, None]
-    caps = np.ceil(1.06 * zs + 3000).astype(np.int64)
+    caps = ila.bessel_ncap(zs)
     g = ila.qr_banded_solve(1, 1, p, q, r, b=b, ncap_per=caps)
     assert np.all(g["status"] == 0)
     assert np.all(g["ncols"] == g["nconv"] + 1000)            # n = n_conv + COLGROWTH - 1 + l
