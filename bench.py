@@ -287,7 +287,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "achieved": gbs2, "peak": hbm_peak, "unit": "GB/s", "frac": gbs2 / hbm_peak,
                          "traffic": None, "peak_kind": peak_kind, "bytes_per_unit": BYTES_PER_COLUMN,
                          "note": "latency bound: 4096 serial recurrences = 128 warps on 148 SMs"},
-            "gpu_launches_per_step": 3,
+            "gpu_launches_per_step": 4,
         }
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------

@@ -104,21 +104,21 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
 int ila_qr_set_arith_mode(int mode);
 
 /* device-resident two-phase form (no host round trip between the phases; the caller owns all buffers):
- *   phase 1 `_factor_dev`: forward sweep + Q'b + convergence; writes d_ncols, d_nconv, d_status, d_xoff (scan).
- *   phase 2 `_backsolve_dev`: back-substitution into ragged d_x using d_xoff.
- * d_work: ila_qr_banded_work_bytes(l,u,batch,ncap,ncap_per) bytes.  d_woff: batch+1 int64 workspace offsets
- * (in columns), filled by the host helper ila_qr_banded_work_offsets. */
-int64_t ila_qr_banded_work_bytes(int l, int u, int64_t batch, int64_t ncap, const int64_t *ncap_per);
-int ila_qr_banded_work_offsets(int64_t batch, int64_t ncap, const int64_t *ncap_per, int64_t *woff_host);
+ *   phase 1 `_factor_dev`: forward sweep + Q'b + convergence; writes d_ncols, d_nconv, d_nswept, d_status, d_xoff (scan).
+ *   phase 2 `_backsolve_dev`: back-substitution + compaction into the ragged d_x using d_xoff.
+ * Workspace: instances are swept in groups of 32 (one warp); `ila_qr_banded_work_layout` (host helper) fills
+ * gbase_host[(batch+31)/32 + 1] (group bases, in rows) and reports the bytes of d_work (records, coalesced
+ * group-interleaved layout, see csrc/qr_banded.cu) and d_xi (interleaved solution).  d_ncap_per may be NULL (uniform ncap). */
+int ila_qr_banded_work_layout(int l, int u, int64_t batch, int64_t ncap, const int64_t *ncap_per, int64_t *gbase_host,
+                              int64_t *work_bytes, int64_t *xi_bytes);
 int ila_qr_banded_factor_f64_dev(int l, int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
                                  const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
-                                 double tol, int colgrowth, const int64_t *d_woff, double *d_work, int64_t *d_ncols,
-                                 int64_t *d_nconv, int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status,
-                                 int want_reflectors, void *stream);
-int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *d_woff, const double *d_work,
+                                 double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
+                                 const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
+                                 int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int want_reflectors, void *stream);
+int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *d_gbase, const void *d_work, double *d_xi,
                                     const int64_t *d_ncols, const int64_t *d_nswept, const int64_t *d_xoff,
-                                    const int32_t *d_status, double *d_x, int64_t xcap, int want_reflectors,
-                                    void *stream);
+                                    const int32_t *d_status, double *d_x, int64_t xcap, int want_reflectors, void *stream);
 
 #ifdef __cplusplus
 }

@@ -148,13 +148,18 @@ class QrBandedPlan:
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         caps = None if ncap_per is None else np.ascontiguousarray(np.asarray(ncap_per, dtype=np.int64))
-        woff = np.zeros(batch + 1, dtype=np.int64)
-        check(lib().ila_qr_banded_work_offsets(batch, int(ncap), ptr(caps), ptr(woff)))
-        wbytes = lib().ila_qr_banded_work_bytes(l, u, batch, int(ncap), ptr(caps))
-        t = lambda a: None if a is None else torch.from_numpy(a).to(dev)
+        gbase = np.zeros((batch + 31) // 32 + 1, dtype=np.int64)
+        wbytes = C.c_int64(0)
+        xbytes = C.c_int64(0)
+        check(lib().ila_qr_banded_work_layout(l, u, batch, int(ncap), ptr(caps), ptr(gbase), C.byref(wbytes),
+                                              C.byref(xbytes)))
+        t = lambda a: None if a is None else torch.from_numpy(np.array(a, copy=True)).to(dev)
         self.d_p, self.d_q, self.d_r, self.d_shift, self.d_head, self.d_b = t(p), t(q), t(r), t(shift), t(head), t(b)
-        self.d_woff = t(woff)
-        self.d_work = torch.empty(wbytes // 8, dtype=torch.float64, device=dev)
+        self.ncap = int(ncap)
+        self.d_caps = t(caps)
+        self.d_gbase = t(gbase)
+        self.d_work = torch.empty(wbytes.value // 8, dtype=torch.float64, device=dev)
+        self.d_xi = torch.empty(xbytes.value // 8, dtype=torch.float64, device=dev)
         self.d_ncols = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.d_nconv = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.d_nswept = torch.zeros(batch, dtype=torch.int64, device=dev)
@@ -172,23 +177,23 @@ class QrBandedPlan:
     def run(self):
         self.run_factor()
         self.run_backsolve()
-        return 3   # kernels launched: forward, scan, back-substitution
+        return 4   # kernels launched: forward, scan, back-substitution, compaction
 
     def run_factor(self):
         s = self._stream()
         check(lib().ila_qr_banded_factor_f64_dev(
             self.l, self.u, self.batch, ptr(self.d_p), ptr(self.d_q), ptr(self.d_r), ptr(self.d_shift), self.hp,
-            ptr(self.d_head), self.nb, ptr(self.d_b), self.tol, self.colgrowth, ptr(self.d_woff), ptr(self.d_work),
-            ptr(self.d_ncols), ptr(self.d_nconv), ptr(self.d_nswept), ptr(self.d_xoff), ptr(self.d_status),
-            self.refl, s))
+            ptr(self.d_head), self.nb, ptr(self.d_b), self.tol, self.colgrowth, self.ncap, ptr(self.d_caps),
+            ptr(self.d_gbase), ptr(self.d_work), ptr(self.d_ncols), ptr(self.d_nconv), ptr(self.d_nswept),
+            ptr(self.d_xoff), ptr(self.d_status), self.refl, s))
         return 2
 
     def run_backsolve(self):
         s = self._stream()
         check(lib().ila_qr_banded_backsolve_f64_dev(
-            self.l, self.u, self.batch, ptr(self.d_woff), ptr(self.d_work), ptr(self.d_ncols), ptr(self.d_nswept),
-            ptr(self.d_xoff), ptr(self.d_status), ptr(self.d_x), self.xcap, self.refl, s))
-        return 1
+            self.l, self.u, self.batch, ptr(self.d_gbase), ptr(self.d_work), ptr(self.d_xi), ptr(self.d_ncols),
+            ptr(self.d_nswept), ptr(self.d_xoff), ptr(self.d_status), ptr(self.d_x), self.xcap, self.refl, s))
+        return 2
 
 
 def bessel_operator(z):

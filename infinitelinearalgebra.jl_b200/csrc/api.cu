@@ -20,19 +20,20 @@ struct QrFwdArgs {
     const double *p, *q, *r, *shift, *head, *b;
     int hp, nb, colgrowth;
     double tol;
-    const int64_t *woff;
-    double *work;
+    const int64_t *gbase;
+    const int64_t *ncap_per;
+    int64_t ncap;
+    double2 *work;
     int64_t *ncols, *nconv, *nswept;
     int32_t *status;
 };
 struct QrBwdArgs {
     int64_t batch;
-    const int64_t *woff;
-    const double *work;
-    const int64_t *ncols, *nswept, *xoff;
+    const int64_t *gbase;
+    const double2 *work;
+    double *xi;
+    const int64_t *ncols, *nswept;
     const int32_t *status;
-    double *x;
-    int64_t xcap;
 };
 int qr_record_doubles(int l, int u, bool refl);
 void qr_set_arith_mode(int mode);
@@ -40,7 +41,9 @@ int qr_get_arith_mode();
 int launch_qr_forward(int l, int u, const QrFwdArgs &a, bool refl, cudaStream_t s);
 int launch_qr_scan(const int64_t *d_ncols, int64_t batch, int64_t *d_xoff, cudaStream_t s);
 int launch_qr_backsolve(int l, int u, const QrBwdArgs &a, bool refl, cudaStream_t s);
-int launch_qr_export(int l, int u, int64_t batch, const int64_t *d_woff, const double *d_work, const int64_t *d_ncols,
+int launch_qr_compact(int64_t batch, const int64_t *d_gbase, const double *d_xi, const int64_t *d_ncols,
+                      const int64_t *d_nswept, const int64_t *d_xoff, double *d_x, int64_t xcap, cudaStream_t s);
+int launch_qr_export(int l, int u, int64_t batch, const int64_t *d_gbase, const double2 *d_work, const int64_t *d_ncols,
                      const int64_t *d_nswept, const int64_t *d_xoff, double *d_factors, double *d_tau, double *d_qtb,
                      cudaStream_t s);
 
@@ -316,53 +319,52 @@ int ila_qr_set_arith_mode(int mode)
     return 0;
 }
 
-int ila_qr_banded_work_offsets(int64_t batch, int64_t ncap, const int64_t *ncap_per, int64_t *woff_host)
+int ila_qr_banded_work_layout(int l, int u, int64_t batch, int64_t ncap, const int64_t *ncap_per, int64_t *gbase_host,
+                              int64_t *work_bytes, int64_t *xi_bytes)
 {
-    if (batch < 0 || !woff_host) return set_error(ILA_ERR_ARG, "qr_banded_work_offsets: bad arguments");
+    if (batch < 0 || !gbase_host) return set_error(ILA_ERR_ARG, "qr_banded_work_layout: bad arguments");
+    const int64_t groups = (batch + 31) / 32;
     int64_t acc = 0;
-    for (int64_t i = 0; i < batch; i++) {
-        woff_host[i] = acc;
-        int64_t c = ncap_per ? ncap_per[i] : ncap;
-        if (c < 0) c = 0;
-        acc += (c + 3) & ~(int64_t)3;   // keep every instance's records 32 B aligned
+    for (int64_t g = 0; g < groups; g++) {
+        gbase_host[g] = acc;
+        int64_t mx = 0;
+        for (int64_t i = g * 32; i < batch && i < (g + 1) * 32; i++) {
+            const int64_t c = ncap_per ? ncap_per[i] : ncap;
+            if (c > mx) mx = c;
+        }
+        acc += (mx + 7) & ~(int64_t)7;
     }
-    woff_host[batch] = acc;
+    gbase_host[groups] = acc;
+    // records sized for the widest form (with reflectors) so one buffer serves both modes
+    if (work_bytes) *work_bytes = acc * 32 * (int64_t)sizeof(double) * qr_record_doubles(l, u, true);
+    if (xi_bytes) *xi_bytes = acc * 32 * (int64_t)sizeof(double);
     return 0;
-}
-
-int64_t ila_qr_banded_work_bytes(int l, int u, int64_t batch, int64_t ncap, const int64_t *ncap_per)
-{
-    int64_t acc = 0;
-    for (int64_t i = 0; i < batch; i++) {
-        int64_t c = ncap_per ? ncap_per[i] : ncap;
-        if (c < 0) c = 0;
-        acc += (c + 3) & ~(int64_t)3;
-    }
-    // sized for the widest record (with reflectors) so one buffer serves both modes
-    return acc * (int64_t)sizeof(double) * qr_record_doubles(l, u, true);
 }
 
 int ila_qr_banded_factor_f64_dev(int l, int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
                                  const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
-                                 double tol, int colgrowth, const int64_t *d_woff, double *d_work, int64_t *d_ncols,
-                                 int64_t *d_nconv, int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status,
-                                 int want_reflectors, void *stream)
+                                 double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
+                                 const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
+                                 int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int want_reflectors, void *stream)
 {
     if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
     if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0) return set_error(ILA_ERR_ARG, "qr_banded: bad sizes");
-    QrFwdArgs a{batch, d_p, d_q, d_r, d_shift, d_head, d_b, hp, nb, colgrowth, tol, d_woff, d_work, d_ncols, d_nconv, d_nswept, d_status};
+    QrFwdArgs a{batch, d_p, d_q, d_r, d_shift, d_head, d_b, hp, nb, colgrowth, tol, d_gbase, d_ncap_per, ncap,
+                (double2 *)d_work, d_ncols, d_nconv, d_nswept, d_status};
     int rc = launch_qr_forward(l, u, a, want_reflectors != 0, (cudaStream_t)stream);
     if (rc) return rc;
     return launch_qr_scan(d_ncols, batch, d_xoff, (cudaStream_t)stream);
 }
 
-int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *d_woff, const double *d_work,
+int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *d_gbase, const void *d_work, double *d_xi,
                                     const int64_t *d_ncols, const int64_t *d_nswept, const int64_t *d_xoff,
                                     const int32_t *d_status, double *d_x, int64_t xcap, int want_reflectors, void *stream)
 {
     if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
-    QrBwdArgs a{batch, d_woff, d_work, d_ncols, d_nswept, d_xoff, d_status, d_x, xcap};
-    return launch_qr_backsolve(l, u, a, want_reflectors != 0, (cudaStream_t)stream);
+    QrBwdArgs a{batch, d_gbase, (const double2 *)d_work, d_xi, d_ncols, d_nswept, d_status};
+    int rc = launch_qr_backsolve(l, u, a, want_reflectors != 0, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_qr_compact(batch, d_gbase, d_xi, d_ncols, d_nswept, d_xoff, d_x, xcap, (cudaStream_t)stream);
 }
 
 int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const double *q, const double *r,
@@ -388,10 +390,12 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
     struct Shard {
         int64_t cnt = 0;
         std::vector<double> p, q, r, shift, b;
-        std::vector<int64_t> woff, ncols, nconv, nswept, xoff;
+        std::vector<int64_t> gbase, caps, ncols, nconv, nswept, xoff;
+        int64_t work_bytes = 0, xi_bytes = 0;
         std::vector<int32_t> status;
-        double *d_p, *d_q, *d_r, *d_shift, *d_head, *d_b, *d_work, *d_x, *d_fac, *d_tau, *d_qtb;
-        int64_t *d_woff, *d_ncols, *d_nconv, *d_nswept, *d_xoff;
+        double *d_p, *d_q, *d_r, *d_shift, *d_head, *d_b, *d_x, *d_xi, *d_fac, *d_tau, *d_qtb;
+        char *d_work;
+        int64_t *d_gbase, *d_caps, *d_ncols, *d_nconv, *d_nswept, *d_xoff;
         int32_t *d_status;
         int64_t total = 0;
     };
@@ -402,7 +406,8 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
         S.p.resize(S.cnt * nd); S.q.resize(S.cnt * nd); S.b.resize(S.cnt * nb);
         if (r) S.r.resize(S.cnt * nd);
         if (shift) S.shift.resize(S.cnt);
-        std::vector<int64_t> caps(S.cnt);
+        S.caps.resize(S.cnt);
+        std::vector<int64_t> &caps = S.caps;
         for (int64_t j = 0; j < S.cnt; j++) {
             const int64_t i = j * G + d;
             memcpy(&S.p[j * nd], p + i * nd, sizeof(double) * nd);
@@ -412,8 +417,8 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
             memcpy(&S.b[j * nb], b + i * nb, sizeof(double) * nb);
             caps[j] = ncap_per ? ncap_per[i] : ncap;
         }
-        S.woff.resize(S.cnt + 1);
-        ila_qr_banded_work_offsets(S.cnt, 0, caps.data(), S.woff.data());
+        S.gbase.resize((S.cnt + 31) / 32 + 1);
+        ila_qr_banded_work_layout(l, u, S.cnt, 0, caps.data(), S.gbase.data(), &S.work_bytes, &S.xi_bytes);
         S.ncols.resize(S.cnt); S.nconv.resize(S.cnt); S.nswept.resize(S.cnt); S.status.resize(S.cnt); S.xoff.resize(S.cnt + 1);
     }
     // phase 1 on every device
@@ -429,22 +434,25 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
         if (shift && (rc = dev_buf_t(pd, 7, S.shift.size(), &S.d_shift))) return rc;
         if (hp > 0 && (rc = dev_buf_t(pd, 8, (size_t)nd * hp, &S.d_head))) return rc;
         if ((rc = dev_buf_t(pd, 9, S.b.size(), &S.d_b))) return rc;
-        if ((rc = dev_buf_t(pd, 10, (size_t)S.cnt + 1, &S.d_woff))) return rc;
+        if ((rc = dev_buf_t(pd, 10, S.gbase.size(), &S.d_gbase))) return rc;
+        if ((rc = dev_buf_t(pd, 21, (size_t)S.cnt, &S.d_caps))) return rc;
         if ((rc = dev_buf_t(pd, 11, (size_t)S.cnt, &S.d_ncols))) return rc;
         if ((rc = dev_buf_t(pd, 12, (size_t)S.cnt, &S.d_nconv))) return rc;
         if ((rc = dev_buf_t(pd, 13, (size_t)S.cnt, &S.d_nswept))) return rc;
         if ((rc = dev_buf_t(pd, 14, (size_t)S.cnt + 1, &S.d_xoff))) return rc;
         if ((rc = dev_buf_t(pd, 15, (size_t)S.cnt, &S.d_status))) return rc;
-        if ((rc = dev_buf_t(pd, 16, (size_t)S.woff[S.cnt] * REC, &S.d_work))) return rc;
+        if ((rc = dev_buf_t(pd, 16, (size_t)S.work_bytes, &S.d_work))) return rc;
+        if ((rc = dev_buf_t(pd, 22, (size_t)S.xi_bytes / sizeof(double), &S.d_xi))) return rc;
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_p, S.p.data(), sizeof(double) * S.p.size(), cudaMemcpyHostToDevice, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_q, S.q.data(), sizeof(double) * S.q.size(), cudaMemcpyHostToDevice, s));
         if (r) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_r, S.r.data(), sizeof(double) * S.r.size(), cudaMemcpyHostToDevice, s));
         if (shift) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_shift, S.shift.data(), sizeof(double) * S.shift.size(), cudaMemcpyHostToDevice, s));
         if (hp > 0) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_head, head, sizeof(double) * nd * hp, cudaMemcpyHostToDevice, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_b, S.b.data(), sizeof(double) * S.b.size(), cudaMemcpyHostToDevice, s));
-        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_woff, S.woff.data(), sizeof(int64_t) * (S.cnt + 1), cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_gbase, S.gbase.data(), sizeof(int64_t) * S.gbase.size(), cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_caps, S.caps.data(), sizeof(int64_t) * S.cnt, cudaMemcpyHostToDevice, s));
         rc = ila_qr_banded_factor_f64_dev(l, u, S.cnt, S.d_p, S.d_q, S.d_r, S.d_shift, hp, S.d_head, nb, S.d_b, tol, colgrowth,
-                                          S.d_woff, S.d_work, S.d_ncols, S.d_nconv, S.d_nswept, S.d_xoff, S.d_status, refl, s);
+                                          0, S.d_caps, S.d_gbase, S.d_work, S.d_ncols, S.d_nconv, S.d_nswept, S.d_xoff, S.d_status, refl, s);
         if (rc) return rc;
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.ncols.data(), S.d_ncols, sizeof(int64_t) * S.cnt, cudaMemcpyDeviceToHost, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.nconv.data(), S.d_nconv, sizeof(int64_t) * S.cnt, cudaMemcpyDeviceToHost, s));
@@ -479,7 +487,7 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
         cudaStream_t s = g_dev[pd].stream;
         S.total = S.xoff[S.cnt];
         if ((rc = dev_buf_t(pd, 17, (size_t)S.total, &S.d_x))) return rc;
-        rc = ila_qr_banded_backsolve_f64_dev(l, u, S.cnt, S.d_woff, S.d_work, S.d_ncols, S.d_nswept, S.d_xoff, S.d_status, S.d_x,
+        rc = ila_qr_banded_backsolve_f64_dev(l, u, S.cnt, S.d_gbase, S.d_work, S.d_xi, S.d_ncols, S.d_nswept, S.d_xoff, S.d_status, S.d_x,
                                              S.total, refl, s);
         if (rc) return rc;
         S.d_fac = S.d_tau = S.d_qtb = nullptr;
@@ -491,7 +499,7 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
             if (tau_opt && (rc = dev_buf_t(pd, 19, (size_t)S.total, &S.d_tau))) return rc;
             if (qtb_opt && (rc = dev_buf_t(pd, 20, (size_t)S.total, &S.d_qtb))) return rc;
             if (refl) {
-                if ((rc = launch_qr_export(l, u, S.cnt, S.d_woff, S.d_work, S.d_ncols, S.d_nswept, S.d_xoff, S.d_fac, S.d_tau, S.d_qtb, s))) return rc;
+                if ((rc = launch_qr_export(l, u, S.cnt, S.d_gbase, (const double2 *)S.d_work, S.d_ncols, S.d_nswept, S.d_xoff, S.d_fac, S.d_tau, S.d_qtb, s))) return rc;
             } else {
                 return set_error(ILA_ERR_UNSUPPORTED, "qr_banded_solve: qtb_opt requires factors_opt or tau_opt");
             }

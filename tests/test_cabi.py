@@ -47,10 +47,13 @@ def test_product_path_never_imports_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "libila_oracle" not in src, f
 
 
-def test_work_offsets_host_helper(ila):
+def test_work_layout_host_helper(ila):
+    import ctypes
     from ila_b200 import _lib
-    woff = np.zeros(4, dtype=np.int64)
-    caps = np.array([5, 8, 13], dtype=np.int64)
-    _lib.check(ila.lib().ila_qr_banded_work_offsets(3, 0, _lib.ptr(caps), _lib.ptr(woff)))
-    assert list(woff) == [0, 8, 16, 32]
-    assert ila.lib().ila_qr_banded_work_bytes(1, 1, 3, 0, _lib.ptr(caps)) == 32 * 8 * 6
+    caps = np.array([5, 8, 13] + [3] * 31, dtype=np.int64)          # 34 instances -> 2 groups of 32
+    gbase = np.zeros(3, dtype=np.int64)
+    wb, xb = ctypes.c_int64(0), ctypes.c_int64(0)
+    _lib.check(ila.lib().ila_qr_banded_work_layout(1, 1, 34, 0, _lib.ptr(caps), _lib.ptr(gbase), ctypes.byref(wb),
+                                                   ctypes.byref(xb)))
+    assert list(gbase) == [0, 16, 24]                               # group capacities rounded up to 8 rows
+    assert xb.value == 24 * 32 * 8 and wb.value == 24 * 32 * 8 * 6  # 6 doubles per record with reflectors (l=u=1)
