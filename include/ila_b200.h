@@ -70,6 +70,11 @@ int ila_ql_toeplitz_l11_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d
 int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank,
                                 double *d_L11, double *d_tail_opt, int32_t *d_status, void *stream);
 
+/* Shifts per thread of the K3 kernel: consecutive shifts of one thread warm-start the root finder from the previous
+ * shift's roots (any doubt falls back to a cold simultaneous solve, so results do not depend on it).
+ * 0 = automatic (default), 1 = every shift cold. */
+int ila_ql_set_shifts_per_thread(int spt);
+
 /* ---- K1+K2: adaptive banded QR solve  x_i = A_i \ b_i ----------------------------------------
  * Replaces qr(A) -> adaptiveqr (src/infqr.jl:163-174) and `\` = ldiv!(F.R, F.Q'*b) (src/infqr.jl:370-374):
  * AdaptiveQRData/partialqr! (:2-13,32-48) -> _banded_qr!, the Q'b adaptive driver (:236-274) and the

@@ -14,6 +14,8 @@ std::atomic<int64_t> g_launches{0};
 int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
                        int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream);
 
+void tz_set_spt(int v);
+
 // from qr_banded.cu
 struct QrFwdArgs {
     int64_t batch;
@@ -308,6 +310,13 @@ int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_l
 {
     if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
     return launch_ql_toeplitz(true, l, u, a, branch_rank, d_lambda, n, d_L11, d_tail_opt, d_status, (cudaStream_t)stream);
+}
+
+int ila_ql_set_shifts_per_thread(int spt)
+{
+    if (spt < 0 || spt > 16) return set_error(ILA_ERR_ARG, "shifts per thread must be in 0..16 (0 = automatic)");
+    tz_set_spt(spt);
+    return 0;
 }
 
 // ================================ K1+K2: adaptive banded QR solve =======================================

@@ -20,6 +20,8 @@ namespace ila {
 
 constexpr int kMaxDeg = 8;   // l + 1 <= 8
 constexpr int kAberthMaxIt = 48;
+static int g_tz_spt = 0;   // 0 = automatic; set by ila_ql_set_shifts_per_thread (1 = every shift starts cold)
+void tz_set_spt(int v) { g_tz_spt = v; }
 
 template <int N>
 struct TzParams {
@@ -29,6 +31,19 @@ struct TzParams {
     double beta2;      // |β|^2
     int branch_rank;
 };
+
+// branch-free reciprocal for the root-finder's corrections (MUFU seed + two Newton steps, ~1 ulp): an iteration that
+// converges to the root does not need correctly rounded quotients; the final factors use IEEE division.
+__device__ __forceinline__ double fast_rcp(double b)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(r, -b, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(r, -b, 1.0);
+    return fma(r, e, r);
+}
 
 __device__ __forceinline__ double dsign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
 
@@ -45,15 +60,147 @@ __device__ __forceinline__ void horner2(const cplx (&cf)[N + 1], cplx w, cplx &p
     }
 }
 
+// ---- single-precision scout ----------------------------------------------------------------------------
+// All N roots are located (and tracked from shift to shift) in FP32 on the FP32 pipe, which runs beside the FP64
+// pipe: 1e-7 is ample to rank the moduli away from near-ties and to seed the FP64 Newton iteration that takes the
+// selected root to full precision.  Near-ties and anything that does not converge fall back to the FP64 solve.
+struct cplxf {
+    float re, im;
+};
+__device__ __forceinline__ cplxf mkf(float re, float im = 0.f) { return cplxf{re, im}; }
+__device__ __forceinline__ cplxf operator+(cplxf a, cplxf b) { return cplxf{a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cplxf operator-(cplxf a, cplxf b) { return cplxf{a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ cplxf operator*(cplxf a, cplxf b) { return cplxf{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ cplxf operator*(float s, cplxf a) { return cplxf{s * a.re, s * a.im}; }
+__device__ __forceinline__ cplxf conjf_(cplxf a) { return cplxf{a.re, -a.im}; }
+__device__ __forceinline__ float abs2f(cplxf a) { return a.re * a.re + a.im * a.im; }
+
+template <int N>
+__device__ __forceinline__ int aberth_sweep_f32(const cplxf (&cf)[N + 1], cplxf (&w)[N])
+{
+    bool notconv = false, big = false;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        cplxf pv = mkf(1.f), dv = mkf(0.f);
+#pragma unroll
+        for (int k = 1; k <= N; k++) {
+            dv = dv * w[j] + pv;
+            pv = pv * w[j] + cf[k];
+        }
+        cplxf num = mkf(0.f), den = mkf(1.f);
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (k == j) continue;
+            const cplxf d = w[j] - w[k];
+            num = num * d + den;
+            den = den * d;
+        }
+        const cplxf top = pv * den;
+        const cplxf bot = dv * den - pv * num;
+        const float b2 = abs2f(bot);
+        cplxf corr = mkf(0.f);
+        if (b2 > 1e-30f && b2 < 1e30f) corr = __frcp_rn(b2) * (top * conjf_(bot));
+        else big = true;
+        w[j] = w[j] - corr;
+        const float w2 = abs2f(w[j]), c2 = abs2f(corr);
+        notconv = notconv || (c2 > 4e-12f * w2);   // |corr| > 2e-6 |w|
+        big = big || (c2 > 1e-4f * w2) || !(w2 < 1e30f);
+    }
+    return big ? 2 : (notconv ? 1 : 0);
+}
+
+// One Gauss–Seidel Aberth–Ehrlich sweep over all N roots; returns 0 when every correction is below 1e-9 |w_j|
+// (converged), 1 when all are below 1e-2 |w_j| (tracking), 2 otherwise.
+template <int N>
+__device__ __forceinline__ int aberth_sweep(const cplx (&cf)[N + 1], cplx (&w)[N])
+{
+    bool notconv = false, big = false;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        cplx pv, dv;
+        horner2<N>(cf, w[j], pv, dv);
+        // sum_k 1/(w_j - w_k) kept as num/den to spend a single division per root
+        cplx num = mk(0.0, 0.0), den = mk(1.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (k == j) continue;
+            const cplx d = w[j] - w[k];
+            num = num * d + den;
+            den = den * d;
+        }
+        const cplx top = pv * den;
+        const cplx bot = dv * den - pv * num;
+        const double b2 = abs2(bot);
+        cplx corr = mk(0.0, 0.0);
+        if (b2 > 1e-280 && b2 < 1e280) corr = fast_rcp(b2) * (top * conj(bot));
+        else if (b2 > 0.0) corr = (1.0 / b2) * (top * conj(bot));
+        w[j] = w[j] - corr;
+        const double w2 = abs2(w[j]);
+        const double c2 = abs2(corr);
+        notconv = notconv || (c2 > 1e-18 * w2);
+        big = big || (c2 > 1e-4 * w2);
+    }
+    return big ? 2 : (notconv ? 1 : 0);
+}
+
+// Branch selection on |μ|^2 = |β|^2 |w|^2 (findmax / k-th largest; ties: Julia's (re, im) eigenvalue order).
+// gap_out: relative distance of the selected |w|^2 to its nearest neighbour in the ranking.
+template <int N>
+__device__ __forceinline__ int select_root(const cplx (&w)[N], int branch_rank, double &gap_out)
+{
+    double n2[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) n2[j] = abs2(w[j]);
+    int want = branch_rank - 1;   // number of roots ranked above the selected one
+    if (want < 0) want = 0;
+    if (want > N - 1) want = N - 1;
+    int jsel = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        int larger = 0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (k == j) continue;
+            const cplx mj = w[j], mk_ = w[k];
+            bool gt = n2[k] > n2[j];
+            if (n2[k] == n2[j]) {
+                // tie: the reference keeps the first maximum in (real, imag)-sorted order
+                gt = (mk_.re < mj.re) || (mk_.re == mj.re && mk_.im < mj.im) || (mk_.re == mj.re && mk_.im == mj.im && k < j);
+            }
+            larger += gt ? 1 : 0;
+        }
+        if (larger == want) jsel = j;
+    }
+    double nsel = n2[0];
+#pragma unroll
+    for (int j = 1; j < N; j++)
+        if (j == jsel) nsel = n2[j];
+    double gap = 1e300;
+#pragma unroll
+    for (int j = 0; j < N; j++)
+        if (j != jsel) gap = fmin(gap, fabs(n2[j] - nsel));
+    gap_out = (nsel > 0.0) ? gap / nsel : 0.0;
+    return jsel;
+}
+
+// Each thread owns SPT consecutive shifts.  The first one starts cold (roots on a circle); the following ones start
+// from the previous shift's roots, which on a grid are O(Δλ) away: one Aberth sweep re-establishes every root to ~1e-5
+// (enough to rank the moduli unless they nearly tie), then only the selected root is taken to full precision by Newton.
+// Any doubt (large corrections, near-tie in the ranking, slow Newton) falls back to full simultaneous convergence, so
+// the result never depends on the warm start.
 template <int N, bool REAL_PATH, bool WANT_TAIL>
 __global__ void __launch_bounds__(128)
-ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t n, double *__restrict__ L11,
+ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t n, int spt, double *__restrict__ L11,
                        double *__restrict__ tail, int32_t *__restrict__ status)
 {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * spt;
+    if (first >= n) return;
     constexpr int M = N + 1;   // number of symbol coefficients (reference's m)
+    const int64_t last = (first + spt < n) ? first + spt : n;
 
+    cplxf wf[N];                 // FP32 scout roots, carried from shift to shift
+    bool have_roots = false;
+  for (int64_t idx = first; idx < last; idx++) {
     cplx lam;
     if (REAL_PATH) {
         lam = mk(lambda[idx], 0.0);
@@ -72,87 +219,91 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     for (int k = 2; k <= N; k++) g[k] = P.a[N - k] * P.ginv;
     // monic characteristic polynomial of C/β:  P(w) = sum_k (-1)^k g_k w^{N-k}
     cplx cf[N + 1];
+    cplxf cff[N + 1];
 #pragma unroll
-    for (int k = 0; k <= N; k++) cf[k] = (k & 1) ? -g[k] : g[k];
-
-    // ---- initial guesses: circle around the centroid with the geometric-mean radius |P(c)|^(1/N)
-    cplx w[N];
-    {
-        const cplx c = (1.0 / N) * g[1];
-        cplx pc, dc;
-        horner2<N>(cf, c, pc, dc);
-        double rad;   // |P(c)|^(1/N)
-        if (N == 2) rad = sqrt(sqrt(abs2(pc)));
-        else if (N == 4) rad = sqrt(sqrt(sqrt(abs2(pc))));
-        else if (N == 8) rad = sqrt(sqrt(sqrt(sqrt(abs2(pc)))));
-        else rad = pow(abs2(pc), 0.5 / N);
-        if (!(rad > 1e-8)) {
-            double mx = 0.0;
-#pragma unroll
-            for (int k = 1; k <= N; k++) mx = fmax(mx, abs2(g[k]));
-            rad = 1.0 + sqrt(mx);
-        }
-#pragma unroll
-        for (int j = 0; j < N; j++) w[j] = c + rad * P.unit[j];
+    for (int k = 0; k <= N; k++) {
+        cf[k] = (k & 1) ? -g[k] : g[k];
+        cff[k] = mkf((float)cf[k].re, (float)cf[k].im);
     }
 
-    // ---- Aberth–Ehrlich, Gauss–Seidel sweeps
+    // ---- FP32 scout: cold start on a circle around the centroid with the geometric-mean radius |P(c)|^(1/N),
+    //      warm start from the previous shift's roots
+    if (!have_roots) {
+        const cplxf c = (1.0f / N) * mkf((float)g[1].re, (float)g[1].im);
+        cplxf pc = mkf(1.f);
+#pragma unroll
+        for (int k = 1; k <= N; k++) pc = pc * c + cff[k];
+        float rad = powf(abs2f(pc), 0.5f / N);
+        if (!(rad > 1e-4f) || !(rad < 1e15f)) {
+            float mx = 0.f;
+#pragma unroll
+            for (int k = 1; k <= N; k++) mx = fmaxf(mx, abs2f(cff[k]));
+            rad = 1.0f + sqrtf(mx);
+        }
+#pragma unroll
+        for (int j = 0; j < N; j++) wf[j] = c + rad * mkf((float)P.unit[j].re, (float)P.unit[j].im);
+    }
+    int scout = 2;
     for (int it = 0; it < kAberthMaxIt; it++) {
-        bool done = true;
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            cplx pv, dv;
-            horner2<N>(cf, w[j], pv, dv);
-            // sum_k 1/(w_j - w_k) kept as num/den to spend a single division per root
-            cplx num = mk(0.0, 0.0), den = mk(1.0, 0.0);
-#pragma unroll
-            for (int k = 0; k < N; k++) {
-                if (k == j) continue;
-                const cplx d = w[j] - w[k];
-                num = num * d + den;
-                den = den * d;
-            }
-            const cplx top = pv * den;
-            const cplx bot = dv * den - pv * num;
-            const double b2 = abs2(bot);
-            cplx corr = mk(0.0, 0.0);
-            if (b2 > 0.0) corr = (1.0 / b2) * (top * conj(bot));
-            w[j] = w[j] - corr;
-            if (abs2(corr) > 1e-18 * abs2(w[j])) done = false;
-        }
-        if (done) break;
+        scout = aberth_sweep_f32<N>(cff, wf);
+        if (scout == 0) break;
     }
-
-    // ---- branch selection on |μ|^2 = |β w|^2 (findmax / k-th largest; ties: Julia's (re, im) eigenvalue order)
-    int jsel = 0;
-    {
-        double n2[N];
+    cplx w[N];
 #pragma unroll
-        for (int j = 0; j < N; j++) n2[j] = abs2(w[j]);
-        int want = P.branch_rank - 1;   // number of roots strictly "larger" than the selected one
-        if (want < 0) want = 0;
-        if (want > N - 1) want = N - 1;
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            int larger = 0;
-#pragma unroll
-            for (int k = 0; k < N; k++) {
-                if (k == j) continue;
-                const cplx mj = w[j] , mk_ = w[k];
-                bool gt = n2[k] > n2[j];
-                if (n2[k] == n2[j]) {
-                    // tie: the reference keeps the first maximum in (real, imag)-sorted order
-                    gt = (mk_.re < mj.re) || (mk_.re == mj.re && mk_.im < mj.im) || (mk_.re == mj.re && mk_.im == mj.im && k < j);
-                }
-                larger += gt ? 1 : 0;
-            }
-            if (larger == want) jsel = j;
-        }
-    }
+    for (int j = 0; j < N; j++) w[j] = mk((double)wf[j].re, (double)wf[j].im);
+    double gap;
+    int jsel = select_root<N>(w, P.branch_rank, gap);
     cplx ws = w[0];
 #pragma unroll
     for (int j = 1; j < N; j++)
         if (j == jsel) ws = w[j];
+    bool full = (scout != 0) || (gap < 1e-4);
+    bool newton_done = false;
+    if (!full) {
+        // ---- FP64 Newton on the selected root only (1e-7 -> 1e-14 -> rounding level)
+        double c2 = 1.0, w2 = 1.0;
+#pragma unroll
+        for (int it = 0; it < 3; it++) {
+            cplx pv, dv;
+            horner2<N>(cf, ws, pv, dv);
+            const double d2 = abs2(dv);
+            cplx corr = mk(0.0, 0.0);
+            if (d2 > 1e-280 && d2 < 1e280) corr = fast_rcp(d2) * (pv * conj(dv));
+            ws = ws - corr;
+            c2 = abs2(corr);
+            w2 = abs2(ws);
+        }
+        newton_done = (c2 <= 1e-24 * w2);   // the third step must be pure rounding noise
+        full = !newton_done;
+    }
+    if (full) {
+        // ---- FP64 simultaneous solve from the scout's roots (near-tie in the ranking, or the scout/Newton had doubts)
+        if (scout == 2) {
+            // scout lost: restart cold in FP64
+            const cplx c = (1.0 / N) * g[1];
+            cplx pc, dc;
+            horner2<N>(cf, c, pc, dc);
+            double rad = pow(abs2(pc), 0.5 / N);
+            if (!(rad > 1e-8)) {
+                double mx = 0.0;
+#pragma unroll
+                for (int k = 1; k <= N; k++) mx = fmax(mx, abs2(g[k]));
+                rad = 1.0 + sqrt(mx);
+            }
+#pragma unroll
+            for (int j = 0; j < N; j++) w[j] = c + rad * P.unit[j];
+        }
+        for (int it = 0; it < kAberthMaxIt; it++)
+            if (aberth_sweep<N>(cf, w) == 0) break;
+        jsel = select_root<N>(w, P.branch_rank, gap);
+        ws = w[0];
+#pragma unroll
+        for (int j = 1; j < N; j++)
+            if (j == jsel) ws = w[j];
+#pragma unroll
+        for (int j = 0; j < N; j++) wf[j] = mkf((float)w[j].re, (float)w[j].im);
+    }
+    have_roots = true;
 
     int32_t st = ILA_OK;
     if (REAL_PATH) {
@@ -160,9 +311,8 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
         if (!(fabs(ws.im) <= 1e-9 * fabs(ws.re))) st = ILA_NOT_REAL;
         ws.im = 0.0;
     }
-    // one Newton polish of the selected root (the last Aberth correction already is one; this removes
-    // any dependence on the other iterates)
-    {
+    // one Newton polish of the selected root (removes any dependence on the other iterates)
+    if (!newton_done) {
         cplx pv, dv;
         horner2<N>(cf, ws, pv, dv);
         const double d2 = abs2(dv);
@@ -284,6 +434,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
             t[2 * M + 1] = make_double2(tau2.re, tau2.im);
         }
     }
+  }   // next shift of this thread
 }
 
 // ---- host-side launcher -------------------------------------------------------------------------
@@ -305,11 +456,17 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     }
     if (n <= 0) return 0;
     const int threads = 128;
-    const int64_t blocks = (n + threads - 1) / threads;
+    // shifts per thread: consecutive shifts share a warm start; keep >= ~16 warps per SM in flight
+    int spt = (int)(n / (148 * 16 * 32));
+    if (g_tz_spt > 0) spt = g_tz_spt;
+    if (spt < 1) spt = 1;
+    if (spt > 16) spt = 16;
+    const int64_t nthreads = (n + spt - 1) / spt;
+    const int64_t blocks = (nthreads + threads - 1) / threads;
     if (d_tail)
-        ql_toeplitz_l11_kernel<N, REAL_PATH, true><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, d_L11, d_tail, d_status);
+        ql_toeplitz_l11_kernel<N, REAL_PATH, true><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status);
     else
-        ql_toeplitz_l11_kernel<N, REAL_PATH, false><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, d_L11, d_tail, d_status);
+        ql_toeplitz_l11_kernel<N, REAL_PATH, false><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status);
     count_launch();
     ILA_CUDA_CHECK(cudaGetLastError());
     return 0;

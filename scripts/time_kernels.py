@@ -51,3 +51,9 @@ for name, zs in (("64 z in [1e3,1e4]", np.linspace(1e3, 1e4, 64)), ("4096 z in [
     ncols = plan.d_ncols.cpu().numpy(); nsw = plan.d_nswept.cpu().numpy()
     print(f"QR {name}: fwd {mf:.2f} ms bwd {mb:.2f} ms total {mt:.2f} ms; sum ncols {ncols.sum()} swept {nsw.sum()} max {nsw.max()}"
           f" -> {nsw.sum()/mt/1e-3/1e9:.3f} Gcol/s; fwd cycles/col(longest) {mf*1e-3*1.9e9/nsw.max():.0f} bwd {mb*1e-3*1.9e9/nsw.max():.0f}; GB/s {nsw.sum()*72/mt/1e-3/1e9:.0f}")
+
+# K3 shifts-per-thread sweep
+for spt in (1, 2, 4, 8, 16, 0):
+    _lib.check(_lib.lib().ila_ql_set_shifts_per_thread(spt))
+    med, mn = ev_time(f, reps=20)
+    print(f"K3 spt={spt}: median {med*1e3:.1f} us min {mn*1e3:.1f} us -> {lam.numel()/med/1e-3/1e9:.2f} Gpts/s")

@@ -114,13 +114,14 @@ def test_full_grid_properties(ila):
     assert np.all(L[ok].imag == 0) and np.all(L[ok].real <= 0)
     # idempotence / determinism
     L2, st2 = ila.ql_toeplitz_l11(BULLHEAD_COLUMN, lam)
-    assert np.array_equal(st, st2) and np.array_equal(L[ok], L2[ok])
+    assert np.array_equal(st, st2) and np.array_equal(L[ok], L2[ok])      # same launch shape -> same bits
     # sub-grid consistency: every 4th point equals the 256-grid computed separately
     sub = lam[::4, ::4].copy()
     Ls, sts = ila.ql_toeplitz_l11(BULLHEAD_COLUMN, sub)
     assert np.array_equal(sts, st[::4, ::4])
     m = sts == 0
-    assert np.array_equal(Ls[m], L[::4, ::4][m])
+    # (consecutive shifts of a thread share a warm start, so regrouping may move the last bits)
+    assert np.allclose(Ls[m], L[::4, ::4][m], rtol=1e-12, atol=2e-12)
     # |L11|^2 + |a_u|^2 = |mu|^2 where mu solves the symbol equation: check the polynomial residual
     mu2 = L[ok].real ** 2 + 4.0
     assert mu2.min() >= 4.0
