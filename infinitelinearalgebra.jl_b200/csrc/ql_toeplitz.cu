@@ -23,14 +23,6 @@ constexpr int kAberthMaxIt = 48;
 static int g_tz_spt = 0;   // 0 = automatic; set by ila_ql_set_shifts_per_thread (1 = every shift starts cold)
 void tz_set_spt(int v) { g_tz_spt = v; }
 
-template <int N>
-struct TzParams {
-    cplx a[N + 1];     // reversed data column: a[0] = a_{-l}, ..., a[N-1] = a_0, a[N] = a_{+1} = β
-    cplx ginv;         // 1/β
-    cplx unit[N];      // initial directions exp(i(θ0 + 2πj/N))
-    double beta2;      // |β|^2
-    int branch_rank;
-};
 
 // branch-free reciprocal for the root-finder's corrections (MUFU seed + two Newton steps, ~1 ulp): an iteration that
 // converges to the root does not need correctly rounded quotients; the final factors use IEEE division.
@@ -76,6 +68,17 @@ __device__ __forceinline__ cplxf conjf_(cplxf a) { return cplxf{a.re, -a.im}; }
 __device__ __forceinline__ float abs2f(cplxf a) { return a.re * a.re + a.im * a.im; }
 
 template <int N>
+struct TzParams {
+    cplx a[N + 1];     // reversed data column: a[0] = a_{-l}, ..., a[N-1] = a_0, a[N] = a_{+1} = β
+    cplx ginv;         // 1/β
+    cplx cf0[N + 1];   // (-1)^k a_{m-k}/β, k = 0..N, before the shift (only k = 1 moves with λ)
+    cplxf cf0f[N + 1];
+    cplx unit[N];      // initial directions exp(i(θ0 + 2πj/N))
+    double beta2;      // |β|^2
+    int branch_rank;
+};
+
+template <int N>
 __device__ __forceinline__ int aberth_sweep_f32(const cplxf (&cf)[N + 1], cplxf (&w)[N])
 {
     bool notconv = false, big = false;
@@ -103,7 +106,7 @@ __device__ __forceinline__ int aberth_sweep_f32(const cplxf (&cf)[N + 1], cplxf 
         else big = true;
         w[j] = w[j] - corr;
         const float w2 = abs2f(w[j]), c2 = abs2f(corr);
-        notconv = notconv || (c2 > 4e-12f * w2);   // |corr| > 2e-6 |w|
+        notconv = notconv || (c2 > 2.5e-5f * w2);   // |corr| > 5e-3 |w|: the cubic step then lands at ~1e-6 or better
         big = big || (c2 > 1e-4f * w2) || !(w2 < 1e30f);
     }
     return big ? 2 : (notconv ? 1 : 0);
@@ -211,20 +214,20 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     // A - λI: only the diagonal coefficient moves (InfToeplitz - UniformScaling)
     const cplx adiag = P.a[N - 1] - lam;
 
-    // normalised symbol coefficients g_k = a_{m-k}/β, k = 1..N  (c_k of SURVEY A.2 divided by β)
-    cplx g[N + 1];
-    g[0] = mk(1.0, 0.0);
-    g[1] = adiag * P.ginv;
-#pragma unroll
-    for (int k = 2; k <= N; k++) g[k] = P.a[N - k] * P.ginv;
-    // monic characteristic polynomial of C/β:  P(w) = sum_k (-1)^k g_k w^{N-k}
+    // monic characteristic polynomial of C/β:  P(w) = sum_k cf_k w^{N-k},  cf_k = (-1)^k a_{m-k}/β  (SURVEY A.2 with
+    // w = μ/β); only cf_1 = -(a_0 - λ)/β depends on the shift
     cplx cf[N + 1];
     cplxf cff[N + 1];
 #pragma unroll
     for (int k = 0; k <= N; k++) {
-        cf[k] = (k & 1) ? -g[k] : g[k];
-        cff[k] = mkf((float)cf[k].re, (float)cf[k].im);
+        cf[k] = P.cf0[k];
+        cff[k] = P.cf0f[k];
     }
+    cf[1] = cf[1] + lam * P.ginv;
+    cff[1] = mkf((float)cf[1].re, (float)cf[1].im);
+    cplx g[N + 1];   // g_k = (-1)^k cf_k = a_{m-k}/β
+#pragma unroll
+    for (int k = 0; k <= N; k++) g[k] = (k & 1) ? -cf[k] : cf[k];
 
     // ---- FP32 scout: cold start on a circle around the centroid with the geometric-mean radius |P(c)|^(1/N),
     //      warm start from the previous shift's roots
@@ -253,27 +256,38 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     for (int j = 0; j < N; j++) w[j] = mk((double)wf[j].re, (double)wf[j].im);
     double gap;
     int jsel = select_root<N>(w, P.branch_rank, gap);
+    if (scout == 0 && gap < 1e-3) {
+        // near-tie in the ranking: one more (cubic) sweep takes the scout to FP32 precision before deciding
+        scout = aberth_sweep_f32<N>(cff, wf);
+        if (scout != 2) scout = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) w[j] = mk((double)wf[j].re, (double)wf[j].im);
+        jsel = select_root<N>(w, P.branch_rank, gap);
+    }
     cplx ws = w[0];
 #pragma unroll
     for (int j = 1; j < N; j++)
         if (j == jsel) ws = w[j];
-    bool full = (scout != 0) || (gap < 1e-4);
+    bool full = (scout != 0) || (gap < 1e-5);
     bool newton_done = false;
     if (!full) {
-        // ---- FP64 Newton on the selected root only (1e-7 -> 1e-14 -> rounding level)
+        // ---- FP64 Newton on the selected root only (~1e-6 -> 1e-12 -> rounding level); accepted when the last
+        //      correction applied is below 1e-10 |w| (the iterate is then exact to rounding)
         double c2 = 1.0, w2 = 1.0;
 #pragma unroll
         for (int it = 0; it < 3; it++) {
-            cplx pv, dv;
-            horner2<N>(cf, ws, pv, dv);
-            const double d2 = abs2(dv);
-            cplx corr = mk(0.0, 0.0);
-            if (d2 > 1e-280 && d2 < 1e280) corr = fast_rcp(d2) * (pv * conj(dv));
-            ws = ws - corr;
-            c2 = abs2(corr);
-            w2 = abs2(ws);
+            if (it < 2 || c2 > 1e-20 * w2) {
+                cplx pv, dv;
+                horner2<N>(cf, ws, pv, dv);
+                const double d2 = abs2(dv);
+                cplx corr = mk(0.0, 0.0);
+                if (d2 > 1e-280 && d2 < 1e280) corr = fast_rcp(d2) * (pv * conj(dv));
+                ws = ws - corr;
+                c2 = abs2(corr);
+                w2 = abs2(ws);
+            }
         }
-        newton_done = (c2 <= 1e-24 * w2);   // the third step must be pure rounding noise
+        newton_done = (c2 <= 1e-20 * w2);
         full = !newton_done;
     }
     if (full) {
@@ -357,8 +371,8 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
             const double nu = copysign(normu, xi1.re);
             xi1.re += nu;
             X2[N] = mk(-nu, 0.0);
-            X1[N] = X1[N] / xi1;
-            tau2 = xi1 / nu;
+            X1[N] = fast_rcp(abs2(xi1)) * (X1[N] * conj(xi1));
+            tau2 = fast_rcp(nu) * xi1;
 #pragma unroll
             for (int j = 0; j < N; j++) {
                 cplx vA = X2[j] + conj(X1[N]) * X1[j];
@@ -393,7 +407,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
             const double nu = copysign(normu, xi1.re);
             xi1.re += nu;
             X1[N - 1] = mk(-nu, 0.0);
-            tau1 = xi1 / nu;
+            tau1 = fast_rcp(nu) * xi1;
 #pragma unroll
             for (int j = 0; j < N - 1; j++) X1[j] = X1[j] - conj(tau1) * X1[j];
         }
@@ -449,6 +463,14 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     P.ginv = cplx{beta.re / b2, -beta.im / b2};
     P.beta2 = b2;
     P.branch_rank = branch_rank;
+    for (int k = 0; k <= N; k++) {
+        // cf0_k = (-1)^k a_{m-k}/β with a_{m-k} = a_rev[N-k]; cf0_0 = 1
+        cplx v = (k == 0) ? cplx{1.0, 0.0} : cplx{a_rev[N - k].re * P.ginv.re - a_rev[N - k].im * P.ginv.im,
+                                                  a_rev[N - k].re * P.ginv.im + a_rev[N - k].im * P.ginv.re};
+        if (k & 1) v = cplx{-v.re, -v.im};
+        P.cf0[k] = v;
+        P.cf0f[k] = cplxf{(float)v.re, (float)v.im};
+    }
     const double theta0 = 0.7;   // asymmetric start: a conjugate-symmetric start cannot split real root pairs
     for (int j = 0; j < N; j++) {
         const double th = theta0 + 2.0 * 3.14159265358979323846 * j / N;
