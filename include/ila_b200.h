@@ -125,6 +125,26 @@ int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *
                                     const int64_t *d_ncols, const int64_t *d_nswept, const int64_t *d_xoff,
                                     const int32_t *d_status, double *d_x, int64_t xcap, int want_reflectors, void *stream);
 
+/* ---- K5+K2: adaptive banded Cholesky solve  x_i = S_i \ b_i,  S_i symmetric positive definite, banded --------------
+ * Replaces cholesky(S) -> adaptivecholesky (src/infcholesky.jl:71-75), partialcholesky! (:42-59, banded_chol! = LAPACK
+ * pbtrf 'U' per COLGROWTH block + the U1'\B / B'B hand-off), the adaptive L \ b (:94-133, tolerance floatmin, coupling
+ * between chunks) and U \ b (:135-140), fused per instance with on-device convergence detection.
+ * The operator is described by the generators of its UPPER bands only (data rows 0..u <-> diagonals +u..0, same
+ * generator form as the QR entry; position t = row index).  Outputs as for the QR entry; factors_opt is the ragged
+ * (u+1) x ncols[i] column-major band storage of U, y_opt = L \ b before the back-substitution. */
+int ila_chol_banded_solve_f64(int u, int64_t batch, const double *p, const double *q, const double *r,
+                              const double *shift, int hp, const double *head, int nb, const double *b, double tol,
+                              int colgrowth, int64_t ncap, const int64_t *ncap_per, double *x, int64_t xcap,
+                              int64_t *xoff, int64_t *ncols, int64_t *nconv, double *factors_opt, double *y_opt,
+                              int32_t *status, int ngpus);
+/* device-resident phase 1 (phase 2 is ila_qr_banded_backsolve_f64_dev with l = 0: same record layout);
+ * workspace from ila_qr_banded_work_layout(0, u, ...).  full_sweep != 0 factorizes all ncols columns (factor export). */
+int ila_chol_banded_factor_f64_dev(int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                   const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
+                                   double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
+                                   const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
+                                   int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int full_sweep, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,11 @@ SIGNATURES = {
                                           C.c_double, C.c_int, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp,
                                           _vp, _vp, _vp, C.c_int]),
     "ila_qr_set_arith_mode": (C.c_int, [C.c_int]),
+    "ila_chol_banded_solve_f64": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_double,
+                                            C.c_int, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "ila_chol_banded_factor_f64_dev": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp,
+                                                 C.c_double, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                 _vp, C.c_int, _vp]),
     "ila_qr_banded_work_layout": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
     "ila_qr_banded_factor_f64_dev": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int,
                                                _vp, C.c_double, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

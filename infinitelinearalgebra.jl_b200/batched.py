@@ -124,6 +124,54 @@ def qr_banded_solve(l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=FLO
     return out
 
 
+def chol_banded_solve(u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=FLOATMIN, colgrowth=1000, ncap=20_000,
+                      ncap_per=None, batch=None, want_factors=False, ngpus=1, xcap=None):
+    """Batched `cholesky(S_i) \\ b_i` by adaptive banded Cholesky (reference src/infcholesky.jl:42-59,94-140).
+
+    The symmetric operators are described by their UPPER bands (data rows 0..u <-> diagonals +u..0), generators as for
+    `qr_banded_solve`.  Returns dict(x, xflat, xoff, ncols, nconv, status[, factors (ncols x (u+1)), y]).
+    """
+    nd = u + 1
+    if batch is None:
+        batch = int(np.asarray(p).reshape(-1, nd).shape[0])
+    p, q, r, shift, hp, head = _op_arrays(nd, batch, p, q, r, shift, head)
+    b = np.asarray(b, dtype=np.float64)
+    if b.ndim == 1:
+        b = np.broadcast_to(b, (batch, b.shape[0]))
+    b = np.ascontiguousarray(b)
+    nb = b.shape[1]
+    caps = None if ncap_per is None else np.ascontiguousarray(np.asarray(ncap_per, dtype=np.int64))
+    if xcap is None:
+        xcap = int(caps.sum()) if caps is not None else int(batch) * int(ncap)
+    x = np.empty(xcap, dtype=np.float64)
+    xoff = np.zeros(batch + 1, dtype=np.int64)
+    ncols = np.zeros(batch, dtype=np.int64)
+    nconv = np.zeros(batch, dtype=np.int64)
+    status = np.zeros(batch, dtype=np.int32)
+    fac = np.empty(xcap * nd) if want_factors else None
+    y = np.empty(xcap) if want_factors else None
+    check(lib().ila_chol_banded_solve_f64(u, batch, ptr(p), ptr(q), ptr(r), ptr(shift), hp, ptr(head), nb, ptr(b),
+                                          float(tol), int(colgrowth), int(ncap), ptr(caps), ptr(x), xcap, ptr(xoff),
+                                          ptr(ncols), ptr(nconv), ptr(fac), ptr(y), ptr(status), ngpus))
+    out = dict(xflat=x[:xoff[batch]], xoff=xoff, ncols=ncols, nconv=nconv, status=status,
+               x=[x[xoff[i]:xoff[i + 1]] for i in range(batch)])
+    if want_factors:
+        out["factors"] = [fac[xoff[i] * nd:xoff[i + 1] * nd].reshape(-1, nd) for i in range(batch)]
+        out["y"] = [y[xoff[i]:xoff[i + 1]] for i in range(batch)]
+    return out
+
+
+def pentadiagonal_operator(sigma, eps=1e-4):
+    """BASELINE config C4: S_σ = pentadiag(diag 6+σ+ε·k, ±1: -4, ±2: 1), upper bands in data-row order (+2, +1, 0)."""
+    sigma = np.atleast_1d(np.asarray(sigma, dtype=np.float64))
+    batch = sigma.shape[0]
+    p = np.tile(np.array([1.0, -4.0, 6.0]), (batch, 1))
+    p[:, 2] += sigma
+    q = np.zeros((batch, 3))
+    q[:, 2] = eps
+    return p, q
+
+
 class QrBandedPlan:
     """Device-resident two-phase adaptive QR solve (torch tensors as plain device memory).
 

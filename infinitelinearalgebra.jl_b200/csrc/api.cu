@@ -45,16 +45,33 @@ int launch_qr_scan(const int64_t *d_ncols, int64_t batch, int64_t *d_xoff, cudaS
 int launch_qr_backsolve(int l, int u, const QrBwdArgs &a, bool refl, cudaStream_t s);
 int launch_qr_compact(int64_t batch, const int64_t *d_gbase, const double *d_xi, const int64_t *d_ncols,
                       const int64_t *d_nswept, const int64_t *d_xoff, double *d_x, int64_t xcap, cudaStream_t s);
-int launch_qr_export(int l, int u, int64_t batch, const int64_t *d_gbase, const double2 *d_work, const int64_t *d_ncols,
+int launch_qr_export(int l, int u, int has_refl, int64_t batch, const int64_t *d_gbase, const double2 *d_work, const int64_t *d_ncols,
                      const int64_t *d_nswept, const int64_t *d_xoff, double *d_factors, double *d_tau, double *d_qtb,
                      cudaStream_t s);
+
+// from chol_banded.cu
+struct CholFwdArgs {
+    int64_t batch;
+    const double *p, *q, *r, *shift, *head, *b;
+    int hp, nb, colgrowth, full_sweep;
+    double tol;
+    const int64_t *gbase;
+    const int64_t *ncap_per;
+    int64_t ncap;
+    double2 *work;
+    int64_t *ncols, *nconv, *nswept;
+    int32_t *status;
+};
+int launch_chol_forward(int u, const CholFwdArgs &a, cudaStream_t s);
 
 // ---- per-device grow-only buffer pool (host entry points only) ---------------------------------------
 constexpr int kMaxDev = 16;
 constexpr int kSlots = 24;
+constexpr int kPipe = 3;   // copy/compute pipeline depth of the host entry points
 struct DevState {
     bool init = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe[kPipe] = {};
     void *buf[kSlots] = {};
     size_t cap[kSlots] = {};
 };
@@ -66,6 +83,7 @@ static int dev_init(int d)
     ILA_CUDA_CHECK(cudaSetDevice(d));
     if (!g_dev[d].init) {
         ILA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_dev[d].stream, cudaStreamNonBlocking));
+        for (int i = 0; i < kPipe; i++) ILA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_dev[d].pipe[i], cudaStreamNonBlocking));
         g_dev[d].init = true;
     }
     return 0;
@@ -266,19 +284,27 @@ static int ql_toeplitz_host(bool real_path, int l, int u, const double *a, const
         if ((rc = dev_buf_t(pd, 1, (size_t)cnt * w, &d_L))) return rc;
         if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
         if (tail_opt && (rc = dev_buf_t(pd, 3, (size_t)cnt * tl * w, &d_tail))) return rc;
-        cudaStream_t s = g_dev[pd].stream;
-        ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam, lambda + lo * w, sizeof(double) * cnt * w, cudaMemcpyHostToDevice, s));
-        if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam, cnt, d_L, d_tail, d_st, s))) return rc;
-        ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + lo * w, d_L, sizeof(double) * cnt * w, cudaMemcpyDeviceToHost, s));
-        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
-        if (tail_opt)
-            ILA_CUDA_CHECK(cudaMemcpyAsync(tail_opt + lo * tl * w, d_tail, sizeof(double) * cnt * tl * w, cudaMemcpyDeviceToHost, s));
+        // chunked three-stream pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c
+        // (full-duplex PCIe when the caller's buffers are pinned; pageable buffers still work, serialised)
+        const int64_t chunk = cnt > (1 << 18) ? (1 << 17) : cnt;
+        int ci = 0;
+        for (int64_t c0 = 0; c0 < cnt; c0 += chunk, ci++) {
+            const int64_t cc = (c0 + chunk <= cnt) ? chunk : cnt - c0;
+            cudaStream_t s = g_dev[pd].pipe[ci % kPipe];
+            ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam + c0 * w, lambda + (lo + c0) * w, sizeof(double) * cc * w, cudaMemcpyHostToDevice, s));
+            if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam + c0 * w, cc, d_L + c0 * w,
+                                         d_tail ? d_tail + c0 * tl * w : nullptr, d_st + c0, s))) return rc;
+            ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + (lo + c0) * w, d_L + c0 * w, sizeof(double) * cc * w, cudaMemcpyDeviceToHost, s));
+            ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo + c0, d_st + c0, sizeof(int32_t) * cc, cudaMemcpyDeviceToHost, s));
+            if (tail_opt)
+                ILA_CUDA_CHECK(cudaMemcpyAsync(tail_opt + (lo + c0) * tl * w, d_tail + c0 * tl * w, sizeof(double) * cc * tl * w, cudaMemcpyDeviceToHost, s));
+        }
     }
     for (int d = 0; d < G; d++) {
         const int pd = phys(d, G);
         if (!g_dev[pd].init) continue;
         ILA_CUDA_CHECK(cudaSetDevice(pd));
-        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+        for (int i = 0; i < kPipe; i++) ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].pipe[i]));
     }
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
@@ -376,7 +402,23 @@ int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *
     return launch_qr_compact(batch, d_gbase, d_xi, d_ncols, d_nswept, d_xoff, d_x, xcap, (cudaStream_t)stream);
 }
 
-int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const double *q, const double *r,
+int ila_chol_banded_factor_f64_dev(int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                   const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
+                                   double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
+                                   const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
+                                   int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int full_sweep, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0) return set_error(ILA_ERR_ARG, "chol_banded: bad sizes");
+    CholFwdArgs a{batch, d_p, d_q, d_r, d_shift, d_head, d_b, hp, nb, colgrowth, full_sweep, tol, d_gbase, d_ncap_per, ncap,
+                  (double2 *)d_work, d_ncols, d_nconv, d_nswept, d_status};
+    int rc = launch_chol_forward(u, a, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_qr_scan(d_ncols, batch, d_xoff, (cudaStream_t)stream);
+}
+
+// shared host driver of the two adaptive banded solves: kind 0 = QR (K1+K2), kind 1 = Cholesky (K5+K2, l == 0)
+static int banded_solve_host(int kind, int l, int u, int64_t batch, const double *p, const double *q, const double *r,
                             const double *shift, int hp, const double *head, int nb, const double *b, double tol,
                             int colgrowth, int64_t ncap, const int64_t *ncap_per, double *x, int64_t xcap,
                             int64_t *xoff, int64_t *ncols, int64_t *nconv, double *factors_opt, double *tau_opt,
@@ -384,7 +426,8 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
 {
     if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0 || !p || !q || !b || !xoff || !ncols || !nconv || !status || (hp > 0 && !head))
         return set_error(ILA_ERR_ARG, "qr_banded_solve: bad arguments");
-    if (l < 1) return set_error(ILA_ERR_UNSUPPORTED, "qr_banded_solve: l == 0 (triangular operator, Q = I) is not on the accelerated path");
+    if (kind == 0 && l < 1) return set_error(ILA_ERR_UNSUPPORTED, "qr_banded_solve: l == 0 (triangular operator, Q = I) is not on the accelerated path");
+    if (kind == 1 && (tau_opt || l != 0)) return set_error(ILA_ERR_ARG, "chol_banded_solve: bad arguments");
     int G = 0;
     int rc = resolve_ngpus(ngpus, &G);
     if (rc) return rc;
@@ -392,7 +435,8 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
     std::lock_guard<std::mutex> lock(g_mutex);
     if (G > batch) G = (int)batch;
     const int nd = l + u + 1, LD = 2 * l + u + 1;
-    const bool refl = factors_opt || tau_opt;
+    const bool refl = kind == 0 && (factors_opt || tau_opt);
+    const bool want_export = factors_opt || tau_opt || qtb_opt;
     const int REC = qr_record_doubles(l, u, refl);
 
     // round-robin sharding: instance i -> device i % G, local index i / G
@@ -460,8 +504,12 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_b, S.b.data(), sizeof(double) * S.b.size(), cudaMemcpyHostToDevice, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_gbase, S.gbase.data(), sizeof(int64_t) * S.gbase.size(), cudaMemcpyHostToDevice, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_caps, S.caps.data(), sizeof(int64_t) * S.cnt, cudaMemcpyHostToDevice, s));
-        rc = ila_qr_banded_factor_f64_dev(l, u, S.cnt, S.d_p, S.d_q, S.d_r, S.d_shift, hp, S.d_head, nb, S.d_b, tol, colgrowth,
-                                          0, S.d_caps, S.d_gbase, S.d_work, S.d_ncols, S.d_nconv, S.d_nswept, S.d_xoff, S.d_status, refl, s);
+        if (kind == 0)
+            rc = ila_qr_banded_factor_f64_dev(l, u, S.cnt, S.d_p, S.d_q, S.d_r, S.d_shift, hp, S.d_head, nb, S.d_b, tol, colgrowth,
+                                              0, S.d_caps, S.d_gbase, S.d_work, S.d_ncols, S.d_nconv, S.d_nswept, S.d_xoff, S.d_status, refl, s);
+        else
+            rc = ila_chol_banded_factor_f64_dev(u, S.cnt, S.d_p, S.d_q, S.d_r, S.d_shift, hp, S.d_head, nb, S.d_b, tol, colgrowth,
+                                                0, S.d_caps, S.d_gbase, S.d_work, S.d_ncols, S.d_nconv, S.d_nswept, S.d_xoff, S.d_status, want_export ? 1 : 0, s);
         if (rc) return rc;
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.ncols.data(), S.d_ncols, sizeof(int64_t) * S.cnt, cudaMemcpyDeviceToHost, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(S.nconv.data(), S.d_nconv, sizeof(int64_t) * S.cnt, cudaMemcpyDeviceToHost, s));
@@ -500,18 +548,15 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
                                              S.total, refl, s);
         if (rc) return rc;
         S.d_fac = S.d_tau = S.d_qtb = nullptr;
-        if (refl || qtb_opt) {
+        if (want_export) {
+            if (kind == 0 && !refl) return set_error(ILA_ERR_UNSUPPORTED, "qr_banded_solve: qtb_opt requires factors_opt or tau_opt");
             if (factors_opt) {
                 if ((rc = dev_buf_t(pd, 18, (size_t)S.total * LD, &S.d_fac))) return rc;
                 ILA_CUDA_CHECK(cudaMemsetAsync(S.d_fac, 0, sizeof(double) * S.total * LD, s));
             }
             if (tau_opt && (rc = dev_buf_t(pd, 19, (size_t)S.total, &S.d_tau))) return rc;
             if (qtb_opt && (rc = dev_buf_t(pd, 20, (size_t)S.total, &S.d_qtb))) return rc;
-            if (refl) {
-                if ((rc = launch_qr_export(l, u, S.cnt, S.d_gbase, (const double2 *)S.d_work, S.d_ncols, S.d_nswept, S.d_xoff, S.d_fac, S.d_tau, S.d_qtb, s))) return rc;
-            } else {
-                return set_error(ILA_ERR_UNSUPPORTED, "qr_banded_solve: qtb_opt requires factors_opt or tau_opt");
-            }
+            if ((rc = launch_qr_export(l, u, refl ? 1 : 0, S.cnt, S.d_gbase, (const double2 *)S.d_work, S.d_ncols, S.d_nswept, S.d_xoff, S.d_fac, S.d_tau, S.d_qtb, s))) return rc;
         }
         if (G == 1) {
             ILA_CUDA_CHECK(cudaMemcpyAsync(x, S.d_x, sizeof(double) * S.total, cudaMemcpyDeviceToHost, s));
@@ -535,6 +580,27 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
     }
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
+}
+
+int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const double *q, const double *r,
+                            const double *shift, int hp, const double *head, int nb, const double *b, double tol,
+                            int colgrowth, int64_t ncap, const int64_t *ncap_per, double *x, int64_t xcap,
+                            int64_t *xoff, int64_t *ncols, int64_t *nconv, double *factors_opt, double *tau_opt,
+                            double *qtb_opt, int32_t *status, int ngpus)
+{
+    return banded_solve_host(0, l, u, batch, p, q, r, shift, hp, head, nb, b, tol, colgrowth, ncap, ncap_per, x, xcap, xoff,
+                             ncols, nconv, factors_opt, tau_opt, qtb_opt, status, ngpus);
+}
+
+int ila_chol_banded_solve_f64(int u, int64_t batch, const double *p, const double *q, const double *r,
+                              const double *shift, int hp, const double *head, int nb, const double *b, double tol,
+                              int colgrowth, int64_t ncap, const int64_t *ncap_per, double *x, int64_t xcap,
+                              int64_t *xoff, int64_t *ncols, int64_t *nconv, double *factors_opt, double *y_opt,
+                              int32_t *status, int ngpus)
+{
+    if (u < 1) return set_error(ILA_ERR_UNSUPPORTED, "chol_banded_solve: u == 0 (diagonal operator) is not on the accelerated path");
+    return banded_solve_host(1, 0, u, batch, p, q, r, shift, hp, head, nb, b, tol, colgrowth, ncap, ncap_per, x, xcap, xoff,
+                             ncols, nconv, factors_opt, nullptr, y_opt, status, ngpus);
 }
 
 } // extern "C"
