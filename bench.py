@@ -28,15 +28,18 @@ sys.path.insert(0, ROOT)
 BULLHEAD_COLUMN = np.array([2j, 0.0, 0.0, 1.0, 0.7])      # BandedMatrix(-3=>7/10, -2=>1, 1=>2im) data column
 NX = NY = 1024
 BYTES_PER_POINT = 36            # 16 (λ) + 16 (L11) + 4 (status): SURVEY §8d
-FLOPS_PER_POINT = 6.9e3         # LAPACK-style count of the reference's per-λ work
+FLOPS_PER_POINT_LAPACK = 6.9e3  # LAPACK-style count of the reference's per-λ work, for context
+FP64_FLOPS_PER_POINT = 351.0    # FP64 flops this kernel EXECUTES per shift (ncu op counts, profiles/r01_k3_ql_toeplitz_ncu_full.txt)
+K3_DRAM_TRAFFIC = 24.4e6        # dram read+write bytes of one 1024x1024 launch (same capture)
 BYTES_PER_COLUMN = 72           # Bessel (l=u=1): SURVEY §8d
 FLOPS_PER_COLUMN = 42
 
 
 def grid_slab(rank: int, world: int) -> np.ndarray:
-    """Rows [rank*NY, (rank+1)*NY) of the global 1024 x (1024*world) λ grid over the C3 window."""
+    """Rows rank, rank+world, ... of the global 1024 x (1024*world) λ grid over the C3 window (interleaved, so that
+    every rank covers the whole window and the per-GPU work is the same)."""
     x = np.linspace(-10.0, 7.0, NX)
-    y = np.linspace(-7.0, 8.0, NY * world)[rank * NY:(rank + 1) * NY]
+    y = np.linspace(-7.0, 8.0, NY * world)[rank::world]
     return (x[None, :] + 1j * y[:, None]).reshape(-1)
 
 
@@ -264,13 +267,17 @@ def run_ours(args, rank, local_rank, world):
                 "d2h_bytes_per_step": 20 * n, "ms_per_step": e2e_ms, "host_matches_device": same},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved_gbs / hbm_peak, "traffic": K3_DRAM_TRAFFIC if n == NX * NY else None,
+                     "peak_kind": peak_kind,
                      "kernel": "ql_toeplitz_l11_kernel<4,false,false>", "bytes_per_unit": BYTES_PER_POINT,
                      "note": "FP64-pipe bound, not HBM bound: see roofline_fp64"},
-        "roofline_fp64": {"bound": "fp64", "achieved": FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12,
+        "roofline_fp64": {"bound": "fp64", "achieved": FP64_FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12,
                           "peak": fp64_peak, "unit": "TFLOP/s",
-                          "frac": FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12 / fp64_peak,
-                          "flops_per_unit": FLOPS_PER_POINT, "peak_kind": "measured DFMA probe (this run)"},
+                          "frac": FP64_FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12 / fp64_peak,
+                          "flops_per_unit": FP64_FLOPS_PER_POINT, "peak_kind": "measured DFMA probe (this run)",
+                          "note": "executed FP64 flops (ncu); the kernel also runs ~0.8k FP32 instr/shift on the FP32 pipe "
+                                  "and is issue-slot bound (ncu: issue active 69-75 %); the reference's LAPACK path is "
+                                  f"~{FLOPS_PER_POINT_LAPACK:.0f} flop/shift"},
         "clocks": sampler.summary(),
     }
 

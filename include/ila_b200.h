@@ -145,6 +145,21 @@ int ila_chol_banded_factor_f64_dev(int u, int64_t batch, const double *d_p, cons
                                    const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
                                    int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int full_sweep, void *stream);
 
+/* ---- K6: block-tridiagonal perturbed-Toeplitz QL,  L11[i] = ql(A - energy[i]*I).L[1,1] ----------------------------
+ * A = BlockTridiagonal(Vcat(dl_head, Fill(c,∞)), Vcat(d_head, Fill(a,∞)), Vcat(du_head, Fill(b,∞))) with n x n blocks
+ * (column-major; dl = A[Block(k+1,k)], du = A[Block(k,k+1)]; head tables hold n_dl / n_d / n_du blocks, n <= 4,
+ * at most 4 head block columns).  Replaces ql(::BlockTriPertToeplitz) -> _blocktripert_ql (src/infql.jl:189-209):
+ * blocktailiterate (:166-182; dense 2n x 3n Householder QL per iteration, stop when (d,e) move by <= atol, reference
+ * atol = 1e-10, maxit = 1_000_000) and the finite block head QL (:193-198).  iters[i] = fixed-point iterations taken;
+ * status 3 = "Did not converge" (src/infql.jl:181), e.g. inside the essential spectrum. */
+int ila_ql_blocktri_l11_f64(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
+                            int n_d, const double *d_head, int n_du, const double *du_head, const double *energy,
+                            int64_t batch, double atol, int maxit, double *L11, int32_t *iters, int32_t *status, int ngpus);
+int ila_ql_blocktri_l11_f64_dev(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
+                                int n_d, const double *d_head, int n_du, const double *du_head, const double *d_energy,
+                                int64_t batch, double atol, int maxit, double *d_L11, int32_t *d_iters, int32_t *d_status,
+                                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,49 @@ def ql_toeplitz_l11_dev(data_column, d_lambda, d_L11, d_status, branch_rank: int
 
 
 # ------------------------------------------------------------------------------------------------
+# K6: block-tridiagonal Toeplitz-tail QL
+# ------------------------------------------------------------------------------------------------
+
+def _blocks(lst, n):
+    if lst is None or len(lst) == 0:
+        return None, 0
+    arr = np.stack([np.asfortranarray(np.asarray(m, dtype=np.float64)).reshape(-1, order="F") for m in lst])
+    assert arr.shape[1] == n * n
+    return np.ascontiguousarray(arr), len(lst)
+
+
+def ql_blocktri_l11(dl_head, d_head, du_head, c, a, b, energies, atol=1e-10, maxit=1_000_000, ngpus=1):
+    """L[1,1] of ql(A - x*I) over `energies` for the block-tridiagonal perturbed Toeplitz operator
+    A = BlockTridiagonal(Vcat(dl_head, Fill(c,∞)), Vcat(d_head, Fill(a,∞)), Vcat(du_head, Fill(b,∞)))
+    (reference src/infql.jl:166-209; examples/periodicschrodinger.jl:13-27).  Returns (L11, iters, status)."""
+    c = np.asarray(c, dtype=np.float64)
+    n = c.shape[0]
+    flat = lambda m: np.ascontiguousarray(np.asarray(m, dtype=np.float64).reshape(-1, order="F"))
+    cc, aa, bb = flat(c), flat(a), flat(b)
+    dlh, ndl = _blocks(dl_head, n)
+    dh, nd = _blocks(d_head, n)
+    duh, ndu = _blocks(du_head, n)
+    e = np.ascontiguousarray(np.asarray(energies, dtype=np.float64).reshape(-1))
+    L11 = np.empty(e.size)
+    iters = np.empty(e.size, dtype=np.int32)
+    status = np.empty(e.size, dtype=np.int32)
+    check(lib().ila_ql_blocktri_l11_f64(n, ptr(cc), ptr(aa), ptr(bb), ndl, ptr(dlh), nd, ptr(dh), ndu, ptr(duh), ptr(e),
+                                        e.size, float(atol), int(maxit), ptr(L11), ptr(iters), ptr(status), ngpus))
+    shape = np.asarray(energies).shape
+    return L11.reshape(shape), iters.reshape(shape), status.reshape(shape)
+
+
+def periodic_schrodinger_blocks():
+    """Blocks of examples/periodicschrodinger.jl:8-17: (dl_head, d_head, du_head, c, a, b)."""
+    c = np.array([[0.0, 1.0], [0.0, 0.0]])
+    a = np.array([[-1.0, 1.0], [1.0, 1.0]])
+    b = np.array([[0.0, 0.0], [1.0, 0.0]])
+    a0 = a.copy()
+    a0[0, 0] = 2.0
+    return [c], [a0], [b], c, a, b
+
+
+# ------------------------------------------------------------------------------------------------
 # K1+K2: adaptive banded QR solve
 # ------------------------------------------------------------------------------------------------
 

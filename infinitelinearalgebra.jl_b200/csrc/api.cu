@@ -64,6 +64,20 @@ struct CholFwdArgs {
 };
 int launch_chol_forward(int u, const CholFwdArgs &a, cudaStream_t s);
 
+// from ql_blocktri.cu
+constexpr int kBtMaxN = 4;
+constexpr int kBtMaxHead = 4;
+struct BlockTriParams {
+    int n, n_dl, n_d, n_du, maxit;
+    double atol;
+    double c[kBtMaxN * kBtMaxN], a[kBtMaxN * kBtMaxN], b[kBtMaxN * kBtMaxN];
+    double dl_head[kBtMaxHead][kBtMaxN * kBtMaxN];
+    double d_head[kBtMaxHead][kBtMaxN * kBtMaxN];
+    double du_head[kBtMaxHead][kBtMaxN * kBtMaxN];
+};
+int launch_ql_blocktri(const BlockTriParams &P, const double *d_energy, int64_t batch, double *d_L11, int32_t *d_iters,
+                       int32_t *d_status, cudaStream_t s);
+
 // ---- per-device grow-only buffer pool (host entry points only) ---------------------------------------
 constexpr int kMaxDev = 16;
 constexpr int kSlots = 24;
@@ -336,6 +350,83 @@ int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_l
 {
     if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
     return launch_ql_toeplitz(true, l, u, a, branch_rank, d_lambda, n, d_L11, d_tail_opt, d_status, (cudaStream_t)stream);
+}
+
+// ================================ K6: block-tridiagonal Toeplitz-tail QL ================================
+
+static int blocktri_params(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
+                           int n_d, const double *d_head, int n_du, const double *du_head, double atol, int maxit,
+                           BlockTriParams *P)
+{
+    if (n < 1 || n > kBtMaxN) return set_error(ILA_ERR_UNSUPPORTED, "ql_blocktri: block size n must be in 1..4");
+    if (n_dl < 0 || n_d < 0 || n_du < 0 || n_dl > kBtMaxHead || n_d > kBtMaxHead || n_du + 1 > kBtMaxHead)
+        return set_error(ILA_ERR_UNSUPPORTED, "ql_blocktri: at most 4 head block columns");
+    if (!c || !a || !b || (n_dl && !dl_head) || (n_d && !d_head) || (n_du && !du_head) || maxit < 1)
+        return set_error(ILA_ERR_ARG, "ql_blocktri: bad arguments");
+    memset(P, 0, sizeof(*P));
+    P->n = n; P->n_dl = n_dl; P->n_d = n_d; P->n_du = n_du; P->maxit = maxit; P->atol = atol;
+    const int nn = n * n;
+    memcpy(P->c, c, sizeof(double) * nn);
+    memcpy(P->a, a, sizeof(double) * nn);
+    memcpy(P->b, b, sizeof(double) * nn);
+    for (int k = 0; k < n_dl; k++) memcpy(P->dl_head[k], dl_head + k * nn, sizeof(double) * nn);
+    for (int k = 0; k < n_d; k++) memcpy(P->d_head[k], d_head + k * nn, sizeof(double) * nn);
+    for (int k = 0; k < n_du; k++) memcpy(P->du_head[k], du_head + k * nn, sizeof(double) * nn);
+    return 0;
+}
+
+int ila_ql_blocktri_l11_f64_dev(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
+                                int n_d, const double *d_head, int n_du, const double *du_head, const double *d_energy,
+                                int64_t batch, double atol, int maxit, double *d_L11, int32_t *d_iters, int32_t *d_status,
+                                void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    BlockTriParams P;
+    int rc = blocktri_params(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, atol, maxit, &P);
+    if (rc) return rc;
+    return launch_ql_blocktri(P, d_energy, batch, d_L11, d_iters, d_status, (cudaStream_t)stream);
+}
+
+int ila_ql_blocktri_l11_f64(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
+                            int n_d, const double *d_head, int n_du, const double *du_head, const double *energy,
+                            int64_t batch, double atol, int maxit, double *L11, int32_t *iters, int32_t *status, int ngpus)
+{
+    if (batch < 0 || (batch > 0 && (!energy || !L11 || !iters || !status))) return set_error(ILA_ERR_ARG, "ql_blocktri: bad arguments");
+    BlockTriParams P;
+    int rc = blocktri_params(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, atol, maxit, &P);
+    if (rc) return rc;
+    int G = 0;
+    if ((rc = resolve_ngpus(ngpus, &G))) return rc;
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int64_t per = (batch + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= batch ? per : batch - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        double *d_e, *d_L;
+        int32_t *d_it, *d_st;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt, &d_e))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt, &d_L))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
+        if ((rc = dev_buf_t(pd, 3, (size_t)cnt, &d_it))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_e, energy + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+        if ((rc = launch_ql_blocktri(P, d_e, cnt, d_L, d_it, d_st, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + lo, d_L, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(iters + lo, d_it, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
 }
 
 int ila_ql_set_shifts_per_thread(int spt)

@@ -1,0 +1,79 @@
+"""Parity of the CUDA block-tridiagonal Toeplitz-tail QL (K6) against the numpy oracle, through the C ABI.
+Bar: bit-exact L[1,1] and identical iteration counts (same operation order, no FMA, IEEE sqrt/div)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_periodic_schrodinger_bit_exact(ila):
+    from oracle import block_ql as bq
+    xx = np.concatenate([np.arange(-0.95, 0.951, 0.05), np.arange(2.25, 4.0001, 0.125 / 4)])
+    blocks = ila.periodic_schrodinger_blocks()
+    L, it, st = ila.ql_blocktri_l11(*blocks, xx)
+    ref = [bq.periodic_schrodinger(x) for x in xx]
+    assert np.all(st == 0)
+    assert np.array_equal(it, [r[1] for r in ref])
+    assert np.array_equal(L, [r[0] for r in ref])
+    assert it.min() == 7 and it.max() == 51
+
+
+def test_block_sizes_and_heads_bit_exact(ila):
+    from oracle import block_ql as bq
+    # degenerate 2x2 (test_periodic.jl:28-34)
+    c2, a2, b2 = np.array([[0, 0.5], [0, 0]]), np.array([[0, 2.0], [0.5, 0]]), np.array([[0, 0.0], [2.0, 0]])
+    L, it, st = ila.ql_blocktri_l11([c2], [a2], [b2], c2, a2, b2, [0.0])
+    r = bq.blocktri_ql_l11([c2], [a2], [b2], c2, a2, b2)
+    assert st[0] == 0 and it[0] == r[1] and L[0] == r[0] and abs(L[0]) <= 1e-11
+    # 4x4 blocks (test_periodic.jl:42-60)
+    B = np.array([[0, 0, 1, 0], [0, 0, 0, 1], [0, 0, 0, 0], [0, 0, 0, 0]]) / 2
+    A0 = np.array([[1, .5, .5, 0], [.5, -1, 0, .5], [.5, 0, -1, 0], [0, .5, 0, 1.0]])
+    A = np.array([[1, 0, .5, 0], [0, -1, 0, .5], [.5, 0, -1, 0], [0, .5, 0, 1.0]])
+    xs = np.array([0.0, 2.5, -2.5, 3.0])
+    L, it, st = ila.ql_blocktri_l11([B], [A0], [B.T.copy()], B, A, B.T.copy(), xs)
+    for i, x in enumerate(xs):
+        r = bq.blocktri_ql_l11([B], [A0], [B.T.copy()], B, A, B.T.copy(), shift=x)
+        assert st[i] == r[2]
+        if r[2] == 0:
+            assert it[i] == r[1] and L[i] == r[0]
+    # scalar blocks (n = 1) with a longer head: a tridiagonal operator seen as 1x1 blocks
+    rng = np.random.default_rng(5)
+    dl = [np.array([[0.7]]), np.array([[1.1]])]
+    d = [np.array([[v]]) for v in rng.normal(size=3)]
+    du = [np.array([[0.4]])]
+    c, a, b = np.array([[1.0]]), np.array([[0.2]]), np.array([[0.5]])
+    xs = np.array([3.0, -3.5, 4.0 ])
+    L, it, st = ila.ql_blocktri_l11(dl, d, du, c, a, b, xs)
+    for i, x in enumerate(xs):
+        r = bq.blocktri_ql_l11(dl, d, du, c, a, b, shift=x)
+        assert st[i] == 0 and it[i] == r[1] and L[i] == r[0]
+
+
+def test_not_converged_inside_spectrum(ila):
+    # inside the essential spectrum the iteration never settles: "Did not converge" (src/infql.jl:181) -> status 3
+    blocks = ila.periodic_schrodinger_blocks()
+    L, it, st = ila.ql_blocktri_l11(*blocks, [1.5], maxit=2000)
+    assert st[0] == 3 and np.isnan(L[0]) and it[0] == 2000
+
+
+def test_c5_full_size_properties(ila):
+    """BASELINE config C5 (512 energies in [-0.95,0.95] ∪ [2.25,4.0]): determinism, gap symmetry, finite-section check."""
+    from oracle import toeplitz_ql as tq
+    xs = np.concatenate([np.linspace(-0.95, 0.95, 256), np.linspace(2.25, 4.0, 256)])
+    blocks = ila.periodic_schrodinger_blocks()
+    L, it, st = ila.ql_blocktri_l11(*blocks, xs)
+    L2, it2, st2 = ila.ql_blocktri_l11(*blocks, xs)
+    assert np.all(st == 0) and np.array_equal(L, L2) and np.array_equal(it, it2)
+    assert it.max() < 200
+    dl, d, du = blocks[3], blocks[4], blocks[5]
+    for i in (0, 255, 300, 511):
+        nb, n = 120, 2
+        A = np.zeros((nb * n, nb * n))
+        for k in range(nb):
+            A[k * n:(k + 1) * n, k * n:(k + 1) * n] = d - xs[i] * np.eye(n)
+            if k < nb - 1:
+                A[k * n:(k + 1) * n, (k + 1) * n:(k + 2) * n] = du
+                A[(k + 1) * n:(k + 2) * n, k * n:(k + 1) * n] = dl
+        A[0, 0] = 2.0 - xs[i]
+        F, _ = tq.dense_ql(A)
+        assert np.isclose(L[i], F[0, 0], atol=5e-9)
