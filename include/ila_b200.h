@@ -70,6 +70,19 @@ int ila_ql_toeplitz_l11_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d
 int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank,
                                 double *d_L11, double *d_tail_opt, int32_t *d_status, void *stream);
 
+/* ---- K3+K4: perturbed Toeplitz, u == 1:  L11[i] = ql(A - lambda[i]*I).L[1,1],  A = finite head + Toeplitz tail ----
+ * Replaces ql(::PertToeplitz) -> ql_hessenberg!(B) (src/infql.jl:60-93): tail fixed point (K3), last head row rebuilt
+ * from row 1 of Q∞' (:81-82), finite Householder QL of the p x p head (:83).
+ *   head   p x p top-left corner of A (column-major, WITHOUT the shift), l+1 <= p <= 8; row p of A must already be pure
+ *          Toeplitz (the reference takes p from InfiniteArrays' PertToeplitz constructor — SURVEY A.3)
+ *   a      l+u+1 tail coefficients in BandedMatrices data-column order (as for ila_ql_toeplitz_l11_*)
+ *   head_factors_opt  NULL or n x (p x p): the factored head (L in the lower triangle, reflectors above)
+ */
+int ila_ql_perttoeplitz_l11_c64(int l, int u, int p, const ila_c64 *head, const ila_c64 *a, const ila_c64 *lambda, int64_t n,
+                                int branch_rank, ila_c64 *L11, ila_c64 *head_factors_opt, int32_t *status, int ngpus);
+int ila_ql_perttoeplitz_l11_f64(int l, int u, int p, const double *head, const double *a, const double *lambda, int64_t n,
+                                int branch_rank, double *L11, double *head_factors_opt, int32_t *status, int ngpus);
+
 /* Shifts per thread of the K3 kernel: consecutive shifts of one thread warm-start the root finder from the previous
  * shift's roots (any doubt falls back to a cold simultaneous solve, so results do not depend on it).
  * 0 = automatic (default), 1 = every shift cold. */

@@ -61,6 +61,35 @@ def ql_toeplitz_l11_dev(data_column, d_lambda, d_L11, d_status, branch_rank: int
     check(fn(l, 1, ptr(col), ptr(d_lambda), n, branch_rank, ptr(d_L11), ptr(d_tail), ptr(d_status), s))
 
 
+def ql_perttoeplitz_l11(head, data_column, lambdas, branch_rank: int = 1, want_head_factors: bool = False,
+                        ngpus: int = 1, real_path: bool | None = None):
+    """L[1,1] of ql(A - λI) for a perturbed Toeplitz A (bandwidths (l,1)): `head` is the dense p x p top-left corner
+    of A, `data_column` the Toeplitz tail column [a_{+1}, a_0, ..., a_{-l}] (reference src/infql.jl:60-93).
+    Returns (L11, status[, head_factors (..., p, p)])."""
+    col = np.asarray(data_column)
+    head = np.asarray(head)
+    lam = np.asarray(lambdas)
+    if real_path is None:
+        real_path = not (np.iscomplexobj(col) or np.iscomplexobj(lam) or np.iscomplexobj(head))
+    dt = np.float64 if real_path else np.complex128
+    col = np.ascontiguousarray(col, dtype=dt)
+    p = head.shape[0]
+    hflat = np.ascontiguousarray(np.asarray(head, dtype=dt).reshape(-1, order="F"))
+    shape = lam.shape
+    lam = np.ascontiguousarray(lam, dtype=dt).reshape(-1)
+    n = lam.size
+    l = col.size - 2
+    L11 = np.empty(n, dtype=dt)
+    status = np.empty(n, dtype=np.int32)
+    hf = np.empty((n, p * p), dtype=dt) if want_head_factors else None
+    fn = lib().ila_ql_perttoeplitz_l11_f64 if real_path else lib().ila_ql_perttoeplitz_l11_c64
+    check(fn(l, 1, p, ptr(hflat), ptr(col), ptr(lam), n, branch_rank, ptr(L11), ptr(hf), ptr(status), ngpus))
+    res = (L11.reshape(shape), status.reshape(shape))
+    if want_head_factors:
+        res = res + (hf.reshape(shape + (p, p)).swapaxes(-1, -2),)     # column-major -> [i, j]
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 # K6: block-tridiagonal Toeplitz-tail QL
 # ------------------------------------------------------------------------------------------------

@@ -15,6 +15,9 @@ int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int b
                        int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream);
 
 void tz_set_spt(int v);
+int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
+                        int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
+                        cudaStream_t stream);
 
 // from qr_banded.cu
 struct QrFwdArgs {
@@ -350,6 +353,65 @@ int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_l
 {
     if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
     return launch_ql_toeplitz(true, l, u, a, branch_rank, d_lambda, n, d_L11, d_tail_opt, d_status, (cudaStream_t)stream);
+}
+
+// ================================ K4: perturbed-Toeplitz head ==========================================
+
+static int ql_pert_host(bool real_path, int l, int u, int p, const double *head, const double *a, const double *lambda,
+                        int64_t n, int branch_rank, double *L11, double *head_factors_opt, int32_t *status, int ngpus)
+{
+    if (n < 0 || !a || !head || (n > 0 && (!lambda || !L11 || !status))) return set_error(ILA_ERR_ARG, "ql_perttoeplitz: bad arguments");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    const int w = real_path ? 1 : 2;
+    const int m = l + 2, tl = 2 * m + 2;
+    if (G > n) G = (int)n;
+    const int64_t per = (n + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= n ? per : n - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        double *d_lam, *d_L, *d_tail, *d_hf = nullptr;
+        int32_t *d_st;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt * w, &d_lam))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt * w, &d_L))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
+        if ((rc = dev_buf_t(pd, 3, (size_t)cnt * tl * w, &d_tail))) return rc;
+        if (head_factors_opt && (rc = dev_buf_t(pd, 23, (size_t)cnt * p * p * w, &d_hf))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam, lambda + lo * w, sizeof(double) * cnt * w, cudaMemcpyHostToDevice, s));
+        if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam, cnt, d_L, d_tail, d_st, s))) return rc;
+        if ((rc = launch_ql_pert_head(real_path, l, p, a, head, d_lam, cnt, d_tail, d_st, d_L, d_hf, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + lo * w, d_L, sizeof(double) * cnt * w, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+        if (head_factors_opt)
+            ILA_CUDA_CHECK(cudaMemcpyAsync(head_factors_opt + lo * p * p * w, d_hf, sizeof(double) * cnt * p * p * w, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
+int ila_ql_perttoeplitz_l11_c64(int l, int u, int p, const ila_c64 *head, const ila_c64 *a, const ila_c64 *lambda, int64_t n,
+                                int branch_rank, ila_c64 *L11, ila_c64 *head_factors_opt, int32_t *status, int ngpus)
+{
+    return ql_pert_host(false, l, u, p, (const double *)head, (const double *)a, (const double *)lambda, n, branch_rank,
+                        (double *)L11, (double *)head_factors_opt, status, ngpus);
+}
+
+int ila_ql_perttoeplitz_l11_f64(int l, int u, int p, const double *head, const double *a, const double *lambda, int64_t n,
+                                int branch_rank, double *L11, double *head_factors_opt, int32_t *status, int ngpus)
+{
+    return ql_pert_host(true, l, u, p, head, a, lambda, n, branch_rank, L11, head_factors_opt, status, ngpus);
 }
 
 // ================================ K6: block-tridiagonal Toeplitz-tail QL ================================

@@ -530,4 +530,120 @@ int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int b
                      : launch_any<false>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
 }
 
+
+// ---- K4: perturbed-Toeplitz head ---------------------------------------------------------------------------
+// ql_hessenberg!(B) (src/infql.jl:70-93) for A = finite head + Toeplitz tail, bandwidths (l, 1): the tail fixed point
+// comes from the K3 kernel above (its `tail` output: X[1,:], X[2,:], tau); this kernel forms row 1 of Q∞' from the
+// 2x2 block q = QLPackedQ(X[:, m-1:m], tau)  ((Q∞')[1,j] = conj(q11 q21^(j-1)), src/banded/hessenbergq.jl:125-135,162),
+// overwrites the last row of the p x p head  (B~[p,p] = L∞[1,1],  B~[p, p-l'+1:p-1] = (Q∞')[1,1:l'-1] T[l':2(l'-1),1:l'-1],
+// src/infql.jl:81-82) and runs the finite Householder QL of the head (src/infql.jl:83); L[1,1] = factors[1,1].
+constexpr int kHeadMax = 8;
+
+struct TzHeadParams {
+    int N, p;                              // N = l + 1 = l' ; head is p x p, p >= l'
+    cplx a_rev[kMaxDeg + 1];               // unshifted tail symbol a_{-l} .. a_{+1}
+    cplx h[kHeadMax * kHeadMax];           // unshifted p x p top-left corner of A, column-major
+};
+
+template <bool REAL_PATH>
+__global__ void __launch_bounds__(128)
+ql_pert_head_kernel(TzHeadParams H, const double *__restrict__ lambda, int64_t n, const double *__restrict__ tail,
+                    const int32_t *__restrict__ status, double *__restrict__ L11, double *__restrict__ head_factors)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int N = H.N, M = N + 1, p = H.p, W = REAL_PATH ? 1 : 2;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    auto put = [&](cplx v) {
+        if (REAL_PATH) L11[idx] = v.re;
+        else reinterpret_cast<double2 *>(L11)[idx] = make_double2(v.re, v.im);
+    };
+    if (status[idx] != ILA_OK) { put(mk(qnan, qnan)); return; }
+    const double *t = tail + idx * (2 * M + 2) * W;
+    auto tl = [&](int k) -> cplx { return REAL_PATH ? mk(t[k], 0.0) : mk(t[2 * k], t[2 * k + 1]); };
+    const cplx lam = REAL_PATH ? mk(lambda[idx], 0.0) : mk(lambda[2 * idx], lambda[2 * idx + 1]);
+    const cplx l11inf = tl(N - 1), v = tl(N), tau1 = tl(2 * M), tau2 = tl(2 * M + 1);
+    // q = H_2 H_1,  H_1 = diag(1 - tau1, 1),  H_2 = I - tau2 [v;1][v;1]'
+    const cplx one = mk(1.0, 0.0);
+    const cplx s1 = one - tau1;
+    const cplx q11 = (one - abs2(v) * tau2) * s1;
+    const cplx q21 = (-(conj(v) * tau2)) * s1;
+    cplx B[kHeadMax][kHeadMax];
+    for (int j = 0; j < p; j++)
+        for (int i = 0; i < p; i++) {
+            cplx e = H.h[i + j * p];
+            if (i == j) e = e - lam;
+            B[i][j] = e;
+        }
+    B[p - 1][p - 1] = l11inf;
+    {
+        cplx qrow[kMaxDeg];
+        cplx pw = q11;
+        for (int j = 0; j < N - 1; j++) { qrow[j] = conj(pw); pw = pw * q21; }
+        for (int jj = 0; jj < N - 1; jj++) {
+            cplx acc = mk(0.0, 0.0);
+            for (int ii = 0; ii <= jj; ii++) acc = acc + qrow[ii] * H.a_rev[jj - ii];   // T[l'-1+ii+1, jj+1] = a_rev[jj-ii]
+            B[p - 1][p - N + jj] = acc;
+        }
+    }
+    // finite Householder QL of the head (reference loop: k = p..1 complex, p..2 real)
+    for (int k = p; k >= (REAL_PATH ? 2 : 1); k--) {
+        double s = abs2(B[k - 1][k - 1]);
+        for (int i = 1; i < k; i++) s += abs2(B[k - 1 - i][k - 1]);
+        const double normu = sqrt(s);
+        cplx tk = mk(0.0, 0.0);
+        if (normu != 0.0) {
+            cplx xi1 = B[k - 1][k - 1];
+            const double nu = copysign(normu, xi1.re);
+            xi1.re += nu;
+            B[k - 1][k - 1] = mk(-nu, 0.0);
+            const double r2 = 1.0 / abs2(xi1);
+            for (int i = 1; i < k; i++) B[k - 1 - i][k - 1] = r2 * (B[k - 1 - i][k - 1] * conj(xi1));
+            tk = (1.0 / nu) * xi1;
+        }
+        for (int j = 0; j < k - 1; j++) {
+            cplx vA = B[k - 1][j];
+            for (int i = 1; i < k; i++) vA = vA + conj(B[k - 1 - i][k - 1]) * B[k - 1 - i][j];
+            vA = conj(tk) * vA;
+            B[k - 1][j] = B[k - 1][j] - vA;
+            for (int i = 1; i < k; i++) B[k - 1 - i][j] = B[k - 1 - i][j] - B[k - 1 - i][k - 1] * vA;
+        }
+    }
+    put(B[0][0]);
+    if (head_factors) {
+        double *o = head_factors + idx * (int64_t)p * p * W;
+        for (int j = 0; j < p; j++)
+            for (int i = 0; i < p; i++) {
+                if (REAL_PATH) o[i + j * p] = B[i][j].re;
+                else { o[2 * (i + j * p)] = B[i][j].re; o[2 * (i + j * p) + 1] = B[i][j].im; }
+            }
+    }
+}
+
+// head_host: p x p column-major top-left corner of A (no shift), same scalar type as the symbol
+int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
+                        int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
+                        cudaStream_t stream)
+{
+    if (p < l + 1 || p > kHeadMax) return set_error(ILA_ERR_UNSUPPORTED, "ql_perttoeplitz: head size p must satisfy l+1 <= p <= 8");
+    TzHeadParams H;
+    memset(&H, 0, sizeof(H));
+    H.N = l + 1;
+    H.p = p;
+    const int m = l + 2;
+    for (int j = 0; j < m; j++) {
+        const int src = m - 1 - j;
+        H.a_rev[j] = real_path ? cplx{a_host[src], 0.0} : cplx{a_host[2 * src], a_host[2 * src + 1]};
+    }
+    for (int k = 0; k < p * p; k++) H.h[k] = real_path ? cplx{head_host[k], 0.0} : cplx{head_host[2 * k], head_host[2 * k + 1]};
+    if (n <= 0) return 0;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    if (real_path) ql_pert_head_kernel<true><<<blocks, threads, 0, stream>>>(H, d_lambda, n, d_tail, d_status, d_L11, d_head_factors);
+    else ql_pert_head_kernel<false><<<blocks, threads, 0, stream>>>(H, d_lambda, n, d_tail, d_status, d_L11, d_head_factors);
+    count_launch();
+    ILA_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 } // namespace ila

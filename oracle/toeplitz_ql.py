@@ -268,3 +268,67 @@ def ql_packed_Q(factors, tau):
         H = np.eye(m, dtype=factors.dtype) - tau[k - 1] * np.outer(v, np.conj(v))
         Q = H @ Q
     return Q
+
+
+# ----------------------------------------------------------------------------------------------
+# perturbed Toeplitz head: ql_hessenberg!(B)  (src/infql.jl:60-93), u == 1
+# ----------------------------------------------------------------------------------------------
+
+def _toeplitz_entry(a_rev, i, j):
+    """T[i,j] (1-based) of the Toeplitz tail with reversed coefficient vector a_rev = [a_{-l},...,a_0,a_{+1}]."""
+    m = len(a_rev)
+    k = (j - i) + m - 2
+    return a_rev[k] if 0 <= k < m else 0.0
+
+
+def ql_pert_toeplitz(head, a_rev, real_path=None, branch_rank=1):
+    """`ql_hessenberg!` restated for a perturbed Toeplitz operator with bandwidths (l, 1).
+
+    head : p x p top-left corner of A (dense), p >= l + 1; row p of A must already be pure Toeplitz
+    a_rev: tail symbol [a_{-l}, ..., a_0, a_{+1}] (shift already applied to head and a_rev by the caller)
+    Returns dict(L11, head_factors (p x p, L in the lower triangle), head_tau, tail=..., status).
+    """
+    head = np.array(head, copy=True)
+    a_rev = np.asarray(a_rev)
+    if real_path is None:
+        real_path = not (np.iscomplexobj(head) or np.iscomplexobj(a_rev))
+    dt = np.float64 if real_path else np.complex128
+    head = head.astype(dt)
+    a_rev = a_rev.astype(dt)
+    p = head.shape[0]
+    m = len(a_rev)
+    lp = m - 1                                   # l' = l + u: lower bandwidth after widening (infql.jl:60)
+    tail = ql_toeplitz_tail(a_rev, branch_rank, real_path)
+    if tail["status"] != 0:
+        return dict(L11=np.nan, status=int(tail["status"]), tail=tail)
+    X, tau = tail["X"], tail["tau"]
+    # 2x2 block q = QLPackedQ(X[:, m-1:m], tau) = H_2 H_1  (infqltoeplitz.jl:64)
+    q = ql_packed_Q(X[:, m - 2:m].astype(dt), tau.astype(dt))
+    # (Q∞')[1, j] = conj(q11 q21^(j-1))   (LowerHessenbergQ with every block equal to q, hessenbergq.jl:111-135,162)
+    qrow = np.array([np.conj(q[0, 0] * q[1, 0] ** (j - 1)) for j in range(1, lp)], dtype=dt)
+    Bt = head.copy()
+    Bt[p - 1, p - 1] = tail["L11"]
+    if lp > 1:
+        Tblk = np.array([[_toeplitz_entry(a_rev, lp - 1 + ii, jj) for jj in range(1, lp)] for ii in range(1, lp)], dtype=dt)
+        Bt[p - 1, p - lp:p - 1] = qrow @ Tblk     # infql.jl:82
+    F, ftau = dense_ql(Bt)                        # infql.jl:83 (banded ql!: zeros outside the band stay zero)
+    return dict(L11=F[0, 0], head_factors=F, head_tau=ftau, tail=tail, status=0)
+
+
+def pert_toeplitz_head(head_data, a_col, p=None):
+    """Dense p x p top-left corner from BandedMatrices data (l+2) x p_head (rows: +1, 0, -1, ..., -l), continued by
+    the Toeplitz column a_col when p exceeds the head width."""
+    head_data = np.asarray(head_data)
+    a_col = np.asarray(a_col)
+    nrow, ph = head_data.shape
+    if p is None:
+        p = max(ph, nrow - 1)
+    dt = np.result_type(head_data.dtype, a_col.dtype)
+    H = np.zeros((p, p), dtype=dt)
+    for j in range(p):
+        col = head_data[:, j] if j < ph else a_col
+        for r in range(nrow):
+            i = j + r - 1          # data row r <-> diagonal d = 1 - r, row index i = j - d
+            if 0 <= i < p:
+                H[i, j] = col[r]
+    return H
