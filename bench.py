@@ -38,9 +38,8 @@ FLOPS_PER_COLUMN = 42
 def grid_slab(rank: int, world: int) -> np.ndarray:
     """Rows rank, rank+world, ... of the global 1024 x (1024*world) λ grid over the C3 window (interleaved, so that
     every rank covers the whole window and the per-GPU work is the same)."""
-    x = np.linspace(-10.0, 7.0, NX)
-    y = np.linspace(-7.0, 8.0, NY * world)[rank::world]
-    return (x[None, :] + 1j * y[:, None]).reshape(-1)
+    import ila_b200
+    return ila_b200.sharding.grid_rows(NX, NY * world, rank, world)
 
 
 def c2_z():

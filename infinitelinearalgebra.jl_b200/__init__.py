@@ -8,7 +8,7 @@ The directory name contains a dot, so import it through the top-level alias modu
 Contents: `csrc/` (hand-written sm_100a CUDA + the C ABI of include/ila_b200.h), `_lib` (ctypes binding),
 `batched` (batched numpy/torch-pointer entry points), `api` (host-side mirror of the reference's Julia interface).
 """
-from . import _lib
+from . import _lib, api, sharding
 from ._lib import IlaError, SO_PATH, build, lib
 from .batched import (FLOATMIN, QrBandedPlan, bessel_ncap, bessel_operator, chol_banded_solve, pentadiagonal_operator, fp64_peak_tflops, periodic_schrodinger_blocks, ql_blocktri_l11, ql_perttoeplitz_l11, ql_toeplitz_l11,
                       ql_toeplitz_l11_dev, qr_banded_solve)

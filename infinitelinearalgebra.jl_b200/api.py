@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference's Julia interface for the hot path (names, argument meaning, error behaviour).
+
+Julia is not available in this image, so this thin Python layer plays the role of the `ccall` shim
+(`julia/ILAB200.jl`): it only describes operators symbolically and marshals them to the C ABI; every factorization
+runs in the CUDA library.  The spelling follows the reference so that tests read like its own:
+
+    A = BandedMatrix({-3: Fill(7/10), -2: Fill(1), 1: Fill(2j)})          # README.md:83-85
+    ql(A - 5*I).L[1, 1]                                                    # src/banded/infqltoeplitz.jl:191
+    ql_L11(A, lambdas)                                                     # batched form over a vector of shifts
+    A = BandedMatrix({0: Affine(0, -2, z), 1: Ones(), -1: Ones()})        # README.md:41
+    J = qr(A) / Vcat([besselj1], Zeros())    ( `A \\ b` is spelled  qr(A).solve(b)  or  ldiv(A, b) )
+    cholesky(S).solve(b)                                                   # src/infcholesky.jl:71-75
+    ql(BlockTridiagonal(...) - x*I).L[1, 1]                                # src/infql.jl:207
+
+Indices in `.L[i, j]` / `.Q[i, j]` are 1-based like the reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import batched as _b
+
+
+class DomainError(ValueError):
+    """The reference's DomainError (src/banded/infqltoeplitz.jl:12-13,23)."""
+
+
+class NotConvergedError(RuntimeError):
+    """`error("Did not converge")` (src/infql.jl:181) / capacity reached."""
+
+
+class PosDefException(ArithmeticError):
+    pass
+
+
+_QL_MSG = ("QL factorization does not exist. This could indicate that the operator is not Fredholm or that the "
+           "dimension of the kernel exceeds that of the co-kernel. Try again with the adjoint.")
+_QL_REAL_MSG = ("Real-valued QL factorization does not exist. Try ql(complex(A)) to see if a complex-valued QL "
+                "factorization exists.")
+
+
+def _raise_status(st, what):
+    st = int(st)
+    if st == 1:
+        raise DomainError(_QL_MSG)
+    if st == 2:
+        raise DomainError(_QL_REAL_MSG)
+    if st == 3:
+        raise NotConvergedError(f"{what}: did not converge within the capacity / iteration limit")
+    if st == 4:
+        raise PosDefException(f"{what}: matrix is not positive definite")
+    if st == 5:
+        raise ArithmeticError("Not-a-number encounted")
+
+
+# ---- lazy infinite vectors (the little of InfiniteArrays / FillArrays the fixtures need) -------------------
+
+class Affine:
+    """Entry k (k = 0, 1, ...) = (p + q*k)/r  — covers Fill, 1:∞, -2(0:∞)/z, 2 .+ ε(1:∞)."""
+
+    def __init__(self, p, q=0.0, r=1.0):
+        self.p, self.q, self.r = p, q, r
+
+    def value(self, k):
+        return (self.p + self.q * k) / self.r
+
+
+def Fill(v):
+    return Affine(v, 0.0, 1.0)
+
+
+def Ones():
+    return Fill(1.0)
+
+
+def Zeros():
+    return Fill(0.0)
+
+
+class Vcat:
+    """Vcat(head_values, tail) — finite head followed by a lazy tail (Affine), positions counted from the start."""
+
+    def __init__(self, head, tail):
+        self.head = list(np.atleast_1d(head)) if not isinstance(head, list) else head
+        self.tail = tail
+
+
+class UniformScaling:
+    def __init__(self, lam=1.0):
+        self.lam = lam
+
+    def __rmul__(self, s):
+        return UniformScaling(self.lam * s)
+
+    __mul__ = __rmul__
+
+
+I = UniformScaling(1.0)
+
+
+class BandedMatrix:
+    """∞ banded operator given by its diagonals `{d: diag}` (d = col - row, as in `BandedMatrix(d => v)`)."""
+
+    def __init__(self, diags: dict, shift=0.0):
+        self.diags = {int(d): (v if isinstance(v, (Affine, Vcat)) else Fill(v)) for d, v in diags.items()}
+        self.shift = shift
+
+    @property
+    def bandwidths(self):
+        return (max(0, -min(self.diags)), max(0, max(self.diags)))
+
+    def __sub__(self, other):
+        if isinstance(other, UniformScaling):
+            return BandedMatrix(self.diags, self.shift + other.lam)
+        return NotImplemented
+
+    def __add__(self, other):
+        if isinstance(other, UniformScaling):
+            return BandedMatrix(self.diags, self.shift - other.lam)
+        return NotImplemented
+
+    def _diag(self, d):
+        return self.diags.get(d, Fill(0.0))
+
+    def entry(self, i, j):
+        """A[i, j], 0-based."""
+        d = j - i
+        if d not in self.diags:
+            return -self.shift if d == 0 else 0.0
+        t = min(i, j)
+        v = self.diags[d]
+        val = (v.head[t] if t < len(v.head) else v.tail.value(t)) if isinstance(v, Vcat) else v.value(t)
+        return val - self.shift if d == 0 else val
+
+    def finite(self, n, m=None):
+        m = n if m is None else m
+        cplx = np.iscomplexobj(np.array([self.entry(0, 0), self.shift] + [self.entry(max(0, -d), max(0, d)) for d in self.diags]))
+        A = np.zeros((n, m), dtype=complex if cplx else float)
+        l, u = self.bandwidths
+        for i in range(n):
+            for j in range(max(0, i - l), min(m, i + u + 1)):
+                A[i, j] = self.entry(i, j)
+        return A
+
+    # -- descriptions for the C ABI ------------------------------------------------------------------
+    def is_toeplitz(self):
+        return all(isinstance(v, Affine) and v.q == 0 for v in self.diags.values())
+
+    def tail_column(self):
+        """BandedMatrices data column of the Toeplitz tail: [a_{+u}, ..., a_0, ..., a_{-l}] (no shift)."""
+        l, u = self.bandwidths
+        col = []
+        for d in range(u, -l - 1, -1):
+            v = self._diag(d)
+            t = v.tail if isinstance(v, Vcat) else v
+            if t.q != 0:
+                raise ValueError("operator does not have a Toeplitz tail")
+            col.append(t.p / t.r)
+        return np.array(col)
+
+    def head_rows(self):
+        """Smallest p such that row p of A (1-based) is already pure Toeplitz and p >= l + 1."""
+        l, _ = self.bandwidths
+        p = l + 1
+        for d, v in self.diags.items():
+            if isinstance(v, Vcat):
+                p = max(p, len(v.head) + 1 + max(0, -d))
+        return p
+
+    def head_width(self):
+        return max([len(v.head) for v in self.diags.values() if isinstance(v, Vcat)] + [0])
+
+    def generators(self):
+        """(p, q, r, head) rows in data-row order d = u, ..., -l for the QR / Cholesky entries."""
+        l, u = self.bandwidths
+        hp = self.head_width()
+        p, q, r = [], [], []
+        head = np.zeros((l + u + 1, hp)) if hp else None
+        for rr, d in enumerate(range(u, -l - 1, -1)):
+            v = self._diag(d)
+            t = v.tail if isinstance(v, Vcat) else v
+            p.append(t.p), q.append(t.q), r.append(t.r)
+            for k in range(hp):
+                head[rr, k] = (v.head[k] if (isinstance(v, Vcat) and k < len(v.head)) else t.value(k))
+        return np.array(p, float), np.array(q, float), np.array(r, float), head
+
+
+class Symmetric:
+    def __init__(self, A: BandedMatrix):
+        self.parent = A
+
+
+class _OneBased:
+    def __init__(self, fn):
+        self._fn = fn
+
+    def __getitem__(self, ij):
+        i, j = ij
+        if isinstance(i, slice) or isinstance(j, slice):
+            ri = range(i.start or 1, i.stop + 1) if isinstance(i, slice) else [i]
+            rj = range(j.start or 1, j.stop + 1) if isinstance(j, slice) else [j]
+            return np.array([[self._fn(a, b) for b in rj] for a in ri])
+        return self._fn(i, j)
+
+
+# ---- ql ----------------------------------------------------------------------------------------------------
+
+class QLHessenberg:
+    """Result of ql on a (perturbed) Toeplitz operator with u == 1 (src/banded/hessenbergq.jl:16-72)."""
+
+    def __init__(self, l, X, tau, head_factors=None, head_l11=None):
+        self.l, self.X, self.tau = l, X, tau
+        self._head, self._head_l11 = head_factors, head_l11
+        self.L = _OneBased(self._L)
+        self.Q = _OneBased(self._Q)
+
+    def _L(self, i, j):
+        if self._head is not None:
+            p = self._head.shape[0]
+            if i <= p and j <= p:
+                return self._head[i - 1, j - 1] if i >= j else 0.0
+            raise IndexError("only the p x p head of a perturbed operator's L is materialised")
+        m = self.X.shape[1]
+        if i < j or i - j > m - 1:
+            return 0.0
+        if j == 1:                                   # first column [X[1,m-1]; X[2,m-1:-1:1]]  (infqltoeplitz.jl:63)
+            return self.X[0, m - 2] if i == 1 else self.X[1, m - i]
+        return self.X[1, m - 1 - (i - j)]            # tail column X[2, m:-1:1]
+
+    def _q2(self):
+        m = self.X.shape[1]
+        v = self.X[0, m - 1]
+        H1 = np.diag([1 - self.tau[0], 1])
+        vv = np.array([v, 1])
+        H2 = np.eye(2) - self.tau[1] * np.outer(vv, np.conj(vv))
+        return H2 @ H1
+
+    def _Q(self, i, j):
+        n = max(i, j) + 2
+        q = self._q2()
+        Q = np.eye(n, dtype=q.dtype)
+        for k in range(n - 1):
+            Q[k:k + 2, :] = q @ Q[k:k + 2, :]
+        return Q[i - 1, j - 1]
+
+
+class _BlockQL:
+    def __init__(self, l11):
+        self._l11 = l11
+        self.L = _OneBased(self._L)
+
+    def _L(self, i, j):
+        if (i, j) == (1, 1):
+            return self._l11
+        raise IndexError("only L[1,1] is materialised for block operators")
+
+
+class BlockTridiagonal:
+    """BlockTridiagonal(Vcat(dl_head, Fill(c)), Vcat(d_head, Fill(a)), Vcat(du_head, Fill(b))) — each argument a
+    `(head_list, tail_block)` pair (examples/periodicschrodinger.jl:8-10)."""
+
+    def __init__(self, dl, d, du, shift=0.0, overrides=None):
+        self.dl, self.d, self.du, self.shift = dl, d, du, shift
+        self.overrides = dict(overrides or {})
+
+    def __sub__(self, other):
+        if isinstance(other, UniformScaling):
+            return BlockTridiagonal(self.dl, self.d, self.du, self.shift + other.lam, self.overrides)
+        return NotImplemented
+
+    def __setitem__(self, ij, v):      # A[1,1] = 2 (1-based scalar perturbation inside the first diagonal block)
+        self.overrides[ij] = v
+
+    def _heads(self):
+        d_head = [np.array(m, dtype=float, copy=True) for m in self.d[0]]
+        for (i, j), v in self.overrides.items():
+            n = np.asarray(self.d[1]).shape[0]
+            if i > n or j > n:
+                raise IndexError("only perturbations of the first diagonal block are supported")
+            if not d_head:
+                d_head = [np.array(self.d[1], dtype=float, copy=True)]
+            d_head[0][i - 1, j - 1] = v
+        return list(self.dl[0]), d_head, list(self.du[0])
+
+
+def ql(A, branch=1):
+    """ql(A; branch) for ∞ Toeplitz / perturbed Toeplitz (u == 1) and block-tridiagonal perturbed Toeplitz operators."""
+    if isinstance(A, BlockTridiagonal):
+        dlh, dh, duh = A._heads()
+        L, it, st = _b.ql_blocktri_l11(dlh, dh, duh, A.dl[1], A.d[1], A.du[1], [A.shift])
+        _raise_status(st[0], "ql(BlockTridiagonal)")
+        return _BlockQL(float(L[0]))
+    l, u = A.bandwidths
+    if u != 1:
+        raise NotImplementedError("only u == 1 (ql_pruneband is undefined upstream)")
+    col = A.tail_column()
+    lam = A.shift
+    cplx = np.iscomplexobj(col) or np.iscomplexobj(np.asarray(lam))
+    hp = A.head_width()
+    if hp == 0:
+        L, st, tail = _b.ql_toeplitz_l11(col, np.array([lam]), branch_rank=branch, want_tail=True,
+                                         real_path=not cplx)
+        _raise_status(st[0], "ql")
+        m = l + 2
+        t = tail[0]
+        return QLHessenberg(l, np.stack([t[:m], t[m:2 * m]]), t[2 * m:2 * m + 2])
+    p = A.head_rows()
+    head = A.finite(p) + lam * np.eye(p)             # the C entry applies the shift itself
+    L, st, hf = _b.ql_perttoeplitz_l11(head, col, np.array([lam]), branch_rank=branch, want_head_factors=True,
+                                       real_path=not (cplx or np.iscomplexobj(head)))
+    _raise_status(st[0], "ql")
+    return QLHessenberg(l, None, None, head_factors=hf[0], head_l11=L[0])
+
+
+def ql_L11(A, lambdas, branch=1, ngpus=1):
+    """Batched form over a vector of shifts: L11[i] = ql(A - lambdas[i]*I).L[1,1]; NaN + status where it does not exist."""
+    lam = np.asarray(lambdas) + A.shift
+    if isinstance(A, BlockTridiagonal):
+        dlh, dh, duh = A._heads()
+        L, it, st = _b.ql_blocktri_l11(dlh, dh, duh, A.dl[1], A.d[1], A.du[1], lam, ngpus=ngpus)
+        return L, st
+    col = A.tail_column()
+    if A.head_width() == 0:
+        return _b.ql_toeplitz_l11(col, lam, branch_rank=branch, ngpus=ngpus)
+    p = A.head_rows()
+    head = A.finite(p) + A.shift * np.eye(p)
+    return _b.ql_perttoeplitz_l11(head, col, lam, branch_rank=branch, ngpus=ngpus)
+
+
+# ---- qr / cholesky ------------------------------------------------------------------------------------------
+
+class _Solved(np.ndarray):
+    """Solution prefix of an ∞ vector (zero beyond its length), 0-based numpy indexing."""
+
+
+class AdaptiveQR:
+    def __init__(self, A: BandedMatrix):
+        self.A = A
+
+    def solve(self, b, tolerance=_b.FLOATMIN, ncap=None):
+        p, q, r, head = self.A.generators()
+        l, u = self.A.bandwidths
+        bb = np.atleast_1d(np.asarray(b.head if isinstance(b, Vcat) else b, dtype=float))
+        ncap = int(ncap) if ncap else 400_000
+        out = _b.qr_banded_solve(l, u, p[None], q[None], r[None], shift=[self.A.shift] if self.A.shift else None,
+                                 head=head, b=bb[None], tol=tolerance, ncap=ncap)
+        _raise_status(out["status"][0], "qr(A) \\ b")
+        return out["x"][0]
+
+    __truediv__ = None
+
+    def ldiv(self, b, **kw):
+        return self.solve(b, **kw)
+
+
+def qr(A: BandedMatrix):
+    """qr(A) for an ∞ banded operator → adaptive QR (src/infqr.jl:163-174); `.solve(b)` is `F \\ b`."""
+    return AdaptiveQR(A)
+
+
+def ldiv(A, b, **kw):
+    """`A \\ b` = `qr(A) \\ b` (factorize, src/infqr.jl:173-174,377)."""
+    return qr(A).solve(b, **kw)
+
+
+class AdaptiveCholesky:
+    def __init__(self, S):
+        self.A = S.parent if isinstance(S, Symmetric) else S
+
+    def solve(self, b, ncap=None):
+        p, q, r, head = self.A.generators()
+        l, u = self.A.bandwidths
+        sel = slice(0, u + 1)                         # upper bands only
+        bb = np.atleast_1d(np.asarray(b.head if isinstance(b, Vcat) else b, dtype=float))
+        out = _b.chol_banded_solve(u, p[None, sel], q[None, sel], r[None, sel],
+                                   shift=[self.A.shift] if self.A.shift else None,
+                                   head=None if head is None else head[sel], b=bb[None], ncap=int(ncap) if ncap else 400_000)
+        _raise_status(out["status"][0], "cholesky(S) \\ b")
+        return out["x"][0]
+
+
+def cholesky(S):
+    """cholesky(S) for a symmetric positive definite ∞ banded operator → adaptive Cholesky (src/infcholesky.jl:71-75)."""
+    return AdaptiveCholesky(S)
