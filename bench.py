@@ -13,6 +13,7 @@ has no exchange step).  Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -304,6 +305,48 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches_per_step": 4,
         }
 
+    # ---------------- other §8 configs (device resident, same timing rules): C4 Cholesky, C5 block QL --------
+    if not args.no_secondary:
+        sigma = 0.01 + (10 - 0.01) * np.arange(2048) / 2047
+        p4, q4 = ila_b200.pentadiagonal_operator(sigma)
+        plan4 = ila_b200.QrBandedPlan(0, 2, p4, q4, b=[1.0], ncap=8000, device=dev, kind="chol")
+        k4 = max(1, min(args.steps, 5))
+        ms4 = timed(plan4.run, k4, 2) / k4
+        if int((plan4.d_status != 0).sum().item()) != 0:
+            raise SystemExit("bench.py: C4 instances failed")
+        cols4 = float(plan4.d_nswept.sum().item())
+        xs = np.concatenate([np.linspace(-0.95, 0.95, 256), np.linspace(2.25, 4.0, 256)])
+        blocks = ila_b200.periodic_schrodinger_blocks()
+        d_e = torch.from_numpy(xs).to(dev)
+        d_L5 = torch.empty(512, dtype=torch.float64, device=dev)
+        d_it5 = torch.empty(512, dtype=torch.int32, device=dev)
+        d_st5 = torch.empty(512, dtype=torch.int32, device=dev)
+        flat = lambda m: np.ascontiguousarray(np.asarray(m, dtype=np.float64).reshape(-1, order="F"))
+        hb = [np.ascontiguousarray(np.stack([flat(m) for m in blocks[i]])) for i in range(3)]
+        cb, ab, bb = flat(blocks[3]), flat(blocks[4]), flat(blocks[5])
+
+        def step_c5():
+            _lib.check(lib.ila_ql_blocktri_l11_f64_dev(2, _lib.ptr(cb), _lib.ptr(ab), _lib.ptr(bb), 1, _lib.ptr(hb[0]), 1,
+                                                       _lib.ptr(hb[1]), 1, _lib.ptr(hb[2]), _lib.ptr(d_e), 512, 1e-10,
+                                                       1000000, _lib.ptr(d_L5), _lib.ptr(d_it5), _lib.ptr(d_st5),
+                                                       ctypes.c_void_p(stream)))
+        ms5 = timed(step_c5, k4, 2) / k4
+        its5 = float(d_it5.sum().item())
+        line["other_configs"] = [
+            {"metric": "adaptive_cholesky_columns_per_s", "value": cols4 * world / (ms4 * 1e-3), "unit": "columns/s",
+             "ms_per_step": ms4, "config": {"workload": "C4 pentadiagonal adaptive Cholesky, 2048 shifts (per GPU)",
+                                            "columns_swept": cols4},
+             "roofline": {"bound": "hbm", "achieved": BYTES_PER_COLUMN * cols4 / (ms4 * 1e-3) / 1e9, "peak": hbm_peak,
+                          "unit": "GB/s", "frac": BYTES_PER_COLUMN * cols4 / (ms4 * 1e-3) / 1e9 / hbm_peak,
+                          "traffic": None, "bytes_per_unit": BYTES_PER_COLUMN,
+                          "note": "latency bound: 2048 short serial recurrences (1-2k columns each)"},
+             "gpu_launches_per_step": 4},
+            {"metric": "block_ql_energies_per_s", "value": 512 * world / (ms5 * 1e-3), "unit": "energies/s",
+             "ms_per_step": ms5, "config": {"workload": "C5 periodic Schrödinger block QL, 512 energies (per GPU)",
+                                            "fixed_point_iterations": its5},
+             "gpu_launches_per_step": 1},
+        ]
+
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -311,8 +354,8 @@ def run_ours(args, rank, local_rank, world):
         sample = lam_h[:rows * NX]
         dt, res = cpu_bullhead(sample, threads)
         line["cpu_baseline"] = {"value": sample.size / dt, "unit": "lambda-points/s", "cores": threads, "kind": "port",
-                                "sample": f"{rows}x{NX} λ-points once, numpy/LAPACK zgeev oracle on {threads} threads "
-                                          "(Julia absent: reference cannot run; it is single-threaded)"}
+                                "sample": f"{rows}x{NX} λ-points once, numpy/LAPACK zgeev oracle in {threads} worker "
+                                          "processes (Julia absent: the reference cannot run; it is single-threaded)"}
         if "secondary" in line:
             from oracle import banded as ob
             from scipy.special import jv

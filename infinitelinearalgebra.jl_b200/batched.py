@@ -252,9 +252,12 @@ class QrBandedPlan:
     """
 
     def __init__(self, l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=FLOATMIN, colgrowth=1000,
-                 ncap=200_000, ncap_per=None, device=None, xcap=None, want_reflectors=False):
+                 ncap=200_000, ncap_per=None, device=None, xcap=None, want_reflectors=False, kind="qr"):
         import torch
         self.torch = torch
+        self.kind = kind            # "qr" (K1+K2) or "chol" (K5+K2: l must be 0, generators of the upper bands)
+        if kind == "chol" and l != 0:
+            raise ValueError("Cholesky plans take l = 0 and the upper-band generators")
         nd = l + u + 1
         batch = int(np.asarray(p).reshape(-1, nd).shape[0])
         p, q, r, shift, hp, head = _op_arrays(nd, batch, p, q, r, shift, head)
@@ -301,6 +304,13 @@ class QrBandedPlan:
 
     def run_factor(self):
         s = self._stream()
+        if self.kind == "chol":
+            check(lib().ila_chol_banded_factor_f64_dev(
+                self.u, self.batch, ptr(self.d_p), ptr(self.d_q), ptr(self.d_r), ptr(self.d_shift), self.hp,
+                ptr(self.d_head), self.nb, ptr(self.d_b), self.tol, self.colgrowth, self.ncap, ptr(self.d_caps),
+                ptr(self.d_gbase), ptr(self.d_work), ptr(self.d_ncols), ptr(self.d_nconv), ptr(self.d_nswept),
+                ptr(self.d_xoff), ptr(self.d_status), 0, s))
+            return 2
         check(lib().ila_qr_banded_factor_f64_dev(
             self.l, self.u, self.batch, ptr(self.d_p), ptr(self.d_q), ptr(self.d_r), ptr(self.d_shift), self.hp,
             ptr(self.d_head), self.nb, ptr(self.d_b), self.tol, self.colgrowth, self.ncap, ptr(self.d_caps),
