@@ -57,3 +57,13 @@ for spt in (1, 2, 4, 8, 16, 0):
     _lib.check(_lib.lib().ila_ql_set_shifts_per_thread(spt))
     med, mn = ev_time(f, reps=20)
     print(f"K3 spt={spt}: median {med*1e3:.1f} us min {mn*1e3:.1f} us -> {lam.numel()/med/1e-3/1e9:.2f} Gpts/s")
+
+# C4 Cholesky phases
+sigma = 0.01 + (10 - 0.01) * np.arange(2048) / 2047
+p4, q4 = ila_b200.pentadiagonal_operator(sigma)
+for name, pp, qq in (("C4 2048 shifts", p4, q4), ("C4-like 32768 shifts", np.tile(p4, (16, 1)), np.tile(q4, (16, 1)))):
+    plan4 = ila_b200.QrBandedPlan(0, 2, pp, qq, b=[1.0], ncap=8000, kind="chol")
+    mf, _ = ev_time(plan4.run_factor, reps=10, warm=3)
+    mb, _ = ev_time(plan4.run_backsolve, reps=10, warm=3)
+    nsw = plan4.d_nswept.cpu().numpy()
+    print(f"CHOL {name}: fwd {mf*1e3:.0f} us bwd {mb*1e3:.0f} us; swept {nsw.sum()} max {nsw.max()}; fwd cycles/col(longest) {mf*1e-3*1.965e9/nsw.max():.0f} bwd {mb*1e-3*1.965e9/nsw.max():.0f}; {nsw.sum()/(mf+mb)/1e-3/1e9:.2f} Gcol/s")
