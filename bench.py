@@ -245,6 +245,32 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     e2e_ms = max_over_ranks(t_e2e * 1e3) / args.steps
     e2e_value = n * world / (e2e_ms * 1e-3)
+    # ---------------- e2e, grid form (the reference example's call: ranges x, y in, abs(L11)/-1 matrix out) ----------
+    xg = np.linspace(-10.0, 7.0, NX)
+    yg = np.linspace(-7.0, 8.0, NY * world)[rank::world].copy()
+    h_x = torch.from_numpy(xg).pin_memory()
+    h_y = torch.from_numpy(yg).pin_memory()
+    h_z = torch.empty(NY * NX, dtype=torch.float64).pin_memory()
+
+    def step_grid():
+        _lib.check(lib.ila_ql_toeplitz_absl11_grid_c64(3, 1, _lib.ptr(col), _lib.ptr(h_x), NX, _lib.ptr(h_y), NY, 1,
+                                                       _lib.ptr(h_z), 1))
+
+    for _ in range(args.warmup):
+        step_grid()
+    barrier()
+    t_grid = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_grid()
+        t_grid += time.perf_counter() - t0
+    barrier()
+    grid_ms = max_over_ranks(t_grid * 1e3) / args.steps
+    zref = torch.where(h_st == 0, torch.view_as_real(h_L)[:, 0].abs(), torch.full((n,), -1.0, dtype=torch.float64))
+    if not bool(torch.allclose(h_z, zref, rtol=1e-12, atol=2e-12)):
+        raise SystemExit("bench.py: grid form disagrees with the array form")
     sampler.stop_flag.set()
     sampler.join(timeout=2)
     # cross-check: the host path (chunked launches) and the device path agree (same statuses, L11 to 1e-12)
@@ -264,7 +290,12 @@ def run_ours(args, rank, local_rank, world):
                    "points_per_gpu": n, "l2": "flushed between timed steps (256 MiB fill)", "parallelism":
                    f"shift-grid sharding x{world}, no collective on the data path"},
         "e2e": {"value": e2e_value, "unit": "lambda-points/s", "h2d_bytes_per_step": 16 * n,
-                "d2h_bytes_per_step": 20 * n, "ms_per_step": e2e_ms, "host_matches_device": same},
+                "d2h_bytes_per_step": 20 * n, "ms_per_step": e2e_ms, "host_matches_device": same,
+                "api": "ila_ql_toeplitz_l11_c64 (λ array in, complex L11 + status out)"},
+        "e2e_grid": {"value": n * world / (grid_ms * 1e-3), "unit": "lambda-points/s", "ms_per_step": grid_ms,
+                     "h2d_bytes_per_step": 8 * (NX + NY), "d2h_bytes_per_step": 8 * n,
+                     "api": "ila_ql_toeplitz_absl11_grid_c64 = the example's ℓ11.(Ref(A), x' .+ y.*im): ranges in, "
+                            "abs(L11)/-1.0 matrix out (examples/toeplitz.jl:14-33)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": K3_DRAM_TRAFFIC if n == NX * NY else None,

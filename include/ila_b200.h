@@ -70,6 +70,14 @@ int ila_ql_toeplitz_l11_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d
 int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank,
                                 double *d_L11, double *d_tail_opt, int32_t *d_status, void *stream);
 
+/* Grid form = the λ loop of the reference's examples (examples/toeplitz.jl:14-33: `ℓ11.(Ref(A), x' .+ y.*im)`):
+ * out[k*nx + j] = abs(ql(A - (x[j] + i*y[k])*I).L[1,1]), or -1.0 where the factorization does not exist (the example's
+ * `catch` branch).  Shifts are formed on device; 8 B/shift come back. */
+int ila_ql_toeplitz_absl11_grid_c64(int l, int u, const ila_c64 *a, const double *x, int nx, const double *y, int64_t ny,
+                                    int branch_rank, double *out, int ngpus);
+int ila_ql_toeplitz_absl11_grid_c64_dev(int l, int u, const ila_c64 *a, const double *d_x, int nx, const double *d_y, int64_t ny,
+                                        int branch_rank, double *d_out, void *stream);
+
 /* ---- K3+K4: perturbed Toeplitz, u == 1:  L11[i] = ql(A - lambda[i]*I).L[1,1],  A = finite head + Toeplitz tail ----
  * Replaces ql(::PertToeplitz) -> ql_hessenberg!(B) (src/infql.jl:60-93): tail fixed point (K3), last head row rebuilt
  * from row 1 of Q∞' (:81-82), finite Householder QL of the p x p head (:83).

@@ -47,6 +47,8 @@ SIGNATURES = {
     "ila_ql_toeplitz_l11_f64": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int]),
     "ila_ql_toeplitz_l11_c64_dev": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp]),
     "ila_ql_toeplitz_l11_f64_dev": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, _vp]),
+    "ila_ql_toeplitz_absl11_grid_c64": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, C.c_int]),
+    "ila_ql_toeplitz_absl11_grid_c64_dev": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_int, _vp, _vp]),
     "ila_ql_perttoeplitz_l11_c64": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int]),
     "ila_ql_perttoeplitz_l11_f64": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp, C.c_int]),
     "ila_ql_blocktri_l11_f64": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int64,

@@ -49,6 +49,18 @@ def ql_toeplitz_l11(data_column, lambdas, branch_rank: int = 1, want_tail: bool 
     return res
 
 
+def ql_toeplitz_absl11_grid(data_column, x, y, branch_rank: int = 1, ngpus: int = 1, out=None):
+    """The reference example's λ-grid loop (examples/toeplitz.jl:14-33): z[k, j] = abs(ql(A - (x[j] + i y[k]) I).L[1,1]),
+    -1.0 where the QL factorization does not exist.  Shifts are formed on device."""
+    col = np.ascontiguousarray(np.asarray(data_column), dtype=np.complex128)
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    y = np.ascontiguousarray(np.asarray(y, dtype=np.float64))
+    z = out if out is not None else np.empty((y.size, x.size), dtype=np.float64)
+    check(lib().ila_ql_toeplitz_absl11_grid_c64(col.size - 2, 1, ptr(col), ptr(x), x.size, ptr(y), y.size, branch_rank,
+                                                ptr(z), ngpus))
+    return z
+
+
 def ql_toeplitz_l11_dev(data_column, d_lambda, d_L11, d_status, branch_rank: int = 1, d_tail=None, stream=None,
                         real_path: bool = False):
     """Device-resident form: `d_*` are torch CUDA tensors (complex128 / float64 / int32) on the current device."""

@@ -15,6 +15,8 @@ int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int b
                        int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream);
 
 void tz_set_spt(int v);
+int launch_ql_toeplitz_grid(int l, int u, const double *a_host, int branch_rank, const double *d_gx, int nx,
+                            const double *d_gy, int64_t ny, double *d_absout, cudaStream_t stream);
 int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
                         int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
                         cudaStream_t stream);
@@ -353,6 +355,57 @@ int ila_ql_toeplitz_l11_f64_dev(int l, int u, const double *a, const double *d_l
 {
     if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
     return launch_ql_toeplitz(true, l, u, a, branch_rank, d_lambda, n, d_L11, d_tail_opt, d_status, (cudaStream_t)stream);
+}
+
+int ila_ql_toeplitz_absl11_grid_c64_dev(int l, int u, const ila_c64 *a, const double *d_x, int nx, const double *d_y, int64_t ny,
+                                        int branch_rank, double *d_out, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    return launch_ql_toeplitz_grid(l, u, (const double *)a, branch_rank, d_x, nx, d_y, ny, d_out, (cudaStream_t)stream);
+}
+
+int ila_ql_toeplitz_absl11_grid_c64(int l, int u, const ila_c64 *a, const double *x, int nx, const double *y, int64_t ny,
+                                    int branch_rank, double *out, int ngpus)
+{
+    if (nx < 0 || ny < 0 || !a || ((int64_t)nx * ny > 0 && (!x || !y || !out))) return set_error(ILA_ERR_ARG, "ql_toeplitz grid: bad arguments");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if ((int64_t)nx * ny == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > ny) G = (int)ny;
+    const int64_t per = (ny + G - 1) / G;           // contiguous row slabs per device
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= ny ? per : ny - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        double *d_x, *d_y, *d_o;
+        if ((rc = dev_buf_t(pd, 0, (size_t)nx, &d_x))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt, &d_y))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt * nx, &d_o))) return rc;
+        cudaStream_t s0 = g_dev[pd].pipe[0];
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * nx, cudaMemcpyHostToDevice, s0));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_y, y + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s0));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(s0));
+        // row-chunked pipeline: the D2H of chunk c overlaps the kernel of chunk c+1
+        const int64_t rchunk = cnt > 256 ? 128 : cnt;
+        int ci = 0;
+        for (int64_t r0 = 0; r0 < cnt; r0 += rchunk, ci++) {
+            const int64_t rc_ = (r0 + rchunk <= cnt) ? rchunk : cnt - r0;
+            cudaStream_t s = g_dev[pd].pipe[ci % kPipe];
+            if ((rc = launch_ql_toeplitz_grid(l, u, (const double *)a, branch_rank, d_x, nx, d_y + r0, rc_, d_o + r0 * nx, s))) return rc;
+            ILA_CUDA_CHECK(cudaMemcpyAsync(out + (lo + r0) * nx, d_o + r0 * nx, sizeof(double) * rc_ * nx, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        for (int i = 0; i < kPipe; i++) ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].pipe[i]));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
 }
 
 // ================================ K4: perturbed-Toeplitz head ==========================================

@@ -186,6 +186,15 @@ __device__ __forceinline__ int select_root(const cplx (&w)[N], int branch_rank, 
     return jsel;
 }
 
+// Optional grid mode (the λ loop of examples/toeplitz.jl:29-33, `ℓ11.(Ref(A), x' .+ y.*im)`): shifts are formed on device
+// as complex(gx[j], gy[k]) for idx = k*nx + j, and the result is the example's ℓ11 value: abs(L[1,1]), or -1.0 where
+// the QL factorization does not exist — 8 B out and no λ in per shift.
+struct TzGrid {
+    const double *gx, *gy;
+    int nx;
+    double *absout;
+};
+
 // Each thread owns SPT consecutive shifts.  The first one starts cold (roots on a circle); the following ones start
 // from the previous shift's roots, which on a grid are O(Δλ) away: one Aberth sweep re-establishes every root to ~1e-5
 // (enough to rank the moduli unless they nearly tie), then only the selected root is taken to full precision by Newton.
@@ -194,7 +203,7 @@ __device__ __forceinline__ int select_root(const cplx (&w)[N], int branch_rank, 
 template <int N, bool REAL_PATH, bool WANT_TAIL>
 __global__ void __launch_bounds__(128)
 ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t n, int spt, double *__restrict__ L11,
-                       double *__restrict__ tail, int32_t *__restrict__ status)
+                       double *__restrict__ tail, int32_t *__restrict__ status, TzGrid G)
 {
     const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * spt;
     if (first >= n) return;
@@ -205,7 +214,10 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     bool have_roots = false;
   for (int64_t idx = first; idx < last; idx++) {
     cplx lam;
-    if (REAL_PATH) {
+    if (G.gx) {
+        const int64_t k = idx / G.nx;
+        lam = mk(G.gx[idx - k * G.nx], G.gy[k]);
+    } else if (REAL_PATH) {
         lam = mk(lambda[idx], 0.0);
     } else {
         const double2 t = reinterpret_cast<const double2 *>(lambda)[idx];
@@ -425,6 +437,10 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
         for (int j = 0; j < M; j++) { X1[j] = mk(qnan, qnan); X2[j] = mk(qnan, qnan); }
         tau1 = tau2 = mk(qnan, qnan);
     }
+    if (G.absout) {
+        G.absout[idx] = (st == ILA_OK) ? sqrt(abs2(X1[N - 1])) : -1.0;
+        continue;
+    }
     status[idx] = st;
     if (REAL_PATH) {
         L11[idx] = X1[N - 1].re;
@@ -454,7 +470,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
 // ---- host-side launcher -------------------------------------------------------------------------
 template <int N, bool REAL_PATH>
 static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, int64_t n, double *d_L11,
-                    double *d_tail, int32_t *d_status, cudaStream_t stream)
+                    double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G)
 {
     TzParams<N> P;
     for (int j = 0; j <= N; j++) P.a[j] = a_rev[j];
@@ -486,9 +502,9 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     const int64_t nthreads = (n + spt - 1) / spt;
     const int64_t blocks = (nthreads + threads - 1) / threads;
     if (d_tail)
-        ql_toeplitz_l11_kernel<N, REAL_PATH, true><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status);
+        ql_toeplitz_l11_kernel<N, REAL_PATH, true><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status, G);
     else
-        ql_toeplitz_l11_kernel<N, REAL_PATH, false><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status);
+        ql_toeplitz_l11_kernel<N, REAL_PATH, false><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status, G);
     count_launch();
     ILA_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -496,24 +512,42 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
 
 template <bool REAL_PATH>
 static int launch_any(int l, const cplx *a_rev, int branch_rank, const double *d_lambda, int64_t n, double *d_L11,
-                      double *d_tail, int32_t *d_status, cudaStream_t stream)
+                      double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G)
 {
     switch (l + 1) {
-    case 2: return launch_n<2, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
-    case 3: return launch_n<3, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
-    case 4: return launch_n<4, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
-    case 5: return launch_n<5, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
-    case 6: return launch_n<6, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
-    case 7: return launch_n<7, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
-    case 8: return launch_n<8, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+    case 2: return launch_n<2, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
+    case 3: return launch_n<3, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
+    case 4: return launch_n<4, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
+    case 5: return launch_n<5, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
+    case 6: return launch_n<6, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
+    case 7: return launch_n<7, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
+    case 8: return launch_n<8, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
     default: return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz: lower bandwidth l must be in 1..7");
     }
 }
 
 // Exposed to api.cu.  `a` is in BandedMatrices data-column order (a_{+1}, a_0, ..., a_{-l}); `reverse` (infqltoeplitz.jl:59)
 // is done here.
+int launch_ql_toeplitz_ex(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
+                          int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G);
+
 int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
                        int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream)
+{
+    return launch_ql_toeplitz_ex(real_path, l, u, a_host, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream,
+                                 TzGrid{nullptr, nullptr, 0, nullptr});
+}
+
+// grid mode: |L11| (or -1) for λ = gx[j] + i*gy[k], idx = k*nx + j, k < ny
+int launch_ql_toeplitz_grid(int l, int u, const double *a_host, int branch_rank, const double *d_gx, int nx,
+                            const double *d_gy, int64_t ny, double *d_absout, cudaStream_t stream)
+{
+    return launch_ql_toeplitz_ex(false, l, u, a_host, branch_rank, nullptr, (int64_t)nx * ny, nullptr, nullptr, nullptr,
+                                 stream, TzGrid{d_gx, d_gy, nx, d_absout});
+}
+
+int launch_ql_toeplitz_ex(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
+                          int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G)
 {
     if (u != 1) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz: only u == 1 (Hessenberg) symbols are supported (ql_pruneband is undefined upstream)");
     if (l < 1 || l + 1 > kMaxDeg) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz: lower bandwidth l must be in 1..7");
@@ -526,8 +560,8 @@ int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int b
     }
     if (a_rev[m - 1].re == 0.0 && a_rev[m - 1].im == 0.0)
         return set_error(ILA_ERR_ARG, "ql_toeplitz: super-diagonal coefficient is zero (u would be 0)");
-    return real_path ? launch_any<true>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream)
-                     : launch_any<false>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream);
+    return real_path ? launch_any<true>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G)
+                     : launch_any<false>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
 }
 
 

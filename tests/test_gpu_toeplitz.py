@@ -132,3 +132,18 @@ def test_empty_and_single(ila):
     assert L.shape == (0,) and st.shape == (0,)
     L, st = ila.ql_toeplitz_l11(BULLHEAD_COLUMN, np.array([5.0 + 0j]))
     assert st[0] == 0
+
+
+def test_grid_form_matches_array_form(ila):
+    # examples/toeplitz.jl:14-33: z = ℓ11.(Ref(A), x' .+ y.*im)  (abs(L[1,1]) or -1.0)
+    x = np.linspace(-10.0, 7.0, 200)
+    y = np.linspace(-7.0, 8.0, 150)
+    z = ila.ql_toeplitz_absl11_grid(BULLHEAD_COLUMN, x, y)
+    L, st = ila.ql_toeplitz_l11(BULLHEAD_COLUMN, x[None, :] + 1j * y[:, None])
+    ref = np.where(st == 0, np.abs(L), -1.0)
+    assert z.shape == (150, 200)
+    assert np.array_equal(z == -1.0, st != 0)
+    assert np.allclose(z, ref, rtol=1e-12, atol=2e-12)
+    z2 = ila.ql_toeplitz_absl11_grid(BULLHEAD_COLUMN, x, y, branch_rank=2)
+    L2, st2 = ila.ql_toeplitz_l11(BULLHEAD_COLUMN, x[None, :] + 1j * y[:, None], branch_rank=2)
+    assert np.array_equal(z2 == -1.0, st2 != 0)
