@@ -112,6 +112,36 @@ __device__ __forceinline__ int aberth_sweep_f32(const cplxf (&cf)[N + 1], cplxf 
     return big ? 2 : (notconv ? 1 : 0);
 }
 
+// One Gauss–Seidel Durand–Kerner (Weierstrass) sweep in FP32: corr_j = P(w_j) / prod_{k != j}(w_j - w_k) — no P',
+// less than half the work of an Aberth sweep, quadratic.  Used to TRACK the roots from a predicted start (error
+// O(Δλ²)); same return convention as the Aberth sweep.
+template <int N>
+__device__ __forceinline__ int dk_sweep_f32(const cplxf (&cf)[N + 1], cplxf (&w)[N])
+{
+    bool notconv = false, big = false;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        cplxf pv = mkf(1.f);
+#pragma unroll
+        for (int k = 1; k <= N; k++) pv = pv * w[j] + cf[k];
+        cplxf den = mkf(1.f);
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (k == j) continue;
+            den = den * (w[j] - w[k]);
+        }
+        const float b2 = abs2f(den);
+        cplxf corr = mkf(0.f);
+        if (b2 > 1e-30f && b2 < 1e30f) corr = __frcp_rn(b2) * (pv * conjf_(den));
+        else big = true;
+        w[j] = w[j] - corr;
+        const float w2 = abs2f(w[j]), c2 = abs2f(corr);
+        notconv = notconv || (c2 > 1e-6f * w2);    // |corr| > 1e-3 |w|: the quadratic step then lands at ~1e-6
+        big = big || (c2 > 1e-4f * w2) || !(w2 < 1e30f);
+    }
+    return big ? 2 : (notconv ? 1 : 0);
+}
+
 // One Gauss–Seidel Aberth–Ehrlich sweep over all N roots; returns 0 when every correction is below 1e-9 |w_j|
 // (converged), 1 when all are below 1e-2 |w_j| (tracking), 2 otherwise.
 template <int N>
@@ -211,6 +241,9 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     const int64_t last = (first + spt < n) ? first + spt : n;
 
     cplxf wf[N];                 // FP32 scout roots, carried from shift to shift
+    cplxf dwf[N];                // their last movement: linear predictor for the next shift
+#pragma unroll
+    for (int j = 0; j < N; j++) dwf[j] = mkf(0.f);
     bool have_roots = false;
   for (int64_t idx = first; idx < last; idx++) {
     cplx lam;
@@ -259,9 +292,21 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
         for (int j = 0; j < N; j++) wf[j] = c + rad * mkf((float)P.unit[j].re, (float)P.unit[j].im);
     }
     int scout = 2;
-    for (int it = 0; it < kAberthMaxIt; it++) {
-        scout = aberth_sweep_f32<N>(cff, wf);
-        if (scout == 0) break;
+    if (have_roots) {
+        // warm: linear prediction from the last two shifts, then ONE cheap Durand–Kerner sweep; accepted when every
+        // correction is below 1e-3 |w| (the roots are then good to ~1e-6), otherwise the Aberth loop below takes over
+        cplxf wold[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) { wold[j] = wf[j]; wf[j] = wf[j] + dwf[j]; }
+        scout = dk_sweep_f32<N>(cff, wf);
+#pragma unroll
+        for (int j = 0; j < N; j++) dwf[j] = wf[j] - wold[j];
+    }
+    if (scout != 0) {
+        for (int it = 0; it < kAberthMaxIt; it++) {
+            scout = aberth_sweep_f32<N>(cff, wf);
+            if (scout == 0) break;
+        }
     }
     cplx w[N];
 #pragma unroll
@@ -495,7 +540,7 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     if (n <= 0) return 0;
     const int threads = 128;
     // shifts per thread: consecutive shifts share a warm start; keep >= ~16 warps per SM in flight
-    int spt = (int)(n / (148 * 16 * 32));
+    int spt = (int)(n / (148 * 12 * 32));
     if (g_tz_spt > 0) spt = g_tz_spt;
     if (spt < 1) spt = 1;
     if (spt > 16) spt = 16;
