@@ -40,16 +40,33 @@ __device__ __forceinline__ double fast_rcp(double b)
 __device__ __forceinline__ double dsign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
 
 // Horner: P(w) and P'(w) for the monic polynomial with coefficients cf[1..N]
+// a*b + c with two FMAs per component (the operator form costs three instructions)
+__device__ __forceinline__ cplx cfma(cplx a, cplx b, cplx c)
+{
+    return cplx{fma(a.re, b.re, fma(-a.im, b.im, c.re)), fma(a.re, b.im, fma(a.im, b.re, c.im))};
+}
+
 template <int N>
 __device__ __forceinline__ void horner2(const cplx (&cf)[N + 1], cplx w, cplx &pv, cplx &dv)
 {
-    pv = mk(1.0, 0.0);
-    dv = mk(0.0, 0.0);
+    // k = 1 peeled: (pv, dv) = (1, 0) -> (w + cf_1, 1)
+    dv = mk(1.0, 0.0);
+    pv = w + cf[1];
 #pragma unroll
-    for (int k = 1; k <= N; k++) {
-        dv = dv * w + pv;
-        pv = pv * w + cf[k];
+    for (int k = 2; k <= N; k++) {
+        dv = cfma(dv, w, pv);
+        pv = cfma(pv, w, cf[k]);
     }
+}
+
+// P(w) alone
+template <int N>
+__device__ __forceinline__ cplx horner1(const cplx (&cf)[N + 1], cplx w)
+{
+    cplx pv = w + cf[1];
+#pragma unroll
+    for (int k = 2; k <= N; k++) pv = cfma(pv, w, cf[k]);
+    return pv;
 }
 
 // ---- single-precision scout ----------------------------------------------------------------------------
@@ -66,6 +83,16 @@ __device__ __forceinline__ cplxf operator*(cplxf a, cplxf b) { return cplxf{a.re
 __device__ __forceinline__ cplxf operator*(float s, cplxf a) { return cplxf{s * a.re, s * a.im}; }
 __device__ __forceinline__ cplxf conjf_(cplxf a) { return cplxf{a.re, -a.im}; }
 __device__ __forceinline__ float abs2f(cplxf a) { return a.re * a.re + a.im * a.im; }
+__device__ __forceinline__ cplxf cfmaf(cplxf a, cplxf b, cplxf c)
+{
+    return cplxf{fmaf(a.re, b.re, fmaf(-a.im, b.im, c.re)), fmaf(a.re, b.im, fmaf(a.im, b.re, c.im))};
+}
+__device__ __forceinline__ float rcpf_approx(float x)   // one MUFU; callers keep x inside [1e-30, 1e30]
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 template <int N>
 struct TzParams {
@@ -84,25 +111,26 @@ __device__ __forceinline__ int aberth_sweep_f32(const cplxf (&cf)[N + 1], cplxf 
     bool notconv = false, big = false;
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        cplxf pv = mkf(1.f), dv = mkf(0.f);
+        cplxf dv = mkf(1.f), pv = w[j] + cf[1];
 #pragma unroll
-        for (int k = 1; k <= N; k++) {
-            dv = dv * w[j] + pv;
-            pv = pv * w[j] + cf[k];
+        for (int k = 2; k <= N; k++) {
+            dv = cfmaf(dv, w[j], pv);
+            pv = cfmaf(pv, w[j], cf[k]);
         }
         cplxf num = mkf(0.f), den = mkf(1.f);
+        bool first = true;
 #pragma unroll
         for (int k = 0; k < N; k++) {
             if (k == j) continue;
             const cplxf d = w[j] - w[k];
-            num = num * d + den;
-            den = den * d;
+            if (first) { num = mkf(1.f); den = d; first = false; }
+            else { num = cfmaf(num, d, den); den = den * d; }
         }
         const cplxf top = pv * den;
-        const cplxf bot = dv * den - pv * num;
+        const cplxf bot = cfmaf(dv, den, mkf(0.f) - pv * num);
         const float b2 = abs2f(bot);
         cplxf corr = mkf(0.f);
-        if (b2 > 1e-30f && b2 < 1e30f) corr = __frcp_rn(b2) * (top * conjf_(bot));
+        if (b2 > 1e-30f && b2 < 1e30f) corr = rcpf_approx(b2) * (top * conjf_(bot));
         else big = true;
         w[j] = w[j] - corr;
         const float w2 = abs2f(w[j]), c2 = abs2f(corr);
@@ -121,18 +149,21 @@ __device__ __forceinline__ int dk_sweep_f32(const cplxf (&cf)[N + 1], cplxf (&w)
     bool notconv = false, big = false;
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        cplxf pv = mkf(1.f);
+        cplxf pv = w[j] + cf[1];
 #pragma unroll
-        for (int k = 1; k <= N; k++) pv = pv * w[j] + cf[k];
+        for (int k = 2; k <= N; k++) pv = cfmaf(pv, w[j], cf[k]);
         cplxf den = mkf(1.f);
+        bool first = true;
 #pragma unroll
         for (int k = 0; k < N; k++) {
             if (k == j) continue;
-            den = den * (w[j] - w[k]);
+            const cplxf d = w[j] - w[k];
+            den = first ? d : den * d;
+            first = false;
         }
         const float b2 = abs2f(den);
         cplxf corr = mkf(0.f);
-        if (b2 > 1e-30f && b2 < 1e30f) corr = __frcp_rn(b2) * (pv * conjf_(den));
+        if (b2 > 1e-30f && b2 < 1e30f) corr = rcpf_approx(b2) * (pv * conjf_(den));
         else big = true;
         w[j] = w[j] - corr;
         const float w2 = abs2f(w[j]), c2 = abs2f(corr);
@@ -158,7 +189,7 @@ __device__ __forceinline__ int aberth_sweep(const cplx (&cf)[N + 1], cplx (&w)[N
         for (int k = 0; k < N; k++) {
             if (k == j) continue;
             const cplx d = w[j] - w[k];
-            num = num * d + den;
+            num = cfma(num, d, den);
             den = den * d;
         }
         const cplx top = pv * den;
@@ -214,6 +245,64 @@ __device__ __forceinline__ int select_root(const cplx (&w)[N], int branch_rank, 
         if (j != jsel) gap = fmin(gap, fabs(n2[j] - nsel));
     gap_out = (nsel > 0.0) ? gap / nsel : 0.0;
     return jsel;
+}
+
+// FP32 ranking of the scout's roots (used only to pick the root Newton refines and to detect near-ties; whenever the
+// relative gap is below 1e-5 the FP64 path with the reference's exact tie rule decides instead).
+template <int N>
+__device__ __forceinline__ int select_root_f32(const cplxf (&w)[N], int branch_rank, float &gap_out)
+{
+    float n2[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) n2[j] = abs2f(w[j]);
+    int jsel = 0;
+    if (branch_rank <= 1) {
+        float best = n2[0];
+#pragma unroll
+        for (int j = 1; j < N; j++)
+            if (n2[j] > best) { best = n2[j]; jsel = j; }
+    } else {
+        int want = branch_rank - 1;
+        if (want > N - 1) want = N - 1;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            int larger = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                if (k == j) continue;
+                larger += (n2[k] > n2[j] || (n2[k] == n2[j] && k < j)) ? 1 : 0;
+            }
+            if (larger == want) jsel = j;
+        }
+    }
+    float nsel = n2[0];
+#pragma unroll
+    for (int j = 1; j < N; j++)
+        if (j == jsel) nsel = n2[j];
+    float gap = 3e38f;
+#pragma unroll
+    for (int j = 0; j < N; j++)
+        if (j != jsel) gap = fminf(gap, fabsf(n2[j] - nsel));
+    gap_out = (nsel > 1e-30f && nsel < 1e30f) ? gap * rcpf_approx(nsel) : 0.f;
+    return jsel;
+}
+
+// sqrt for the epilogue: MUFU rsqrt seed + coupled Newton (Goldschmidt) in FP64, branch-free inside a wide exponent
+// box, IEEE sqrt outside.  Result within 1 ulp.
+__device__ __forceinline__ double fast_sqrt(double x)
+{
+    if (!(x > 1e-280 && x < 1e280)) return sqrt(x);
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double g = x * r, h = 0.5 * r;
+    double e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    e = fma(-h, g, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    const double d = fma(-g, g, x);
+    return fma(d, h, g);
 }
 
 // Optional grid mode (the λ loop of examples/toeplitz.jl:29-33, `ℓ11.(Ref(A), x' .+ y.*im)`): shifts are formed on device
@@ -308,47 +397,59 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
             if (scout == 0) break;
         }
     }
-    cplx w[N];
-#pragma unroll
-    for (int j = 0; j < N; j++) w[j] = mk((double)wf[j].re, (double)wf[j].im);
-    double gap;
-    int jsel = select_root<N>(w, P.branch_rank, gap);
-    if (scout == 0 && gap < 1e-3) {
+    float gapf;
+    int jsel = select_root_f32<N>(wf, P.branch_rank, gapf);
+    if (scout == 0 && gapf < 1e-3f) {
         // near-tie in the ranking: one more (cubic) sweep takes the scout to FP32 precision before deciding
         scout = aberth_sweep_f32<N>(cff, wf);
         if (scout != 2) scout = 0;
-#pragma unroll
-        for (int j = 0; j < N; j++) w[j] = mk((double)wf[j].re, (double)wf[j].im);
-        jsel = select_root<N>(w, P.branch_rank, gap);
+        jsel = select_root_f32<N>(wf, P.branch_rank, gapf);
     }
-    cplx ws = w[0];
+    cplxf wsf = wf[0];
 #pragma unroll
     for (int j = 1; j < N; j++)
-        if (j == jsel) ws = w[j];
+        if (j == jsel) wsf = wf[j];
+    cplx ws = mk((double)wsf.re, (double)wsf.im);
+    double gap = (double)gapf;
     bool full = (scout != 0) || (gap < 1e-5);
     bool newton_done = false;
     if (!full) {
         // ---- FP64 Newton on the selected root only (~1e-6 -> 1e-12 -> rounding level); accepted when the last
         //      correction applied is below 1e-10 |w| (the iterate is then exact to rounding)
-        double c2 = 1.0, w2 = 1.0;
-#pragma unroll
-        for (int it = 0; it < 3; it++) {
-            if (it < 2 || c2 > 1e-20 * w2) {
-                cplx pv, dv;
-                horner2<N>(cf, ws, pv, dv);
-                const double d2 = abs2(dv);
-                cplx corr = mk(0.0, 0.0);
-                if (d2 > 1e-280 && d2 < 1e280) corr = fast_rcp(d2) * (pv * conj(dv));
-                ws = ws - corr;
-                c2 = abs2(corr);
-                w2 = abs2(ws);
-            }
+        double c2, w2;
+        {
+            // step 1: Newton
+            cplx pv, dv;
+            horner2<N>(cf, ws, pv, dv);
+            const double d2 = abs2(dv);
+            cplx dinv = mk(0.0, 0.0);   // 1/P'(w)
+            if (d2 > 1e-280 && d2 < 1e280) dinv = fast_rcp(d2) * conj(dv);
+            ws = ws - pv * dinv;
+            // step 2: chord step with the same 1/P' (error ~ e0 e1, already below rounding when e0 ~ 1e-6)
+            const cplx corr = horner1<N>(cf, ws) * dinv;
+            ws = ws - corr;
+            c2 = abs2(corr);
+            w2 = abs2(ws);
+        }
+        if (c2 > 1e-24 * w2) {
+            // slow case (close roots): one more full Newton step, judged by its own correction
+            cplx pv, dv;
+            horner2<N>(cf, ws, pv, dv);
+            const double d2 = abs2(dv);
+            cplx corr = mk(0.0, 0.0);
+            if (d2 > 1e-280 && d2 < 1e280) corr = fast_rcp(d2) * (pv * conj(dv));
+            ws = ws - corr;
+            c2 = abs2(corr);
+            w2 = abs2(ws);
         }
         newton_done = (c2 <= 1e-20 * w2);
         full = !newton_done;
     }
     if (full) {
         // ---- FP64 simultaneous solve from the scout's roots (near-tie in the ranking, or the scout/Newton had doubts)
+        cplx w[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) w[j] = mk((double)wf[j].re, (double)wf[j].im);
         if (scout == 2) {
             // scout lost: restart cold in FP64
             const cplx c = (1.0 / N) * g[1];
@@ -399,6 +500,31 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     const cplx mu = beta * ws;
     const double n2 = abs2(mu);
     if (st == ILA_OK && !(n2 >= P.beta2)) st = ILA_NO_QL;
+
+    if (!WANT_TAIL && !REAL_PATH) {
+        // L[1,1] only: the two reflectors of ql_X! (infqltoeplitz.jl:28-37) touch X[1,m-1] through column m-1 alone, so
+        // the general code below collapses to a closed form.  With V_1 = 1: X[2,m] = -c_abs (real), ν = -‖(c_abs, β)‖,
+        // v = β/(ξ1+ν), τ = (ξ1+ν)/ν (real), y = X[1,m-1] - v τ (X[2,m-1] + conj(v) X[1,m-1]); the k = 1 reflector and
+        // the sign normalisation then give L[1,1] = sign(-c_abs) |y|.
+        const double c_abs = fast_sqrt(n2 - P.beta2);
+        const double normu = fast_sqrt(c_abs * c_abs + P.beta2);
+        const double xi = -(c_abs + normu);
+        const cplx v = fast_rcp(xi) * beta;
+        const double t2 = xi * fast_rcp(-normu);
+        const cplx x2 = (-c_abs) * (g[1] - ws);
+        const cplx vA = t2 * (x2 + conj(v) * adiag);
+        const cplx y = adiag - v * vA;
+        const double ay = fast_sqrt(abs2(y));
+        const double qn = __longlong_as_double(0x7ff8000000000000LL);
+        if (G.absout) {
+            G.absout[idx] = (st == ILA_OK) ? ay : -1.0;
+        } else {
+            status[idx] = st;
+            const double l11 = (c_abs == 0.0) ? copysign(ay, y.re) : -ay;
+            reinterpret_cast<double2 *>(L11)[idx] = (st == ILA_OK) ? make_double2(l11, 0.0) : make_double2(qn, qn);
+        }
+        continue;
+    }
 
     // eigenvector of the companion matrix in closed form (V_1 = 1): V_{i+1} = g_i - w V_i
     cplx V[N];
@@ -539,8 +665,22 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     }
     if (n <= 0) return 0;
     const int threads = 128;
-    // shifts per thread: consecutive shifts share a warm start; keep >= ~16 warps per SM in flight
-    int spt = (int)(n / (148 * 12 * 32));
+    // shifts per thread: consecutive shifts share a warm start (longer runs amortise the cold start), but the grid
+    // should still fill every SM to its resident-block limit: the smallest spt for which the grid is one full wave
+    static int wave_cache[2] = {0, 0};   // resident blocks of this instantiation over the whole GPU (tail / no tail)
+    int wave_blocks = wave_cache[d_tail ? 1 : 0];
+    if (wave_blocks == 0) {
+        int dev = 0, sms = 148, per_sm = 4;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (d_tail)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ql_toeplitz_l11_kernel<N, REAL_PATH, true>, threads, 0);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ql_toeplitz_l11_kernel<N, REAL_PATH, false>, threads, 0);
+        wave_blocks = sms * (per_sm > 0 ? per_sm : 1);
+        wave_cache[d_tail ? 1 : 0] = wave_blocks;
+    }
+    int spt = (int)((n + (int64_t)wave_blocks * threads - 1) / ((int64_t)wave_blocks * threads));
     if (g_tz_spt > 0) spt = g_tz_spt;
     if (spt < 1) spt = 1;
     if (spt > 16) spt = 16;
