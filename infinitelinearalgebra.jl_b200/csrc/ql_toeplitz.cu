@@ -15,6 +15,7 @@
 // eigenvector in closed form from the companion structure (V_1 = 1, V_{i+1} = g_i - w V_i).
 // Everything is FP64/ComplexF64 on the CUDA cores; 36 B of HBM traffic per shift, so the kernel is FP64-pipe bound.
 #include "ila_common.cuh"
+#include <cstdlib>
 
 namespace ila {
 
@@ -320,7 +321,7 @@ struct TzGrid {
 // Any doubt (large corrections, near-tie in the ranking, slow Newton) falls back to full simultaneous convergence, so
 // the result never depends on the warm start.
 template <int N, bool REAL_PATH, bool WANT_TAIL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (N <= 4 && !WANT_TAIL) ? 7 : 1)
 ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t n, int spt, double *__restrict__ L11,
                        double *__restrict__ tail, int32_t *__restrict__ status, TzGrid G)
 {
@@ -664,7 +665,7 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
         P.unit[j] = cplx{cos(th), sin(th)};
     }
     if (n <= 0) return 0;
-    const int threads = 128;
+    static const int threads = getenv("ILA_TZ_THREADS") ? atoi(getenv("ILA_TZ_THREADS")) : 128;   // tuning knob
     // shifts per thread: consecutive shifts share a warm start (longer runs amortise the cold start), but the grid
     // should still fill every SM to its resident-block limit: the smallest spt for which the grid is one full wave
     static int wave_cache[2] = {0, 0};   // resident blocks of this instantiation over the whole GPU (tail / no tail)
@@ -681,6 +682,7 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
         wave_cache[d_tail ? 1 : 0] = wave_blocks;
     }
     int spt = (int)((n + (int64_t)wave_blocks * threads - 1) / ((int64_t)wave_blocks * threads));
+    while (spt & (spt - 1)) spt &= spt - 1;   // power of two: runs then do not straddle the rows of power-of-two grids
     if (g_tz_spt > 0) spt = g_tz_spt;
     if (spt < 1) spt = 1;
     if (spt > 16) spt = 16;
