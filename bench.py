@@ -30,8 +30,9 @@ BULLHEAD_COLUMN = np.array([2j, 0.0, 0.0, 1.0, 0.7])      # BandedMatrix(-3=>7/1
 NX = NY = 1024
 BYTES_PER_POINT = 36            # 16 (λ) + 16 (L11) + 4 (status): SURVEY §8d
 FLOPS_PER_POINT_LAPACK = 6.9e3  # LAPACK-style count of the reference's per-λ work, for context
-FP64_FLOPS_PER_POINT = 351.0    # FP64 flops this kernel EXECUTES per shift (ncu op counts, profiles/r01_k3_ql_toeplitz_ncu_full.txt)
-K3_DRAM_TRAFFIC = 24.4e6        # dram read+write bytes of one 1024x1024 launch (same capture)
+FP64_FLOPS_PER_POINT = 241.0    # FP64 flops this kernel EXECUTES per shift (ncu op counts, profiles/r01_k3_ql_toeplitz_ncu_full.txt)
+K3_DRAM_TRAFFIC = 20.5e6        # dram read+write bytes of one 1024x1024 launch (same capture)
+K3_INSTR_PER_POINT = 905.0      # thread-level instructions issued per shift (smsp__inst_executed.sum * 32 / 2^20, same capture)
 BYTES_PER_COLUMN = 72           # Bessel (l=u=1): SURVEY §8d
 FLOPS_PER_COLUMN = 42
 
@@ -282,6 +283,9 @@ def run_ours(args, rank, local_rank, world):
     hbm_peak, peak_kind = measured_peaks()
     achieved_gbs = BYTES_PER_POINT * n / (ms_step * 1e-3) / 1e9
     fp64_peak = ila_b200.fp64_peak_tflops()
+    clk = sampler.summary()
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_clock_ghz = (clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0) / 1e3
     line = {
         "metric": "bullhead_ql_lambda_points_per_s", "value": value, "unit": "lambda-points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -301,13 +305,19 @@ def run_ours(args, rank, local_rank, world):
                      "frac": achieved_gbs / hbm_peak, "traffic": K3_DRAM_TRAFFIC if n == NX * NY else None,
                      "peak_kind": peak_kind,
                      "kernel": "ql_toeplitz_l11_kernel<4,false,false>", "bytes_per_unit": BYTES_PER_POINT,
-                     "note": "FP64-pipe bound, not HBM bound: see roofline_fp64"},
+                     "note": "issue-slot / FP-latency bound, not HBM bound: see roofline_issue and roofline_fp64"},
+        "roofline_issue": {"bound": "warp-instruction issue (4 schedulers/SM, 1 instr/cycle each)",
+                           "achieved": K3_INSTR_PER_POINT / 32 * n / (ms_step * 1e-3) / 1e9,
+                           "peak": sm_count * 4 * sm_clock_ghz, "unit": "G warp-instr/s",
+                           "frac": K3_INSTR_PER_POINT / 32 * n / (ms_step * 1e-3) / 1e9 / (sm_count * 4 * sm_clock_ghz),
+                           "instr_per_unit": K3_INSTR_PER_POINT,
+                           "note": "per shift: ~148 FP64 + ~400 FP32 arithmetic instructions, rest selects/moves/compares"},
         "roofline_fp64": {"bound": "fp64", "achieved": FP64_FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12,
                           "peak": fp64_peak, "unit": "TFLOP/s",
                           "frac": FP64_FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12 / fp64_peak,
                           "flops_per_unit": FP64_FLOPS_PER_POINT, "peak_kind": "measured DFMA probe (this run)",
-                          "note": "executed FP64 flops (ncu); the kernel also runs ~0.8k FP32 instr/shift on the FP32 pipe "
-                                  "and is issue-slot bound (ncu: issue active 69-75 %); the reference's LAPACK path is "
+                          "note": "executed FP64 flops (ncu); the kernel also runs ~400 FP32 instr/shift on the FP32 pipe "
+                                  "and is issue-slot bound (ncu: issue active 65 %); the reference's LAPACK path is "
                                   f"~{FLOPS_PER_POINT_LAPACK:.0f} flop/shift"},
         "clocks": sampler.summary(),
     }
