@@ -140,6 +140,23 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(torch, local_rank: int) -> str:
+    """Multi-rank runs: pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE the
+    pinned e2e buffers are allocated, so that 8 ranks' PCIe copies do not all cross the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"bound to {len(cpus)} CPUs ({cpus[0]}..{cpus[-1]})"
+    except Exception as e:   # affinity is an optimisation, never a requirement
+        return f"not bound ({type(e).__name__})"
+
+
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
@@ -154,6 +171,7 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.check(ila_b200.lib().ila_set_device(local_rank))
+    numa = bind_to_gpu_numa(torch, local_rank) if world > 1 else "not bound (single rank)"
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -295,7 +313,7 @@ def run_ours(args, rank, local_rank, world):
                    f"shift-grid sharding x{world}, no collective on the data path"},
         "e2e": {"value": e2e_value, "unit": "lambda-points/s", "h2d_bytes_per_step": 16 * n,
                 "d2h_bytes_per_step": 20 * n, "ms_per_step": e2e_ms, "host_matches_device": same,
-                "api": "ila_ql_toeplitz_l11_c64 (λ array in, complex L11 + status out)"},
+                "api": "ila_ql_toeplitz_l11_c64 (λ array in, complex L11 + status out)", "host_affinity": numa},
         "e2e_grid": {"value": n * world / (grid_ms * 1e-3), "unit": "lambda-points/s", "ms_per_step": grid_ms,
                      "h2d_bytes_per_step": 8 * (NX + NY), "d2h_bytes_per_step": 8 * n,
                      "api": "ila_ql_toeplitz_absl11_grid_c64 = the example's ℓ11.(Ref(A), x' .+ y.*im): ranges in, "
