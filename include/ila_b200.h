@@ -181,6 +181,16 @@ int ila_ql_blocktri_l11_f64_dev(int n, const double *c, const double *a, const d
                                 int64_t batch, double atol, int maxit, double *d_L11, int32_t *d_iters, int32_t *d_status,
                                 void *stream);
 
+/* Complex eltype (blocks and/or energies complex, e.g. `A - 5im*I`, test/test_periodic.jl:20-26): the QL loop runs down
+ * to k = 1 and L[1,1] is complex.  Parity bar 1e-12 against the oracle (see csrc/ql_blocktri.cu header). */
+int ila_ql_blocktri_l11_c64(int n, const ila_c64 *c, const ila_c64 *a, const ila_c64 *b, int n_dl, const ila_c64 *dl_head,
+                            int n_d, const ila_c64 *d_head, int n_du, const ila_c64 *du_head, const ila_c64 *energy,
+                            int64_t batch, double atol, int maxit, ila_c64 *L11, int32_t *iters, int32_t *status, int ngpus);
+int ila_ql_blocktri_l11_c64_dev(int n, const ila_c64 *c, const ila_c64 *a, const ila_c64 *b, int n_dl, const ila_c64 *dl_head,
+                                int n_d, const ila_c64 *d_head, int n_du, const ila_c64 *du_head, const ila_c64 *d_energy,
+                                int64_t batch, double atol, int maxit, ila_c64 *d_L11, int32_t *d_iters, int32_t *d_status,
+                                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -272,13 +272,14 @@ class BlockTridiagonal:
         self.overrides[ij] = v
 
     def _heads(self):
-        d_head = [np.array(m, dtype=float, copy=True) for m in self.d[0]]
+        dt = complex if any(np.iscomplexobj(np.asarray(m)) for m in list(self.d[0]) + [self.d[1]]) else float
+        d_head = [np.array(m, dtype=dt, copy=True) for m in self.d[0]]
         for (i, j), v in self.overrides.items():
             n = np.asarray(self.d[1]).shape[0]
             if i > n or j > n:
                 raise IndexError("only perturbations of the first diagonal block are supported")
             if not d_head:
-                d_head = [np.array(self.d[1], dtype=float, copy=True)]
+                d_head = [np.array(self.d[1], dtype=dt, copy=True)]
             d_head[0][i - 1, j - 1] = v
         return list(self.dl[0]), d_head, list(self.du[0])
 
@@ -289,7 +290,7 @@ def ql(A, branch=1):
         dlh, dh, duh = A._heads()
         L, it, st = _b.ql_blocktri_l11(dlh, dh, duh, A.dl[1], A.d[1], A.du[1], [A.shift])
         _raise_status(st[0], "ql(BlockTridiagonal)")
-        return _BlockQL(float(L[0]))
+        return _BlockQL(complex(L[0]) if np.iscomplexobj(L) else float(L[0]))
     l, u = A.bandwidths
     if u != 1:
         raise NotImplementedError("only u == 1 (ql_pruneband is undefined upstream)")

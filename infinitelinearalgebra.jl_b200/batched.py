@@ -106,10 +106,10 @@ def ql_perttoeplitz_l11(head, data_column, lambdas, branch_rank: int = 1, want_h
 # K6: block-tridiagonal Toeplitz-tail QL
 # ------------------------------------------------------------------------------------------------
 
-def _blocks(lst, n):
+def _blocks(lst, n, dt=np.float64):
     if lst is None or len(lst) == 0:
         return None, 0
-    arr = np.stack([np.asfortranarray(np.asarray(m, dtype=np.float64)).reshape(-1, order="F") for m in lst])
+    arr = np.stack([np.asfortranarray(np.asarray(m, dtype=dt)).reshape(-1, order="F") for m in lst])
     assert arr.shape[1] == n * n
     return np.ascontiguousarray(arr), len(lst)
 
@@ -117,20 +117,27 @@ def _blocks(lst, n):
 def ql_blocktri_l11(dl_head, d_head, du_head, c, a, b, energies, atol=1e-10, maxit=1_000_000, ngpus=1):
     """L[1,1] of ql(A - x*I) over `energies` for the block-tridiagonal perturbed Toeplitz operator
     A = BlockTridiagonal(Vcat(dl_head, Fill(c,∞)), Vcat(d_head, Fill(a,∞)), Vcat(du_head, Fill(b,∞)))
-    (reference src/infql.jl:166-209; examples/periodicschrodinger.jl:13-27).  Returns (L11, iters, status)."""
-    c = np.asarray(c, dtype=np.float64)
+    (reference src/infql.jl:166-209; examples/periodicschrodinger.jl:13-27).  Real blocks and energies run the real
+    kernel (QL loop down to k = 2, bit-exact against the oracle); any complex block or energy (`A - 5im*I`,
+    test/test_periodic.jl:20-26) runs the complex one (loop down to k = 1, complex L[1,1]).
+    Returns (L11, iters, status)."""
+    mats = [c, a, b] + list(dl_head or []) + list(d_head or []) + list(du_head or [])
+    cplx = np.iscomplexobj(np.asarray(energies)) or any(np.iscomplexobj(np.asarray(m)) for m in mats)
+    dt = np.complex128 if cplx else np.float64
+    c = np.asarray(c, dtype=dt)
     n = c.shape[0]
-    flat = lambda m: np.ascontiguousarray(np.asarray(m, dtype=np.float64).reshape(-1, order="F"))
+    flat = lambda m: np.ascontiguousarray(np.asarray(m, dtype=dt).reshape(-1, order="F"))
     cc, aa, bb = flat(c), flat(a), flat(b)
-    dlh, ndl = _blocks(dl_head, n)
-    dh, nd = _blocks(d_head, n)
-    duh, ndu = _blocks(du_head, n)
-    e = np.ascontiguousarray(np.asarray(energies, dtype=np.float64).reshape(-1))
-    L11 = np.empty(e.size)
+    dlh, ndl = _blocks(dl_head, n, dt)
+    dh, nd = _blocks(d_head, n, dt)
+    duh, ndu = _blocks(du_head, n, dt)
+    e = np.ascontiguousarray(np.asarray(energies, dtype=dt).reshape(-1))
+    L11 = np.empty(e.size, dtype=dt)
     iters = np.empty(e.size, dtype=np.int32)
     status = np.empty(e.size, dtype=np.int32)
-    check(lib().ila_ql_blocktri_l11_f64(n, ptr(cc), ptr(aa), ptr(bb), ndl, ptr(dlh), nd, ptr(dh), ndu, ptr(duh), ptr(e),
-                                        e.size, float(atol), int(maxit), ptr(L11), ptr(iters), ptr(status), ngpus))
+    fn = lib().ila_ql_blocktri_l11_c64 if cplx else lib().ila_ql_blocktri_l11_f64
+    check(fn(n, ptr(cc), ptr(aa), ptr(bb), ndl, ptr(dlh), nd, ptr(dh), ndu, ptr(duh), ptr(e),
+             e.size, float(atol), int(maxit), ptr(L11), ptr(iters), ptr(status), ngpus))
     shape = np.asarray(energies).shape
     return L11.reshape(shape), iters.reshape(shape), status.reshape(shape)
 

@@ -72,16 +72,25 @@ int launch_chol_forward(int u, const CholFwdArgs &a, cudaStream_t s);
 // from ql_blocktri.cu
 constexpr int kBtMaxN = 4;
 constexpr int kBtMaxHead = 4;
-struct BlockTriParams {
+template <typename T>
+struct BlockTriParamsT {
     int n, n_dl, n_d, n_du, maxit;
     double atol;
-    double c[kBtMaxN * kBtMaxN], a[kBtMaxN * kBtMaxN], b[kBtMaxN * kBtMaxN];
-    double dl_head[kBtMaxHead][kBtMaxN * kBtMaxN];
-    double d_head[kBtMaxHead][kBtMaxN * kBtMaxN];
-    double du_head[kBtMaxHead][kBtMaxN * kBtMaxN];
+    T c[kBtMaxN * kBtMaxN], a[kBtMaxN * kBtMaxN], b[kBtMaxN * kBtMaxN];
+    T dl_head[kBtMaxHead][kBtMaxN * kBtMaxN];
+    T d_head[kBtMaxHead][kBtMaxN * kBtMaxN];
+    T du_head[kBtMaxHead][kBtMaxN * kBtMaxN];
 };
+using BlockTriParams = BlockTriParamsT<double>;
+using BlockTriParamsC = BlockTriParamsT<cplx>;
 int launch_ql_blocktri(const BlockTriParams &P, const double *d_energy, int64_t batch, double *d_L11, int32_t *d_iters,
                        int32_t *d_status, cudaStream_t s);
+int launch_ql_blocktri_c(const BlockTriParamsC &P, const cplx *d_energy, int64_t batch, cplx *d_L11, int32_t *d_iters,
+                         int32_t *d_status, cudaStream_t s);
+static inline int launch_ql_blocktri_any(const BlockTriParams &P, const double *e, int64_t batch, double *L, int32_t *it,
+                                         int32_t *st, cudaStream_t s) { return launch_ql_blocktri(P, e, batch, L, it, st, s); }
+static inline int launch_ql_blocktri_any(const BlockTriParamsC &P, const cplx *e, int64_t batch, cplx *L, int32_t *it,
+                                         int32_t *st, cudaStream_t s) { return launch_ql_blocktri_c(P, e, batch, L, it, st, s); }
 
 // ---- per-device grow-only buffer pool (host entry points only) ---------------------------------------
 constexpr int kMaxDev = 16;
@@ -469,9 +478,11 @@ int ila_ql_perttoeplitz_l11_f64(int l, int u, int p, const double *head, const d
 
 // ================================ K6: block-tridiagonal Toeplitz-tail QL ================================
 
-static int blocktri_params(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
-                           int n_d, const double *d_head, int n_du, const double *du_head, double atol, int maxit,
-                           BlockTriParams *P)
+} // extern "C" (templates below have C++ linkage)
+
+template <typename T>
+static int blocktri_params(int n, const T *c, const T *a, const T *b, int n_dl, const T *dl_head, int n_d, const T *d_head,
+                           int n_du, const T *du_head, double atol, int maxit, BlockTriParamsT<T> *P)
 {
     if (n < 1 || n > kBtMaxN) return set_error(ILA_ERR_UNSUPPORTED, "ql_blocktri: block size n must be in 1..4");
     if (n_dl < 0 || n_d < 0 || n_du < 0 || n_dl > kBtMaxHead || n_d > kBtMaxHead || n_du + 1 > kBtMaxHead)
@@ -481,34 +492,35 @@ static int blocktri_params(int n, const double *c, const double *a, const double
     memset(P, 0, sizeof(*P));
     P->n = n; P->n_dl = n_dl; P->n_d = n_d; P->n_du = n_du; P->maxit = maxit; P->atol = atol;
     const int nn = n * n;
-    memcpy(P->c, c, sizeof(double) * nn);
-    memcpy(P->a, a, sizeof(double) * nn);
-    memcpy(P->b, b, sizeof(double) * nn);
-    for (int k = 0; k < n_dl; k++) memcpy(P->dl_head[k], dl_head + k * nn, sizeof(double) * nn);
-    for (int k = 0; k < n_d; k++) memcpy(P->d_head[k], d_head + k * nn, sizeof(double) * nn);
-    for (int k = 0; k < n_du; k++) memcpy(P->du_head[k], du_head + k * nn, sizeof(double) * nn);
+    memcpy(P->c, c, sizeof(T) * nn);
+    memcpy(P->a, a, sizeof(T) * nn);
+    memcpy(P->b, b, sizeof(T) * nn);
+    for (int k = 0; k < n_dl; k++) memcpy(P->dl_head[k], dl_head + k * nn, sizeof(T) * nn);
+    for (int k = 0; k < n_d; k++) memcpy(P->d_head[k], d_head + k * nn, sizeof(T) * nn);
+    for (int k = 0; k < n_du; k++) memcpy(P->du_head[k], du_head + k * nn, sizeof(T) * nn);
     return 0;
 }
 
-int ila_ql_blocktri_l11_f64_dev(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
-                                int n_d, const double *d_head, int n_du, const double *du_head, const double *d_energy,
-                                int64_t batch, double atol, int maxit, double *d_L11, int32_t *d_iters, int32_t *d_status,
-                                void *stream)
+template <typename T>
+static int blocktri_dev(int n, const T *c, const T *a, const T *b, int n_dl, const T *dl_head, int n_d, const T *d_head,
+                        int n_du, const T *du_head, const T *d_energy, int64_t batch, double atol, int maxit, T *d_L11,
+                        int32_t *d_iters, int32_t *d_status, void *stream)
 {
     if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
-    BlockTriParams P;
-    int rc = blocktri_params(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, atol, maxit, &P);
+    BlockTriParamsT<T> P;
+    int rc = blocktri_params<T>(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, atol, maxit, &P);
     if (rc) return rc;
-    return launch_ql_blocktri(P, d_energy, batch, d_L11, d_iters, d_status, (cudaStream_t)stream);
+    return launch_ql_blocktri_any(P, d_energy, batch, d_L11, d_iters, d_status, (cudaStream_t)stream);
 }
 
-int ila_ql_blocktri_l11_f64(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
-                            int n_d, const double *d_head, int n_du, const double *du_head, const double *energy,
-                            int64_t batch, double atol, int maxit, double *L11, int32_t *iters, int32_t *status, int ngpus)
+template <typename T>
+static int blocktri_host(int n, const T *c, const T *a, const T *b, int n_dl, const T *dl_head, int n_d, const T *d_head,
+                         int n_du, const T *du_head, const T *energy, int64_t batch, double atol, int maxit, T *L11,
+                         int32_t *iters, int32_t *status, int ngpus)
 {
     if (batch < 0 || (batch > 0 && (!energy || !L11 || !iters || !status))) return set_error(ILA_ERR_ARG, "ql_blocktri: bad arguments");
-    BlockTriParams P;
-    int rc = blocktri_params(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, atol, maxit, &P);
+    BlockTriParamsT<T> P;
+    int rc = blocktri_params<T>(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, atol, maxit, &P);
     if (rc) return rc;
     int G = 0;
     if ((rc = resolve_ngpus(ngpus, &G))) return rc;
@@ -521,16 +533,16 @@ int ila_ql_blocktri_l11_f64(int n, const double *c, const double *a, const doubl
         if (cnt <= 0) continue;
         const int pd = phys(d, G);
         if ((rc = dev_init(pd))) return rc;
-        double *d_e, *d_L;
+        T *d_e, *d_L;
         int32_t *d_it, *d_st;
         if ((rc = dev_buf_t(pd, 0, (size_t)cnt, &d_e))) return rc;
         if ((rc = dev_buf_t(pd, 1, (size_t)cnt, &d_L))) return rc;
         if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
         if ((rc = dev_buf_t(pd, 3, (size_t)cnt, &d_it))) return rc;
         cudaStream_t s = g_dev[pd].stream;
-        ILA_CUDA_CHECK(cudaMemcpyAsync(d_e, energy + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
-        if ((rc = launch_ql_blocktri(P, d_e, cnt, d_L, d_it, d_st, s))) return rc;
-        ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + lo, d_L, sizeof(double) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_e, energy + lo, sizeof(T) * cnt, cudaMemcpyHostToDevice, s));
+        if ((rc = launch_ql_blocktri_any(P, d_e, cnt, d_L, d_it, d_st, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + lo, d_L, sizeof(T) * cnt, cudaMemcpyDeviceToHost, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(iters + lo, d_it, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
     }
@@ -542,6 +554,44 @@ int ila_ql_blocktri_l11_f64(int n, const double *c, const double *a, const doubl
     }
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
+}
+
+extern "C" {
+
+int ila_ql_blocktri_l11_f64_dev(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
+                                int n_d, const double *d_head, int n_du, const double *du_head, const double *d_energy,
+                                int64_t batch, double atol, int maxit, double *d_L11, int32_t *d_iters, int32_t *d_status,
+                                void *stream)
+{
+    return blocktri_dev<double>(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, d_energy, batch, atol, maxit, d_L11,
+                                d_iters, d_status, stream);
+}
+
+int ila_ql_blocktri_l11_f64(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
+                            int n_d, const double *d_head, int n_du, const double *du_head, const double *energy,
+                            int64_t batch, double atol, int maxit, double *L11, int32_t *iters, int32_t *status, int ngpus)
+{
+    return blocktri_host<double>(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, energy, batch, atol, maxit, L11,
+                                 iters, status, ngpus);
+}
+
+int ila_ql_blocktri_l11_c64_dev(int n, const ila_c64 *c, const ila_c64 *a, const ila_c64 *b, int n_dl, const ila_c64 *dl_head,
+                                int n_d, const ila_c64 *d_head, int n_du, const ila_c64 *du_head, const ila_c64 *d_energy,
+                                int64_t batch, double atol, int maxit, ila_c64 *d_L11, int32_t *d_iters, int32_t *d_status,
+                                void *stream)
+{
+    return blocktri_dev<cplx>(n, (const cplx *)c, (const cplx *)a, (const cplx *)b, n_dl, (const cplx *)dl_head, n_d,
+                              (const cplx *)d_head, n_du, (const cplx *)du_head, (const cplx *)d_energy, batch, atol, maxit,
+                              (cplx *)d_L11, d_iters, d_status, stream);
+}
+
+int ila_ql_blocktri_l11_c64(int n, const ila_c64 *c, const ila_c64 *a, const ila_c64 *b, int n_dl, const ila_c64 *dl_head,
+                            int n_d, const ila_c64 *d_head, int n_du, const ila_c64 *du_head, const ila_c64 *energy,
+                            int64_t batch, double atol, int maxit, ila_c64 *L11, int32_t *iters, int32_t *status, int ngpus)
+{
+    return blocktri_host<cplx>(n, (const cplx *)c, (const cplx *)a, (const cplx *)b, n_dl, (const cplx *)dl_head, n_d,
+                               (const cplx *)d_head, n_du, (const cplx *)du_head, (const cplx *)energy, batch, atol, maxit,
+                               (cplx *)L11, iters, status, ngpus);
 }
 
 int ila_ql_set_shifts_per_thread(int spt)

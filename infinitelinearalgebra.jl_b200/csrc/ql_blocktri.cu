@@ -11,7 +11,11 @@
 // examples/periodicschrodinger.jl, 4 for the "bi" example of test/test_periodic.jl:42-60); the fixed-point loop, its
 // convergence test and the finite head QL run on device, one energy per thread, no host round trip per iteration.
 // Arithmetic is the reference's operation order with no fused multiply-add and IEEE sqrt/div, so the iterates — and
-// therefore the iteration at which the 1e-10 test fires — reproduce the oracle bit for bit.
+// therefore the iteration at which the 1e-10 test fires — reproduce the oracle bit for bit (real eltype).
+// Complex eltype (test/test_periodic.jl:20-26, `- 5im*I`): the same code instantiated with a complex scalar — the QL loop
+// then runs down to k = 1 (the (T<:Real) bound of examples/jacobi.jl:63 no longer skips it), inner products conjugate
+// the reflector, tau is complex; checked against the oracle to 1e-12 (complex division/multiplication orders differ
+// between numpy, Julia and this file at the rounding level, so bit equality is not claimed there).
 #include "ila_common.cuh"
 
 namespace ila {
@@ -19,52 +23,119 @@ namespace ila {
 constexpr int kBtMaxN = 4;      // block size n <= 4
 constexpr int kBtMaxHead = 4;   // head blocks N <= 4
 
-struct BlockTriParams {
+template <typename T>
+struct BlockTriParamsT {
     int n, n_dl, n_d, n_du, maxit;
     double atol;
-    double c[kBtMaxN * kBtMaxN], a[kBtMaxN * kBtMaxN], b[kBtMaxN * kBtMaxN];   // tail blocks, column-major n x n
-    double dl_head[kBtMaxHead][kBtMaxN * kBtMaxN];   // A[Block(k+1,k)], k = 1..n_dl
-    double d_head[kBtMaxHead][kBtMaxN * kBtMaxN];    // A[Block(k,k)]
-    double du_head[kBtMaxHead][kBtMaxN * kBtMaxN];   // A[Block(k,k+1)]
+    T c[kBtMaxN * kBtMaxN], a[kBtMaxN * kBtMaxN], b[kBtMaxN * kBtMaxN];   // tail blocks, column-major n x n
+    T dl_head[kBtMaxHead][kBtMaxN * kBtMaxN];   // A[Block(k+1,k)], k = 1..n_dl
+    T d_head[kBtMaxHead][kBtMaxN * kBtMaxN];    // A[Block(k,k)]
+    T du_head[kBtMaxHead][kBtMaxN * kBtMaxN];   // A[Block(k,k+1)]
 };
+using BlockTriParams = BlockTriParamsT<double>;
+using BlockTriParamsC = BlockTriParamsT<cplx>;
 
+// ---- scalar layer: no fused multiply-add, IEEE sqrt/div; real overloads are the reference's operations one for one ----
 __device__ __forceinline__ double bmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double badd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double bsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double bdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double bconj(double a) { return a; }
+__device__ __forceinline__ double babs2(double a) { return bmul(a, a); }
+__device__ __forceinline__ double breal(double a) { return a; }
+__device__ __forceinline__ double badd_real(double a, double v) { return badd(a, v); }   // a + v, v real
+__device__ __forceinline__ double bdiv_real(double a, double v) { return bdiv(a, v); }   // a / v, v real
+__device__ __forceinline__ void bset_real(double &a, double v) { a = v; }
+__device__ __forceinline__ bool bisnan(double a) { return a != a; }
 
-// Householder QL of the R x C array X (row-major registers/local), reference loop: k = min(R,C)..2 (real eltype),
-// reflector over rows k..1 of column C-min+k, applied to the columns on its left.  tau[k-1] receives tau_k.
-template <int R, int C>
-__device__ __forceinline__ void dense_ql_real(double (&X)[R][C], double (&tau)[(R < C ? R : C)])
+__device__ __forceinline__ cplx bmul(cplx a, cplx b)
+{
+    return cplx{bsub(bmul(a.re, b.re), bmul(a.im, b.im)), badd(bmul(a.re, b.im), bmul(a.im, b.re))};
+}
+__device__ __forceinline__ cplx badd(cplx a, cplx b) { return cplx{badd(a.re, b.re), badd(a.im, b.im)}; }
+__device__ __forceinline__ cplx bsub(cplx a, cplx b) { return cplx{bsub(a.re, b.re), bsub(a.im, b.im)}; }
+__device__ __forceinline__ cplx bconj(cplx a) { return cplx{a.re, -a.im}; }
+__device__ __forceinline__ double babs2(cplx a) { return badd(bmul(a.re, a.re), bmul(a.im, a.im)); }
+__device__ __forceinline__ double breal(cplx a) { return a.re; }
+__device__ __forceinline__ cplx badd_real(cplx a, double v) { return cplx{badd(a.re, v), a.im}; }
+__device__ __forceinline__ cplx bdiv_real(cplx a, double v) { return cplx{bdiv(a.re, v), bdiv(a.im, v)}; }
+__device__ __forceinline__ void bset_real(cplx &a, double v) { a = cplx{v, 0.0}; }
+__device__ __forceinline__ bool bisnan(cplx a) { return a.re != a.re || a.im != a.im; }
+__device__ __forceinline__ cplx bdiv(cplx a, cplx b)
+{   // Smith's algorithm (the scaling keeps |b|^2 from over/underflowing)
+    if (fabs(b.re) >= fabs(b.im)) {
+        const double r = bdiv(b.im, b.re), den = badd(b.re, bmul(b.im, r));
+        return cplx{bdiv(badd(a.re, bmul(a.im, r)), den), bdiv(bsub(a.im, bmul(a.re, r)), den)};
+    }
+    const double r = bdiv(b.re, b.im), den = badd(bmul(b.re, r), b.im);
+    return cplx{bdiv(badd(bmul(a.re, r), a.im), den), bdiv(bsub(bmul(a.im, r), a.re), den)};
+}
+template <typename T> struct is_cplx { static constexpr bool value = false; };
+template <> struct is_cplx<cplx> { static constexpr bool value = true; };
+template <typename T> __device__ __forceinline__ T bzero();
+template <> __device__ __forceinline__ double bzero<double>() { return 0.0; }
+template <> __device__ __forceinline__ cplx bzero<cplx>() { return cplx{0.0, 0.0}; }
+
+// One Householder step of the QL loop on column `col` of an array accessed through `at(row, col)`: reflector over rows
+// mu-1 .. 0 (reversed), applied to columns 0 .. col-1 (LinearAlgebra.reflector! / reflectorApply!, src/infql.jl:17-19).
+template <typename T, typename At>
+__device__ __forceinline__ T ql_step(At &&at, int mu, int col)
+{
+    double s = babs2(at(mu - 1, col));
+    for (int i = 1; i < mu; i++) s = badd(s, babs2(at(mu - 1 - i, col)));
+    const double normu = __dsqrt_rn(s);
+    T t = bzero<T>();
+    if (normu != 0.0) {
+        T xi1 = at(mu - 1, col);
+        const double v = copysign(normu, breal(xi1));
+        xi1 = badd_real(xi1, v);
+        bset_real(at(mu - 1, col), -v);
+        for (int i = 1; i < mu; i++) at(mu - 1 - i, col) = bdiv(at(mu - 1 - i, col), xi1);
+        t = bdiv_real(xi1, v);
+    }
+    for (int j = 0; j < col; j++) {
+        T vA = at(mu - 1, j);
+        for (int i = 1; i < mu; i++) vA = badd(vA, bmul(bconj(at(mu - 1 - i, col)), at(mu - 1 - i, j)));
+        vA = bmul(bconj(t), vA);
+        at(mu - 1, j) = bsub(at(mu - 1, j), vA);
+        for (int i = 1; i < mu; i++) at(mu - 1 - i, j) = bsub(at(mu - 1 - i, j), bmul(at(mu - 1 - i, col), vA));
+    }
+    return t;
+}
+
+// Householder QL of the R x C register array X, reference loop: k = min(R,C) .. (real ? 2 : 1); tau[k-1] receives tau_k.
+template <typename T, int R, int C>
+__device__ __forceinline__ void dense_ql(T (&X)[R][C], T (&tau)[(R < C ? R : C)])
 {
     constexpr int MN = R < C ? R : C;
+    constexpr int KLO = is_cplx<T>::value ? 1 : 2;
 #pragma unroll
-    for (int k = 0; k < MN; k++) tau[k] = 0.0;
+    for (int k = 0; k < MN; k++) tau[k] = bzero<T>();
 #pragma unroll
-    for (int k = MN; k >= 2; k--) {
+    for (int k = MN; k >= KLO; k--) {
         const int mu = R - MN + k, nu = C - MN + k;   // 1-based
-        // x = X[mu-1 .. 0][nu-1] (reversed rows)
-        double s = bmul(X[mu - 1][nu - 1], X[mu - 1][nu - 1]);
+        // fully unrolled: every index below is a compile-time constant, X stays in registers
+        double s = babs2(X[mu - 1][nu - 1]);
 #pragma unroll
-        for (int i = 1; i < mu; i++) s = badd(s, bmul(X[mu - 1 - i][nu - 1], X[mu - 1 - i][nu - 1]));
+        for (int i = 1; i < mu; i++) s = badd(s, babs2(X[mu - 1 - i][nu - 1]));
         const double normu = __dsqrt_rn(s);
-        double t = 0.0;
+        T t = bzero<T>();
         if (normu != 0.0) {
-            double xi1 = X[mu - 1][nu - 1];
-            const double v = copysign(normu, xi1);
-            xi1 = badd(xi1, v);
-            X[mu - 1][nu - 1] = -v;
+            T xi1 = X[mu - 1][nu - 1];
+            const double v = copysign(normu, breal(xi1));
+            xi1 = badd_real(xi1, v);
+            bset_real(X[mu - 1][nu - 1], -v);
 #pragma unroll
-            for (int i = 1; i < mu; i++) X[mu - 1 - i][nu - 1] = __ddiv_rn(X[mu - 1 - i][nu - 1], xi1);
-            t = __ddiv_rn(xi1, v);
+            for (int i = 1; i < mu; i++) X[mu - 1 - i][nu - 1] = bdiv(X[mu - 1 - i][nu - 1], xi1);
+            t = bdiv_real(xi1, v);
         }
         tau[k - 1] = t;
 #pragma unroll
         for (int j = 0; j < nu - 1; j++) {
-            double vA = X[mu - 1][j];
+            T vA = X[mu - 1][j];
 #pragma unroll
-            for (int i = 1; i < mu; i++) vA = badd(vA, bmul(X[mu - 1 - i][nu - 1], X[mu - 1 - i][j]));
-            vA = bmul(t, vA);
+            for (int i = 1; i < mu; i++) vA = badd(vA, bmul(bconj(X[mu - 1 - i][nu - 1]), X[mu - 1 - i][j]));
+            vA = bmul(bconj(t), vA);
             X[mu - 1][j] = bsub(X[mu - 1][j], vA);
 #pragma unroll
             for (int i = 1; i < mu; i++) X[mu - 1 - i][j] = bsub(X[mu - 1 - i][j], bmul(X[mu - 1 - i][nu - 1], vA));
@@ -72,20 +143,20 @@ __device__ __forceinline__ void dense_ql_real(double (&X)[R][C], double (&tau)[(
     }
 }
 
-template <int n>
-__global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParams P, const double *__restrict__ energy, int64_t batch,
-                                                             double *__restrict__ L11, int32_t *__restrict__ iters,
+template <typename T, int n>
+__global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParamsT<T> P, const T *__restrict__ energy, int64_t batch,
+                                                             T *__restrict__ L11, int32_t *__restrict__ iters,
                                                              int32_t *__restrict__ status)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= batch) return;
-    const double x = energy[idx];
-    auto blk = [&](const double *m, int i, int j) -> double { return m[i + j * n]; };   // column-major
+    const T x = energy[idx];
+    auto blk = [&](const T *m, int i, int j) -> T { return m[i + j * n]; };   // column-major
     // accessors with the head tables falling back to the Toeplitz blocks; the shift acts on diagonal blocks
-    auto DLk = [&](int k, int i, int j) -> double { return k <= P.n_dl ? blk(P.dl_head[k - 1], i, j) : blk(P.c, i, j); };
-    auto DUk = [&](int k, int i, int j) -> double { return k <= P.n_du ? blk(P.du_head[k - 1], i, j) : blk(P.b, i, j); };
-    auto Dk = [&](int k, int i, int j) -> double {
-        const double v = k <= P.n_d ? blk(P.d_head[k - 1], i, j) : blk(P.a, i, j);
+    auto DLk = [&](int k, int i, int j) -> T { return k <= P.n_dl ? blk(P.dl_head[k - 1], i, j) : blk(P.c, i, j); };
+    auto DUk = [&](int k, int i, int j) -> T { return k <= P.n_du ? blk(P.du_head[k - 1], i, j) : blk(P.b, i, j); };
+    auto Dk = [&](int k, int i, int j) -> T {
+        const T v = k <= P.n_d ? blk(P.d_head[k - 1], i, j) : blk(P.a, i, j);
         return (i == j) ? bsub(v, x) : v;
     };
     int N = P.n_du + 1;
@@ -93,7 +164,7 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParams P, c
     if (P.n_dl > N) N = P.n_dl;
 
     // tail blocks c,a,b = A[Block(N+1,N)], A[Block(N,N)], A[Block(N-1,N)]; start (d,e) = (A[Block(2,3)], A[Block(3,3)])
-    double c[n][n], a[n][n], b[n][n], d[n][n], e[n][n];
+    T c[n][n], a[n][n], b[n][n], d[n][n], e[n][n];
 #pragma unroll
     for (int i = 0; i < n; i++)
 #pragma unroll
@@ -107,10 +178,10 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParams P, c
 
     int32_t st = ILA_NOT_CONVERGED;
     int it = 0;
-    double dn[n][n], en[n][n];
+    T dn[n][n], en[n][n];
     for (it = 1; it <= P.maxit; it++) {
-        double X[2 * n][3 * n];
-        double tau[2 * n];
+        T X[2 * n][3 * n];
+        T tau[2 * n];
 #pragma unroll
         for (int i = 0; i < n; i++)
 #pragma unroll
@@ -118,29 +189,29 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParams P, c
                 X[i][j] = c[i][j];
                 X[i][n + j] = a[i][j];
                 X[i][2 * n + j] = b[i][j];
-                X[n + i][j] = 0.0;
+                X[n + i][j] = bzero<T>();
                 X[n + i][n + j] = d[i][j];
                 X[n + i][2 * n + j] = e[i][j];
             }
-        dense_ql_real<2 * n, 3 * n>(X, tau);
+        dense_ql<T, 2 * n, 3 * n>(X, tau);
         // (d~, e~) = L[1:n,1:n], L[1:n,n+1:2n] (lower triangle of that block), then undo the first n reflectors
 #pragma unroll
         for (int i = 0; i < n; i++)
 #pragma unroll
             for (int j = 0; j < n; j++) {
                 dn[i][j] = X[i][j];
-                en[i][j] = (j <= i) ? X[i][n + j] : 0.0;
+                en[i][j] = (j <= i) ? X[i][n + j] : bzero<T>();
             }
         // Q1 = QLPackedQ(factors[1:n, n+1:2n], tau[1:n]):  H_1 first, then H_2, ... (lmul!)
 #pragma unroll
         for (int k = 1; k <= n; k++) {
 #pragma unroll
             for (int j = 0; j < n; j++) {
-                double vB = dn[k - 1][j], vE = en[k - 1][j];
+                T vB = dn[k - 1][j], vE = en[k - 1][j];
 #pragma unroll
                 for (int i = 0; i < k - 1; i++) {
-                    vB = badd(vB, bmul(X[i][n + k - 1], dn[i][j]));
-                    vE = badd(vE, bmul(X[i][n + k - 1], en[i][j]));
+                    vB = badd(vB, bmul(bconj(X[i][n + k - 1]), dn[i][j]));
+                    vE = badd(vE, bmul(bconj(X[i][n + k - 1]), en[i][j]));
                 }
                 vB = bmul(tau[k - 1], vB);
                 vE = bmul(tau[k - 1], vE);
@@ -160,9 +231,9 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParams P, c
         for (int j = 0; j < n; j++)
 #pragma unroll
             for (int i = 0; i < n; i++) {
-                const double td = bsub(dn[i][j], d[i][j]), te = bsub(en[i][j], e[i][j]);
-                sd = first ? bmul(td, td) : badd(sd, bmul(td, td));
-                se = first ? bmul(te, te) : badd(se, bmul(te, te));
+                const double td = babs2(bsub(dn[i][j], d[i][j])), te = babs2(bsub(en[i][j], e[i][j]));
+                sd = first ? td : badd(sd, td);
+                se = first ? te : badd(se, te);
                 first = false;
             }
         const bool nan = (sd != sd) || (se != se);
@@ -177,14 +248,16 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParams P, c
             }
     }
 
-    double l11 = __longlong_as_double(0x7ff8000000000000LL);
+    T l11;
+    bset_real(l11, __longlong_as_double(0x7ff8000000000000LL));
+    if (is_cplx<T>::value) l11 = bmul(l11, l11);   // NaN in both parts
     if (st == ILA_OK) {
         // finite head: N x N blocks (N <= 4), last block row replaced by (d~, e~)   (src/infql.jl:193-198)
         constexpr int HM = kBtMaxHead * n;
-        double H[HM][HM];
+        T H[HM][HM];
         const int hn = N * n;
         for (int i = 0; i < HM; i++)
-            for (int j = 0; j < HM; j++) H[i][j] = 0.0;
+            for (int j = 0; j < HM; j++) H[i][j] = bzero<T>();
         for (int k = 1; k <= N; k++)
             for (int i = 0; i < n; i++)
                 for (int j = 0; j < n; j++) {
@@ -195,34 +268,15 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParams P, c
                     }
                 }
         for (int i = 0; i < n; i++)
-            for (int j = 0; j < hn; j++) H[(N - 1) * n + i][j] = 0.0;
+            for (int j = 0; j < hn; j++) H[(N - 1) * n + i][j] = bzero<T>();
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
                 if (N >= 2) H[(N - 1) * n + i][(N - 2) * n + j] = dn[i][j];
                 H[(N - 1) * n + i][(N - 1) * n + j] = en[i][j];
             }
         // dense QL of the hn x hn head (runtime size, local memory; executed once per energy)
-        for (int k = hn; k >= 2; k--) {
-            double s = bmul(H[k - 1][k - 1], H[k - 1][k - 1]);
-            for (int i = 1; i < k; i++) s = badd(s, bmul(H[k - 1 - i][k - 1], H[k - 1 - i][k - 1]));
-            const double normu = __dsqrt_rn(s);
-            double t = 0.0;
-            if (normu != 0.0) {
-                double xi1 = H[k - 1][k - 1];
-                const double v = copysign(normu, xi1);
-                xi1 = badd(xi1, v);
-                H[k - 1][k - 1] = -v;
-                for (int i = 1; i < k; i++) H[k - 1 - i][k - 1] = __ddiv_rn(H[k - 1 - i][k - 1], xi1);
-                t = __ddiv_rn(xi1, v);
-            }
-            for (int j = 0; j < k - 1; j++) {
-                double vA = H[k - 1][j];
-                for (int i = 1; i < k; i++) vA = badd(vA, bmul(H[k - 1 - i][k - 1], H[k - 1 - i][j]));
-                vA = bmul(t, vA);
-                H[k - 1][j] = bsub(H[k - 1][j], vA);
-                for (int i = 1; i < k; i++) H[k - 1 - i][j] = bsub(H[k - 1 - i][j], bmul(H[k - 1 - i][k - 1], vA));
-            }
-        }
+        auto at = [&](int i, int j) -> T & { return H[i][j]; };
+        for (int k = hn; k >= (is_cplx<T>::value ? 1 : 2); k--) ql_step<T>(at, k, k - 1);
         l11 = H[0][0];
     }
     L11[idx] = l11;
@@ -230,22 +284,34 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParams P, c
     status[idx] = st;
 }
 
-int launch_ql_blocktri(const BlockTriParams &P, const double *d_energy, int64_t batch, double *d_L11, int32_t *d_iters,
-                       int32_t *d_status, cudaStream_t s)
+template <typename T>
+static int launch_ql_blocktri_t(const BlockTriParamsT<T> &P, const T *d_energy, int64_t batch, T *d_L11, int32_t *d_iters,
+                                int32_t *d_status, cudaStream_t s)
 {
     if (batch <= 0) return 0;
     const int threads = 64;
     const unsigned blocks = (unsigned)((batch + threads - 1) / threads);
     switch (P.n) {
-    case 1: ql_blocktri_l11_kernel<1><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
-    case 2: ql_blocktri_l11_kernel<2><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
-    case 3: ql_blocktri_l11_kernel<3><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
-    case 4: ql_blocktri_l11_kernel<4><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
+    case 1: ql_blocktri_l11_kernel<T, 1><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
+    case 2: ql_blocktri_l11_kernel<T, 2><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
+    case 3: ql_blocktri_l11_kernel<T, 3><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
+    case 4: ql_blocktri_l11_kernel<T, 4><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
     default: return set_error(ILA_ERR_UNSUPPORTED, "ql_blocktri: block size n must be in 1..4");
     }
     count_launch();
     ILA_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+int launch_ql_blocktri(const BlockTriParams &P, const double *d_energy, int64_t batch, double *d_L11, int32_t *d_iters,
+                       int32_t *d_status, cudaStream_t s)
+{
+    return launch_ql_blocktri_t<double>(P, d_energy, batch, d_L11, d_iters, d_status, s);
+}
+int launch_ql_blocktri_c(const BlockTriParamsC &P, const cplx *d_energy, int64_t batch, cplx *d_L11, int32_t *d_iters,
+                         int32_t *d_status, cudaStream_t s)
+{
+    return launch_ql_blocktri_t<cplx>(P, d_energy, batch, d_L11, d_iters, d_status, s);
 }
 
 } // namespace ila

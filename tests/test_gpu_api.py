@@ -82,3 +82,8 @@ def test_periodic_schrodinger(ila):
     xx = np.concatenate([np.arange(-0.95, 0.951, 0.05), np.arange(2.25, 4.0001, 0.125 / 4)])
     L, st = ql_L11(A, xx)
     assert np.all(st == 0) and L[0] == l11
+    # complex non-selfadjoint case of test/test_periodic.jl:20-26: A - 5im*I
+    c2, a2, b2 = [[0, 0.5], [0, 0]], [[0, 2.0], [0.5, 0]], [[0, 0.0], [2.0, 0]]
+    Ac = BlockTridiagonal(([c2], c2), ([a2], a2), ([b2], b2)) - 5j * I
+    lc = ql(Ac).L[1, 1]
+    assert isinstance(lc, complex) and lc == pytest.approx(4.79196327384051, rel=1e-12)

@@ -77,3 +77,31 @@ def test_c5_full_size_properties(ila):
         A[0, 0] = 2.0 - xs[i]
         F, _ = tq.dense_ql(A)
         assert np.isclose(L[i], F[0, 0], atol=5e-9)
+
+
+def test_complex_eltype_vs_oracle(ila):
+    """Complex eltype (test/test_periodic.jl:20-26, `A - 5im*I`; complex blocks): the QL loop runs to k = 1.  Bar: same
+    status and iteration count, L[1,1] within 1e-12 relative (complex multiply/divide orders differ at rounding level)."""
+    from oracle import block_ql as bq
+    c2, a2, b2 = np.array([[0, 0.5], [0, 0]]), np.array([[0, 2.0], [0.5, 0]]), np.array([[0, 0.0], [2.0, 0]])
+    xs = np.array([5j, 2.0 + 4.0j, -0.5 - 3.0j, 3.0 + 0.5j, -4.0 + 0.0j])
+    L, it, st = ila.ql_blocktri_l11([c2], [a2], [b2], c2, a2, b2, xs, maxit=5000)
+    assert L.dtype == np.complex128
+    for i, x in enumerate(xs):
+        r = bq.blocktri_ql_l11([c2], [a2], [b2], c2, a2, b2, shift=x, maxit=5000)
+        assert st[i] == r[2]
+        if r[2] == 0:
+            assert it[i] == r[1]
+            assert abs(L[i] - r[0]) <= 1e-12 * abs(r[0])
+    # complex blocks with a perturbed head, real energies
+    rng = np.random.default_rng(11)
+    c = np.array([[0, 1.0], [0, 0]]) * (1 + 0.3j)
+    a = np.array([[-1.0, 1.0 + 0.2j], [1.0 - 0.2j, 1.0]])
+    b = np.array([[0, 0], [1.0 - 0.3j, 0]])
+    a0 = a + 0.1 * (rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2)))
+    xs = np.array([4.0, -4.5, 3.5 + 1j])
+    L, it, st = ila.ql_blocktri_l11([c], [a0], [b], c, a, b, xs, maxit=5000)
+    for i, x in enumerate(xs):
+        r = bq.blocktri_ql_l11([c], [a0], [b], c, a, b, shift=x, maxit=5000)
+        assert st[i] == r[2] == 0 and it[i] == r[1]
+        assert abs(L[i] - r[0]) <= 1e-12 * abs(r[0])

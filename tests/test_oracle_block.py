@@ -37,7 +37,8 @@ def test_against_finite_section():
     for x in (-0.95, 0.3, 2.5, 3.9):
         l11 = bq.periodic_schrodinger(x)[0]
         F, _ = tq.dense_ql(_finite_section(c, a, b, 100, x, d0=a0))
-        assert np.isclose(l11, F[0, 0], rtol=0, atol=5e-9)
+        # (the phase of the tail's fixed point is fixed by the iteration's start, so only |L[1,1]| is comparable)
+        assert np.isclose(abs(l11), abs(F[0, 0]), rtol=0, atol=5e-9)
     # unperturbed operator of test_periodic.jl:6-8: head == tail
     l11 = bq.blocktri_ql_l11([c], [a], [b], c, a, b)[0]
     F, _ = tq.dense_ql(_finite_section(c, a, b, 100, 0.0))
@@ -57,3 +58,16 @@ def test_degenerate_and_four_by_four_blocks():
     assert st == 0
     F, _ = tq.dense_ql(_finite_section(B, A, B.T, 60, 0.0, d0=A0))
     assert np.isclose(l11, F[0, 0], atol=5e-8)
+
+
+def test_complex_nonselfadjoint_shift():
+    # test/test_periodic.jl:20-26: the degenerate blocks shifted by -5im*I (complex eltype: the QL loop runs to k = 1)
+    c2, a2, b2 = np.array([[0, 0.5], [0, 0]]), np.array([[0, 2.0], [0.5, 0]]), np.array([[0, 0.0], [2.0, 0]])
+    for x in (5j, 2.0 + 4.0j, -0.5 - 3.0j):
+        l11, it, st, _ = bq.blocktri_ql_l11([c2], [a2], [b2], c2, a2, b2, shift=x, maxit=5000)
+        assert st == 0 and it < 200
+        A = _finite_section(c2, a2, b2, 40, 0.0).astype(complex) - x * np.eye(80)
+        F, _ = tq.dense_ql(A)
+        assert abs(np.imag(l11)) <= 1e-15 * abs(l11)          # the k = 1 reflector makes L[1,1] real
+        # (the phase of the tail's fixed point is fixed by the iteration's start, so only |L[1,1]| is comparable)
+        assert np.isclose(abs(l11), abs(F[0, 0]), rtol=0, atol=5e-9)
