@@ -391,6 +391,17 @@ def run_ours(args, rank, local_rank, world):
                                                        ctypes.c_void_p(stream)))
         ms5 = timed(step_c5, k4, 2) / k4
         its5 = float(d_it5.sum().item())
+        # K7: resolvent entries e1'(A - λI)^{-1} e1 on the same λ slab = first entry of ql(A - λI) \ e1
+        m7 = 5
+        d_w7 = torch.empty(n * (2 * m7 + 3), dtype=torch.complex128, device=dev)
+        d_x7 = torch.empty(n, dtype=torch.complex128, device=dev)
+        d_st7 = torch.empty(n, dtype=torch.int32, device=dev)
+        b7 = np.array([1.0 + 0j])
+
+        def step_k7():
+            _lib.check(lib.ila_ql_toeplitz_solve_c64_dev(3, 1, _lib.ptr(BULLHEAD_COLUMN), _lib.ptr(d_lam), n, 1, 1, _lib.ptr(b7), 1,
+                                                         _lib.ptr(d_w7), _lib.ptr(d_x7), _lib.ptr(d_st7), ctypes.c_void_p(stream)))
+        ms7 = timed(step_k7, k4, 2) / k4
         line["other_configs"] = [
             {"metric": "adaptive_cholesky_columns_per_s", "value": cols4 * world / (ms4 * 1e-3), "unit": "columns/s",
              "ms_per_step": ms4, "config": {"workload": "C4 pentadiagonal adaptive Cholesky, 2048 shifts (per GPU)",
@@ -404,6 +415,13 @@ def run_ours(args, rank, local_rank, world):
              "ms_per_step": ms5, "config": {"workload": "C5 periodic Schrödinger block QL, 512 energies (per GPU)",
                                             "fixed_point_iterations": its5},
              "gpu_launches_per_step": 1},
+            {"metric": "toeplitz_ql_resolvent_points_per_s", "value": n * world / (ms7 * 1e-3), "unit": "lambda-points/s",
+             "ms_per_step": ms7, "config": {"workload": "K7 ql(A - λI) \\ e1, first entry, same 1024x1024 λ slab (per GPU)"},
+             "roofline": {"bound": "hbm", "achieved": (36 + 2 * 16 * (2 * m7 + 3)) * n / (ms7 * 1e-3) / 1e9, "peak": hbm_peak,
+                          "unit": "GB/s", "frac": (36 + 2 * 16 * (2 * m7 + 3)) * n / (ms7 * 1e-3) / 1e9 / hbm_peak,
+                          "traffic": None, "bytes_per_unit": 36 + 2 * 16 * (2 * m7 + 3),
+                          "note": "36 B in/out + the tail record written by K3 and read back by the solve kernel"},
+             "gpu_launches_per_step": 2},
         ]
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------

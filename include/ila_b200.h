@@ -166,6 +166,22 @@ int ila_chol_banded_factor_f64_dev(int u, int64_t batch, const double *d_p, cons
                                    const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
                                    int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int full_sweep, void *stream);
 
+/* ---- K7: solve with the Toeplitz QL,  x[i, 0:nout] = (ql(A - lambda[i]*I) \ b)[1:nout] -------------------------------
+ * Pure Toeplitz A (u == 1) as in K3; b has nb <= 16 leading entries, zero beyond.  Replaces
+ * ldiv!(F, b) = ldiv!(F.L, lmul!(F.Q', b)) (src/infql.jl:266-267): UpperHessenbergQ apply for n = nb..1
+ * (src/banded/hessenbergq.jl:125-135) and the column-oriented forward substitution with the ∞ lower band L
+ * (src/infql.jl:269-289; the reference stops at exact zeros, here the caller states nout).  x is COLUMN-major
+ * n x nout (x[i + j*n]); rows with status != 0 are NaN.  x[i, 0] for b = e1 is the resolvent entry
+ * e1'(A - lambda[i] I)^{-1} e1.  The _dev forms need d_work of n*(2(l+2)+3) scalars. */
+int ila_ql_toeplitz_solve_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank, int nb,
+                              const ila_c64 *b, int64_t nout, ila_c64 *x, int32_t *status, int ngpus);
+int ila_ql_toeplitz_solve_f64(int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank, int nb,
+                              const double *b, int64_t nout, double *x, int32_t *status, int ngpus);
+int ila_ql_toeplitz_solve_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d_lambda, int64_t n, int branch_rank, int nb,
+                                  const ila_c64 *b, int64_t nout, ila_c64 *d_work, ila_c64 *d_x, int32_t *d_status, void *stream);
+int ila_ql_toeplitz_solve_f64_dev(int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank, int nb,
+                                  const double *b, int64_t nout, double *d_work, double *d_x, int32_t *d_status, void *stream);
+
 /* ---- K6: block-tridiagonal perturbed-Toeplitz QL,  L11[i] = ql(A - energy[i]*I).L[1,1] ----------------------------
  * A = BlockTridiagonal(Vcat(dl_head, Fill(c,∞)), Vcat(d_head, Fill(a,∞)), Vcat(du_head, Fill(b,∞))) with n x n blocks
  * (column-major; dl = A[Block(k+1,k)], du = A[Block(k,k+1)]; head tables hold n_dl / n_d / n_du blocks, n <= 4,

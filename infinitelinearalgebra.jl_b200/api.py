@@ -208,9 +208,10 @@ class _OneBased:
 class QLHessenberg:
     """Result of ql on a (perturbed) Toeplitz operator with u == 1 (src/banded/hessenbergq.jl:16-72)."""
 
-    def __init__(self, l, X, tau, head_factors=None, head_l11=None):
+    def __init__(self, l, X, tau, head_factors=None, head_l11=None, source=None):
         self.l, self.X, self.tau = l, X, tau
         self._head, self._head_l11 = head_factors, head_l11
+        self._source = source                         # (data column, shift, branch) of a pure Toeplitz operator
         self.L = _OneBased(self._L)
         self.Q = _OneBased(self._Q)
 
@@ -226,6 +227,16 @@ class QLHessenberg:
         if j == 1:                                   # first column [X[1,m-1]; X[2,m-1:-1:1]]  (infqltoeplitz.jl:63)
             return self.X[0, m - 2] if i == 1 else self.X[1, m - i]
         return self.X[1, m - 1 - (i - j)]            # tail column X[2, m:-1:1]
+
+    def solve(self, b, n=1000):
+        """First n entries of `F \\ b` (ldiv!(F.L, lmul!(F.Q', b)), src/infql.jl:266-289) for a pure Toeplitz operator."""
+        if self._source is None:
+            raise NotImplementedError("F \\ b is implemented for pure Toeplitz operators (no head perturbation)")
+        col, lam, branch = self._source
+        bb = np.atleast_1d(np.asarray(b.head if isinstance(b, Vcat) else b))
+        x, st = _b.ql_toeplitz_solve(col, np.array([lam]), bb, int(n), branch_rank=branch)
+        _raise_status(st[0], "ql(A) \\ b")
+        return x[0]
 
     def _q2(self):
         m = self.X.shape[1]
@@ -304,7 +315,7 @@ def ql(A, branch=1):
         _raise_status(st[0], "ql")
         m = l + 2
         t = tail[0]
-        return QLHessenberg(l, np.stack([t[:m], t[m:2 * m]]), t[2 * m:2 * m + 2])
+        return QLHessenberg(l, np.stack([t[:m], t[m:2 * m]]), t[2 * m:2 * m + 2], source=(col, lam, branch))
     p = A.head_rows()
     head = A.finite(p) + lam * np.eye(p)             # the C entry applies the shift itself
     L, st, hf = _b.ql_perttoeplitz_l11(head, col, np.array([lam]), branch_rank=branch, want_head_factors=True,

@@ -49,6 +49,30 @@ def ql_toeplitz_l11(data_column, lambdas, branch_rank: int = 1, want_tail: bool 
     return res
 
 
+def ql_toeplitz_solve(data_column, lambdas, b, nout: int, branch_rank: int = 1, ngpus: int = 1,
+                      real_path: bool | None = None):
+    """First `nout` entries of x = ql(A - λI) \\ b over all shifts `lambdas`, for the pure Toeplitz A of
+    `ql_toeplitz_l11` and a right-hand side with len(b) <= 16 leading entries (reference: `F \\ b` →
+    ldiv!(F.L, lmul!(F.Q', b)), src/infql.jl:266-289, src/banded/hessenbergq.jl:125-135; test/test_infql.jl:143-145).
+    Returns (x [shape lambdas.shape + (nout,)], status); rows with status != 0 are NaN."""
+    col = np.asarray(data_column)
+    lam = np.asarray(lambdas)
+    bb = np.asarray(b)
+    if real_path is None:
+        real_path = not (np.iscomplexobj(col) or np.iscomplexobj(lam) or np.iscomplexobj(bb))
+    dt = np.float64 if real_path else np.complex128
+    col = np.ascontiguousarray(col, dtype=dt)
+    bb = np.ascontiguousarray(bb, dtype=dt).reshape(-1)
+    shape = lam.shape
+    lam = np.ascontiguousarray(lam, dtype=dt).reshape(-1)
+    n = lam.size
+    x = np.empty((int(nout), n), dtype=dt)            # column-major n x nout
+    status = np.empty(n, dtype=np.int32)
+    fn = lib().ila_ql_toeplitz_solve_f64 if real_path else lib().ila_ql_toeplitz_solve_c64
+    check(fn(col.size - 2, 1, ptr(col), ptr(lam), n, branch_rank, bb.size, ptr(bb), int(nout), ptr(x), ptr(status), ngpus))
+    return np.ascontiguousarray(x.T).reshape(shape + (int(nout),)), status.reshape(shape)
+
+
 def ql_toeplitz_absl11_grid(data_column, x, y, branch_rank: int = 1, ngpus: int = 1, out=None):
     """The reference example's λ-grid loop (examples/toeplitz.jl:14-33): z[k, j] = abs(ql(A - (x[j] + i y[k]) I).L[1,1]),
     -1.0 where the QL factorization does not exist.  Shifts are formed on device."""

@@ -15,6 +15,8 @@ int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int b
                        int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream);
 
 void tz_set_spt(int v);
+int launch_ql_toeplitz_solve(bool real_path, int l, int nb, const double *b_host, int64_t n, const double *d_tail,
+                             const int32_t *d_status, int64_t nout, double *d_x, cudaStream_t stream);
 int launch_ql_toeplitz_grid(int l, int u, const double *a_host, int branch_rank, const double *d_gx, int nx,
                             const double *d_gy, int64_t ny, double *d_absout, cudaStream_t stream);
 int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
@@ -415,6 +417,96 @@ int ila_ql_toeplitz_absl11_grid_c64(int l, int u, const ila_c64 *a, const double
     }
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
+}
+
+// ================================ K7: solve with the Toeplitz QL ========================================
+
+static int ql_solve_args(int l, int u, int nb, int64_t n, int64_t nout)
+{
+    if (n < 0 || nout < 1 || nb < 1) return set_error(ILA_ERR_ARG, "ql_toeplitz_solve: bad sizes");
+    if (u != 1 || l < 1 || l > 7) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz_solve: only u == 1, l in 1..7");
+    return 0;
+}
+
+static int ql_solve_dev(bool real_path, int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank,
+                        int nb, const double *b, int64_t nout, double *d_work, double *d_x, int32_t *d_status, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    int rc = ql_solve_args(l, u, nb, n, nout);
+    if (rc) return rc;
+    if (!a || !b || (n > 0 && (!d_lambda || !d_work || !d_x || !d_status))) return set_error(ILA_ERR_ARG, "ql_toeplitz_solve: null pointer");
+    const int w = real_path ? 1 : 2;
+    double *d_L = d_work, *d_tail = d_work + (size_t)n * w;   // work = L11 (n) | tail records (n x (2(l+2)+2))
+    if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lambda, n, d_L, d_tail, d_status, (cudaStream_t)stream))) return rc;
+    return launch_ql_toeplitz_solve(real_path, l, nb, b, n, d_tail, d_status, nout, d_x, (cudaStream_t)stream);
+}
+
+static int ql_solve_host(bool real_path, int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank,
+                         int nb, const double *b, int64_t nout, double *x, int32_t *status, int ngpus)
+{
+    int rc = ql_solve_args(l, u, nb, n, nout);
+    if (rc) return rc;
+    if (!a || !b || (n > 0 && (!lambda || !x || !status))) return set_error(ILA_ERR_ARG, "ql_toeplitz_solve: null pointer");
+    int G = 0;
+    if ((rc = resolve_ngpus(ngpus, &G))) return rc;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    const int w = real_path ? 1 : 2;
+    const int tl = 2 * (l + 2) + 2;
+    if (G > n) G = (int)n;
+    const int64_t per = (n + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= n ? per : n - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        double *d_lam, *d_L, *d_tail, *d_x;
+        int32_t *d_st;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt * w, &d_lam))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt * w, &d_L))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
+        if ((rc = dev_buf_t(pd, 3, (size_t)cnt * tl * w, &d_tail))) return rc;
+        if ((rc = dev_buf_t(pd, 4, (size_t)cnt * nout * w, &d_x))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam, lambda + lo * w, sizeof(double) * cnt * w, cudaMemcpyHostToDevice, s));
+        if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam, cnt, d_L, d_tail, d_st, s))) return rc;
+        if ((rc = launch_ql_toeplitz_solve(real_path, l, nb, b, cnt, d_tail, d_st, nout, d_x, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+        // x is column-major n x nout on the host, cnt x nout on the device: one strided copy
+        ILA_CUDA_CHECK(cudaMemcpy2DAsync(x + lo * w, sizeof(double) * n * w, d_x, sizeof(double) * cnt * w,
+                                         sizeof(double) * cnt * w, (size_t)nout, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
+int ila_ql_toeplitz_solve_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank, int nb,
+                              const ila_c64 *b, int64_t nout, ila_c64 *x, int32_t *status, int ngpus)
+{
+    return ql_solve_host(false, l, u, (const double *)a, (const double *)lambda, n, branch_rank, nb, (const double *)b, nout,
+                         (double *)x, status, ngpus);
+}
+int ila_ql_toeplitz_solve_f64(int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank, int nb,
+                              const double *b, int64_t nout, double *x, int32_t *status, int ngpus)
+{
+    return ql_solve_host(true, l, u, a, lambda, n, branch_rank, nb, b, nout, x, status, ngpus);
+}
+int ila_ql_toeplitz_solve_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d_lambda, int64_t n, int branch_rank, int nb,
+                                  const ila_c64 *b, int64_t nout, ila_c64 *d_work, ila_c64 *d_x, int32_t *d_status, void *stream)
+{
+    return ql_solve_dev(false, l, u, (const double *)a, (const double *)d_lambda, n, branch_rank, nb, (const double *)b, nout,
+                        (double *)d_work, (double *)d_x, d_status, stream);
+}
+int ila_ql_toeplitz_solve_f64_dev(int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank, int nb,
+                                  const double *b, int64_t nout, double *d_work, double *d_x, int32_t *d_status, void *stream)
+{
+    return ql_solve_dev(true, l, u, a, d_lambda, n, branch_rank, nb, b, nout, d_work, d_x, d_status, stream);
 }
 
 // ================================ K4: perturbed-Toeplitz head ==========================================

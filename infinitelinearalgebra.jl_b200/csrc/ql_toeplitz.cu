@@ -867,4 +867,107 @@ int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, cons
     return 0;
 }
 
+// ---- K7: solve with the Toeplitz QL,  x = ql(A - λI) \ b  ------------------------------------------------------
+// Reference: ldiv!(F, b) = ldiv!(F.L, lmul!(F.Q', b)) (src/infql.jl:266-267).  Q = LowerHessenbergQ(Fill(q, ∞)) with the
+// 2x2 block q = QLPackedQ(X[:, m-1:m], τ) (infqltoeplitz.jl:63-64); Q' = UpperHessenbergQ(adjoint.(q)) acts on b[n:n+1]
+// for n = nz, ..., 1 (src/banded/hessenbergq.jl:125-135).  L is the lower band with first column
+// [X[1,m-1]; X[2,m-1:-1:1]] and every other column X[2,m:-1:1] (infqltoeplitz.jl:63), solved by the column-oriented
+// forward substitution of src/infql.jl:269-289.  One thread per shift, consuming the K3 `tail` record; the N = m-1
+// pending row updates live in a register window; x is written column-major (x[i + j n]: coalesced across shifts, and the
+// n x nout Matrix a Julia caller wants).  The reference stops when the remaining entries are exactly zero; here the
+// caller states how many entries it wants.
+constexpr int kSolveMaxB = 16;
+struct TzSolveParams {
+    int nb;
+    cplx b[kSolveMaxB];
+};
+
+template <int N, bool REAL_PATH>
+__global__ void __launch_bounds__(128)
+ql_toeplitz_solve_kernel(TzSolveParams S, int64_t n, const double *__restrict__ tail, const int32_t *__restrict__ status,
+                         int64_t nout, double *__restrict__ x)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    constexpr int M = N + 1, W = REAL_PATH ? 1 : 2;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    auto put = [&](int64_t j, cplx v) {
+        if (REAL_PATH) x[j * n + idx] = v.re;
+        else reinterpret_cast<double2 *>(x)[j * n + idx] = make_double2(v.re, v.im);
+    };
+    if (status[idx] != ILA_OK) {
+        for (int64_t j = 0; j < nout; j++) put(j, mk(qnan, qnan));
+        return;
+    }
+    const double *t = tail + idx * (2 * M + 2) * W;
+    auto tl = [&](int k) -> cplx { return REAL_PATH ? mk(t[k], 0.0) : mk(t[2 * k], t[2 * k + 1]); };
+    const cplx l11 = tl(N - 1), v = tl(N), tau1 = tl(2 * M), tau2 = tl(2 * M + 1);
+    // q = H_2 H_1,  H_1 = diag(1 - tau1, 1),  H_2 = I - tau2 [v;1][v;1]'
+    const cplx one = mk(1.0, 0.0);
+    const cplx s1 = one - tau1;
+    const cplx q11 = (one - abs2(v) * tau2) * s1, q21 = (-(conj(v) * tau2)) * s1;
+    const cplx q12 = -(v * tau2), q22 = one - tau2;
+    // Q'b: b[n:n+1] <- q' b[n:n+1], n = nb, ..., 1
+    cplx tb[kSolveMaxB + 1];
+    for (int k = 0; k <= kSolveMaxB; k++) tb[k] = (k < S.nb) ? S.b[k] : mk(0.0, 0.0);
+    for (int k = S.nb; k >= 1; k--) {
+        const cplx u0 = tb[k - 1], u1 = tb[k];
+        tb[k - 1] = conj(q11) * u0 + conj(q21) * u1;
+        tb[k] = conj(q12) * u0 + conj(q22) * u1;
+    }
+    // L \ (Q'b): sub[i-1] = L[j+i, j] = X[2, m-i], i = 1..N; diagonal X[1,m-1] (first column) / X[2,m] (others)
+    cplx sub[N];
+#pragma unroll
+    for (int i = 1; i <= N; i++) sub[i - 1] = tl(M + (M - 1 - i));
+    const cplx dtail = tl(M + M - 1);
+    auto rcp = [&](cplx d) { const double r2 = 1.0 / abs2(d); return r2 * conj(d); };
+    const cplx r_first = rcp(l11), r_tail = rcp(dtail);
+    cplx r[N + 1];   // r[0] = current row, r[k] = pending value of row j + k
+#pragma unroll
+    for (int k = 0; k <= N; k++) r[k] = tb[k <= kSolveMaxB ? k : kSolveMaxB];
+    for (int64_t j = 0; j < nout; j++) {
+        const cplx xj = r[0] * (j == 0 ? r_first : r_tail);
+        put(j, xj);
+        const int64_t nx = j + N + 1;   // row entering the window
+        const cplx tin = (nx <= S.nb) ? tb[nx] : mk(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < N; k++) r[k] = r[k + 1] - sub[k] * xj;
+        r[N] = tin;
+    }
+}
+
+template <bool REAL_PATH>
+static int launch_solve_any(int l, const TzSolveParams &S, int64_t n, const double *d_tail, const int32_t *d_status,
+                            int64_t nout, double *d_x, cudaStream_t stream)
+{
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    switch (l + 1) {
+#define ILA_SOLVE_CASE(NN) \
+    case NN: ql_toeplitz_solve_kernel<NN, REAL_PATH><<<blocks, threads, 0, stream>>>(S, n, d_tail, d_status, nout, d_x); break;
+        ILA_SOLVE_CASE(2) ILA_SOLVE_CASE(3) ILA_SOLVE_CASE(4) ILA_SOLVE_CASE(5) ILA_SOLVE_CASE(6) ILA_SOLVE_CASE(7) ILA_SOLVE_CASE(8)
+#undef ILA_SOLVE_CASE
+    default: return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz_solve: lower bandwidth l must be in 1..7");
+    }
+    count_launch();
+    ILA_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// b_host: nb scalars (real or interleaved complex, like the symbol); d_tail: the `tail` output of launch_ql_toeplitz
+int launch_ql_toeplitz_solve(bool real_path, int l, int nb, const double *b_host, int64_t n, const double *d_tail,
+                             const int32_t *d_status, int64_t nout, double *d_x, cudaStream_t stream)
+{
+    if (nb < 1 || nb > kSolveMaxB) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz_solve: right-hand side length must be in 1..16");
+    if (nout < 1) return set_error(ILA_ERR_ARG, "ql_toeplitz_solve: nout must be positive");
+    if (n <= 0) return 0;
+    TzSolveParams S;
+    S.nb = nb;
+    for (int k = 0; k < kSolveMaxB; k++)
+        S.b[k] = k < nb ? (real_path ? cplx{b_host[k], 0.0} : cplx{b_host[2 * k], b_host[2 * k + 1]}) : cplx{0.0, 0.0};
+    return real_path ? launch_solve_any<true>(l, S, n, d_tail, d_status, nout, d_x, stream)
+                     : launch_solve_any<false>(l, S, n, d_tail, d_status, nout, d_x, stream);
+}
+
+
 } // namespace ila

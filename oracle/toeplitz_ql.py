@@ -270,6 +270,50 @@ def ql_packed_Q(factors, tau):
     return Q
 
 
+def ql_toeplitz_solve(coeffs_data_column, lambdas, b, nout, branch_rank=1, real_path=None):
+    """First `nout` entries of  x = ql(A - λI) \\ b  for the pure Toeplitz A (u == 1) and a finitely supported b.
+
+    Reference: `ldiv!(F, b) = ldiv!(F.L, lmul!(F.Q', b))` (src/infql.jl:266-267) with
+      Q  = LowerHessenbergQ(Fill(q, ∞)), q = QLPackedQ(X, τ) (2×2)      (infqltoeplitz.jl:63-64, hessenbergq.jl:86-135):
+           Q' = UpperHessenbergQ(adjoint.(q)) applied for n = nz, nz-1, ..., 1 to b[n:n+1];
+      L  = lower-triangular band: first column [X[1,m-1]; X[2,m-1:-1:1]], every other column X[2,m:-1:1]
+           (infqltoeplitz.jl:63), solved by the column-oriented forward substitution of src/infql.jl:269-289.
+    Returns (x [shape lambdas.shape + (nout,)], status).  Pinned by test/test_infql.jl:143-145 (vs qr(A) \\ b).
+    """
+    col = np.asarray(coeffs_data_column)
+    lambdas = np.asarray(lambdas)
+    b = np.asarray(b)
+    dt = np.result_type(col.dtype, lambdas.dtype, b.dtype, np.float64)
+    m = col.shape[0]
+    flat = lambdas.reshape(-1)
+    a = np.empty((flat.size, m), dtype=np.result_type(col.dtype, lambdas.dtype))
+    a[...] = col[::-1]
+    a[:, m - 2] = col[1] - flat
+    out = ql_toeplitz_tail(a, branch_rank, real_path)
+    X, tau, status = out["X"], out["tau"], out["status"]
+    dt = np.result_type(dt, X.dtype)
+    nb = b.shape[0]
+    x = np.full((flat.size, nout), np.nan, dtype=dt)
+    for i in range(flat.size):
+        if status[i] != 0:
+            continue
+        q = ql_packed_Q(X[i][:, m - 2:m], tau[i])
+        qh = q.conj().T
+        t = np.zeros(max(nb + 1, nout), dtype=dt)
+        t[:nb] = b
+        for n in range(nb, 0, -1):                     # UpperHessenbergQ: n = nz:-1:1
+            t[n - 1:n + 1] = qh @ t[n - 1:n + 1]
+        t = t[:nout].copy() if t.size >= nout else np.concatenate([t, np.zeros(nout - t.size, dtype=dt)])
+        sub = X[i][1, m - 2::-1]                       # L[j+i, j] = X[2, m-i], i = 1..m-1
+        for j in range(nout):
+            d = X[i][0, m - 2] if j == 0 else X[i][1, m - 1]
+            t[j] = t[j] / d
+            hi = min(nout, j + m)
+            t[j + 1:hi] -= sub[:hi - j - 1] * t[j]
+        x[i] = t
+    return x.reshape(lambdas.shape + (nout,)), status.reshape(lambdas.shape)
+
+
 # ----------------------------------------------------------------------------------------------
 # perturbed Toeplitz head: ql_hessenberg!(B)  (src/infql.jl:60-93), u == 1
 # ----------------------------------------------------------------------------------------------
