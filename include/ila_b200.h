@@ -172,7 +172,8 @@ int ila_chol_banded_factor_f64_dev(int u, int64_t batch, const double *d_p, cons
  * (src/banded/hessenbergq.jl:125-135) and the column-oriented forward substitution with the ∞ lower band L
  * (src/infql.jl:269-289; the reference stops at exact zeros, here the caller states nout).  x is COLUMN-major
  * n x nout (x[i + j*n]); rows with status != 0 are NaN.  x[i, 0] for b = e1 is the resolvent entry
- * e1'(A - lambda[i] I)^{-1} e1.  The _dev forms need d_work of n*(2(l+2)+3) scalars. */
+ * e1'(A - lambda[i] I)^{-1} e1.  One fused launch: the K3 kernel solves from its registers.  The _dev forms need
+ * d_work of n scalars (it receives L[1,1]). */
 int ila_ql_toeplitz_solve_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank, int nb,
                               const ila_c64 *b, int64_t nout, ila_c64 *x, int32_t *status, int ngpus);
 int ila_ql_toeplitz_solve_f64(int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank, int nb,

@@ -17,6 +17,9 @@ int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int b
 void tz_set_spt(int v);
 int launch_ql_toeplitz_solve(bool real_path, int l, int nb, const double *b_host, int64_t n, const double *d_tail,
                              const int32_t *d_status, int64_t nout, double *d_x, cudaStream_t stream);
+int launch_ql_toeplitz_solve_fused(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
+                                   int64_t n, int nb, const double *b_host, int64_t nout, double *d_L11, double *d_x,
+                                   int32_t *d_status, cudaStream_t stream);
 int launch_ql_toeplitz_grid(int l, int u, const double *a_host, int branch_rank, const double *d_gx, int nx,
                             const double *d_gy, int64_t ny, double *d_absout, cudaStream_t stream);
 int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
@@ -435,10 +438,9 @@ static int ql_solve_dev(bool real_path, int l, int u, const double *a, const dou
     int rc = ql_solve_args(l, u, nb, n, nout);
     if (rc) return rc;
     if (!a || !b || (n > 0 && (!d_lambda || !d_work || !d_x || !d_status))) return set_error(ILA_ERR_ARG, "ql_toeplitz_solve: null pointer");
-    const int w = real_path ? 1 : 2;
-    double *d_L = d_work, *d_tail = d_work + (size_t)n * w;   // work = L11 (n) | tail records (n x (2(l+2)+2))
-    if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lambda, n, d_L, d_tail, d_status, (cudaStream_t)stream))) return rc;
-    return launch_ql_toeplitz_solve(real_path, l, nb, b, n, d_tail, d_status, nout, d_x, (cudaStream_t)stream);
+    // one fused launch: the K3 kernel solves from its registers; d_work receives L[1,1] (n scalars)
+    return launch_ql_toeplitz_solve_fused(real_path, l, u, a, branch_rank, d_lambda, n, nb, b, nout, d_work, d_x, d_status,
+                                          (cudaStream_t)stream);
 }
 
 static int ql_solve_host(bool real_path, int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank,
@@ -452,7 +454,6 @@ static int ql_solve_host(bool real_path, int l, int u, const double *a, const do
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
     const int w = real_path ? 1 : 2;
-    const int tl = 2 * (l + 2) + 2;
     if (G > n) G = (int)n;
     const int64_t per = (n + G - 1) / G;
     for (int d = 0; d < G; d++) {
@@ -460,17 +461,15 @@ static int ql_solve_host(bool real_path, int l, int u, const double *a, const do
         if (cnt <= 0) continue;
         const int pd = phys(d, G);
         if ((rc = dev_init(pd))) return rc;
-        double *d_lam, *d_L, *d_tail, *d_x;
+        double *d_lam, *d_L, *d_x;
         int32_t *d_st;
         if ((rc = dev_buf_t(pd, 0, (size_t)cnt * w, &d_lam))) return rc;
         if ((rc = dev_buf_t(pd, 1, (size_t)cnt * w, &d_L))) return rc;
         if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
-        if ((rc = dev_buf_t(pd, 3, (size_t)cnt * tl * w, &d_tail))) return rc;
         if ((rc = dev_buf_t(pd, 4, (size_t)cnt * nout * w, &d_x))) return rc;
         cudaStream_t s = g_dev[pd].stream;
         ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam, lambda + lo * w, sizeof(double) * cnt * w, cudaMemcpyHostToDevice, s));
-        if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam, cnt, d_L, d_tail, d_st, s))) return rc;
-        if ((rc = launch_ql_toeplitz_solve(real_path, l, nb, b, cnt, d_tail, d_st, nout, d_x, s))) return rc;
+        if ((rc = launch_ql_toeplitz_solve_fused(real_path, l, u, a, branch_rank, d_lam, cnt, nb, b, nout, d_L, d_x, d_st, s))) return rc;
         ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
         // x is column-major n x nout on the host, cnt x nout on the device: one strided copy
         ILA_CUDA_CHECK(cudaMemcpy2DAsync(x + lo * w, sizeof(double) * n * w, d_x, sizeof(double) * cnt * w,

@@ -315,6 +315,61 @@ struct TzGrid {
     double *absout;
 };
 
+constexpr int kSolveMaxB = 16;
+struct TzSolveParams {
+    int nb;
+    cplx b[kSolveMaxB];
+};
+
+struct TzSolveArgs {   // fused form: the K3 kernel runs the solve from its registers instead of writing the tail record
+    TzSolveParams S;
+    int64_t nout;
+    double *x;          // column-major n x nout, nullptr = not fused
+};
+
+// Q'b and the forward substitution for one shift (see the K7 header below); l11 = X[1,m-1], v = X[1,m],
+// X2[0..N] = X[2,1..m] after ql_X!.
+template <int N, bool REAL_PATH>
+__device__ __forceinline__ void tz_solve_rows(const TzSolveParams &S, cplx l11, cplx v, const cplx (&X2)[N + 1], cplx tau1,
+                                              cplx tau2, int64_t nout, int64_t n, int64_t idx, double *__restrict__ x)
+{
+    auto put = [&](int64_t j, cplx val) {
+        if (REAL_PATH) x[j * n + idx] = val.re;
+        else reinterpret_cast<double2 *>(x)[j * n + idx] = make_double2(val.re, val.im);
+    };
+    // q = H_2 H_1,  H_1 = diag(1 - tau1, 1),  H_2 = I - tau2 [v;1][v;1]'
+    const cplx one = mk(1.0, 0.0);
+    const cplx s1 = one - tau1;
+    const cplx q11 = (one - abs2(v) * tau2) * s1, q21 = (-(conj(v) * tau2)) * s1;
+    const cplx q12 = -(v * tau2), q22 = one - tau2;
+    // Q'b: b[n:n+1] <- q' b[n:n+1], n = nb, ..., 1
+    cplx tb[kSolveMaxB + 1];
+    for (int k = 0; k <= kSolveMaxB; k++) tb[k] = (k < S.nb) ? S.b[k] : mk(0.0, 0.0);
+    for (int k = S.nb; k >= 1; k--) {
+        const cplx u0 = tb[k - 1], u1 = tb[k];
+        tb[k - 1] = conj(q11) * u0 + conj(q21) * u1;
+        tb[k] = conj(q12) * u0 + conj(q22) * u1;
+    }
+    // L \ (Q'b): sub[i-1] = L[j+i, j] = X[2, m-i], i = 1..N; diagonal X[1,m-1] (first column) / X[2,m] (others)
+    cplx sub[N];
+#pragma unroll
+    for (int i = 1; i <= N; i++) sub[i - 1] = X2[N - i];
+    auto rcp = [&](cplx d) { const double r2 = 1.0 / abs2(d); return r2 * conj(d); };
+    const cplx r_first = rcp(l11), r_tail = rcp(X2[N]);
+    cplx r[N + 1];   // r[0] = current row, r[k] = pending value of row j + k
+#pragma unroll
+    for (int k = 0; k <= N; k++) r[k] = tb[k];
+    for (int64_t j = 0; j < nout; j++) {
+        const cplx xj = r[0] * (j == 0 ? r_first : r_tail);
+        put(j, xj);
+        const int64_t nx = j + N + 1;   // row entering the window
+        const cplx tin = (nx <= S.nb) ? tb[nx] : mk(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < N; k++) r[k] = r[k + 1] - sub[k] * xj;
+        r[N] = tin;
+    }
+}
+
 // Each thread owns SPT consecutive shifts.  The first one starts cold (roots on a circle); the following ones start
 // from the previous shift's roots, which on a grid are O(Δλ) away: one Aberth sweep re-establishes every root to ~1e-5
 // (enough to rank the moduli unless they nearly tie), then only the selected root is taken to full precision by Newton.
@@ -323,7 +378,7 @@ struct TzGrid {
 template <int N, bool REAL_PATH, bool WANT_TAIL>
 __global__ void __launch_bounds__(128, (N <= 4 && !WANT_TAIL) ? 7 : 1)
 ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t n, int spt, double *__restrict__ L11,
-                       double *__restrict__ tail, int32_t *__restrict__ status, TzGrid G)
+                       double *__restrict__ tail, int32_t *__restrict__ status, TzGrid G, TzSolveArgs SV)
 {
     const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * spt;
     if (first >= n) return;
@@ -614,6 +669,18 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
         continue;
     }
     status[idx] = st;
+    if (WANT_TAIL && SV.x) {
+        // fused K7: x = L \ (Q'b) straight from the registers (NaN rows where the factorization does not exist)
+        if (st == ILA_OK) {
+            tz_solve_rows<N, REAL_PATH>(SV.S, X1[N - 1], X1[N], X2, tau1, tau2, SV.nout, n, idx, SV.x);
+        } else {
+            for (int64_t j = 0; j < SV.nout; j++) {
+                if (REAL_PATH) SV.x[j * n + idx] = qnan;
+                else reinterpret_cast<double2 *>(SV.x)[j * n + idx] = make_double2(qnan, qnan);
+            }
+        }
+        continue;
+    }
     if (REAL_PATH) {
         L11[idx] = X1[N - 1].re;
         if (WANT_TAIL) {
@@ -642,7 +709,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
 // ---- host-side launcher -------------------------------------------------------------------------
 template <int N, bool REAL_PATH>
 static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, int64_t n, double *d_L11,
-                    double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G)
+                    double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G, const TzSolveArgs &SV)
 {
     TzParams<N> P;
     for (int j = 0; j <= N; j++) P.a[j] = a_rev[j];
@@ -669,17 +736,18 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     // shifts per thread: consecutive shifts share a warm start (longer runs amortise the cold start), but the grid
     // should still fill every SM to its resident-block limit: the smallest spt for which the grid is one full wave
     static int wave_cache[2] = {0, 0};   // resident blocks of this instantiation over the whole GPU (tail / no tail)
-    int wave_blocks = wave_cache[d_tail ? 1 : 0];
+    const bool want_tail = d_tail != nullptr || SV.x != nullptr;
+    int wave_blocks = wave_cache[want_tail ? 1 : 0];
     if (wave_blocks == 0) {
         int dev = 0, sms = 148, per_sm = 4;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (d_tail)
+        if (want_tail)
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ql_toeplitz_l11_kernel<N, REAL_PATH, true>, threads, 0);
         else
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ql_toeplitz_l11_kernel<N, REAL_PATH, false>, threads, 0);
         wave_blocks = sms * (per_sm > 0 ? per_sm : 1);
-        wave_cache[d_tail ? 1 : 0] = wave_blocks;
+        wave_cache[want_tail ? 1 : 0] = wave_blocks;
     }
     int spt = (int)((n + (int64_t)wave_blocks * threads - 1) / ((int64_t)wave_blocks * threads));
     while (spt & (spt - 1)) spt &= spt - 1;   // power of two: runs then do not straddle the rows of power-of-two grids
@@ -688,10 +756,10 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     if (spt > 16) spt = 16;
     const int64_t nthreads = (n + spt - 1) / spt;
     const int64_t blocks = (nthreads + threads - 1) / threads;
-    if (d_tail)
-        ql_toeplitz_l11_kernel<N, REAL_PATH, true><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status, G);
+    if (want_tail)
+        ql_toeplitz_l11_kernel<N, REAL_PATH, true><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status, G, SV);
     else
-        ql_toeplitz_l11_kernel<N, REAL_PATH, false><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status, G);
+        ql_toeplitz_l11_kernel<N, REAL_PATH, false><<<(unsigned)blocks, threads, 0, stream>>>(P, d_lambda, n, spt, d_L11, d_tail, d_status, G, SV);
     count_launch();
     ILA_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -699,16 +767,16 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
 
 template <bool REAL_PATH>
 static int launch_any(int l, const cplx *a_rev, int branch_rank, const double *d_lambda, int64_t n, double *d_L11,
-                      double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G)
+                      double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G, const TzSolveArgs &SV)
 {
     switch (l + 1) {
-    case 2: return launch_n<2, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
-    case 3: return launch_n<3, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
-    case 4: return launch_n<4, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
-    case 5: return launch_n<5, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
-    case 6: return launch_n<6, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
-    case 7: return launch_n<7, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
-    case 8: return launch_n<8, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
+    case 2: return launch_n<2, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G, SV);
+    case 3: return launch_n<3, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G, SV);
+    case 4: return launch_n<4, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G, SV);
+    case 5: return launch_n<5, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G, SV);
+    case 6: return launch_n<6, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G, SV);
+    case 7: return launch_n<7, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G, SV);
+    case 8: return launch_n<8, REAL_PATH>(a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G, SV);
     default: return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz: lower bandwidth l must be in 1..7");
     }
 }
@@ -716,13 +784,14 @@ static int launch_any(int l, const cplx *a_rev, int branch_rank, const double *d
 // Exposed to api.cu.  `a` is in BandedMatrices data-column order (a_{+1}, a_0, ..., a_{-l}); `reverse` (infqltoeplitz.jl:59)
 // is done here.
 int launch_ql_toeplitz_ex(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
-                          int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G);
+                          int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G,
+                          const TzSolveArgs &SV);
 
 int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
                        int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream)
 {
     return launch_ql_toeplitz_ex(real_path, l, u, a_host, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream,
-                                 TzGrid{nullptr, nullptr, 0, nullptr});
+                                 TzGrid{nullptr, nullptr, 0, nullptr}, TzSolveArgs{});
 }
 
 // grid mode: |L11| (or -1) for λ = gx[j] + i*gy[k], idx = k*nx + j, k < ny
@@ -730,11 +799,12 @@ int launch_ql_toeplitz_grid(int l, int u, const double *a_host, int branch_rank,
                             const double *d_gy, int64_t ny, double *d_absout, cudaStream_t stream)
 {
     return launch_ql_toeplitz_ex(false, l, u, a_host, branch_rank, nullptr, (int64_t)nx * ny, nullptr, nullptr, nullptr,
-                                 stream, TzGrid{d_gx, d_gy, nx, d_absout});
+                                 stream, TzGrid{d_gx, d_gy, nx, d_absout}, TzSolveArgs{});
 }
 
 int launch_ql_toeplitz_ex(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
-                          int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G)
+                          int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream, TzGrid G,
+                          const TzSolveArgs &SV)
 {
     if (u != 1) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz: only u == 1 (Hessenberg) symbols are supported (ql_pruneband is undefined upstream)");
     if (l < 1 || l + 1 > kMaxDeg) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz: lower bandwidth l must be in 1..7");
@@ -747,8 +817,8 @@ int launch_ql_toeplitz_ex(bool real_path, int l, int u, const double *a_host, in
     }
     if (a_rev[m - 1].re == 0.0 && a_rev[m - 1].im == 0.0)
         return set_error(ILA_ERR_ARG, "ql_toeplitz: super-diagonal coefficient is zero (u would be 0)");
-    return real_path ? launch_any<true>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G)
-                     : launch_any<false>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G);
+    return real_path ? launch_any<true>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G, SV)
+                     : launch_any<false>(l, a_rev, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream, G, SV);
 }
 
 
@@ -876,12 +946,6 @@ int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, cons
 // pending row updates live in a register window; x is written column-major (x[i + j n]: coalesced across shifts, and the
 // n x nout Matrix a Julia caller wants).  The reference stops when the remaining entries are exactly zero; here the
 // caller states how many entries it wants.
-constexpr int kSolveMaxB = 16;
-struct TzSolveParams {
-    int nb;
-    cplx b[kSolveMaxB];
-};
-
 template <int N, bool REAL_PATH>
 __global__ void __launch_bounds__(128)
 ql_toeplitz_solve_kernel(TzSolveParams S, int64_t n, const double *__restrict__ tail, const int32_t *__restrict__ status,
@@ -891,49 +955,19 @@ ql_toeplitz_solve_kernel(TzSolveParams S, int64_t n, const double *__restrict__ 
     if (idx >= n) return;
     constexpr int M = N + 1, W = REAL_PATH ? 1 : 2;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    auto put = [&](int64_t j, cplx v) {
-        if (REAL_PATH) x[j * n + idx] = v.re;
-        else reinterpret_cast<double2 *>(x)[j * n + idx] = make_double2(v.re, v.im);
-    };
     if (status[idx] != ILA_OK) {
-        for (int64_t j = 0; j < nout; j++) put(j, mk(qnan, qnan));
+        for (int64_t j = 0; j < nout; j++) {
+            if (REAL_PATH) x[j * n + idx] = qnan;
+            else reinterpret_cast<double2 *>(x)[j * n + idx] = make_double2(qnan, qnan);
+        }
         return;
     }
     const double *t = tail + idx * (2 * M + 2) * W;
     auto tl = [&](int k) -> cplx { return REAL_PATH ? mk(t[k], 0.0) : mk(t[2 * k], t[2 * k + 1]); };
-    const cplx l11 = tl(N - 1), v = tl(N), tau1 = tl(2 * M), tau2 = tl(2 * M + 1);
-    // q = H_2 H_1,  H_1 = diag(1 - tau1, 1),  H_2 = I - tau2 [v;1][v;1]'
-    const cplx one = mk(1.0, 0.0);
-    const cplx s1 = one - tau1;
-    const cplx q11 = (one - abs2(v) * tau2) * s1, q21 = (-(conj(v) * tau2)) * s1;
-    const cplx q12 = -(v * tau2), q22 = one - tau2;
-    // Q'b: b[n:n+1] <- q' b[n:n+1], n = nb, ..., 1
-    cplx tb[kSolveMaxB + 1];
-    for (int k = 0; k <= kSolveMaxB; k++) tb[k] = (k < S.nb) ? S.b[k] : mk(0.0, 0.0);
-    for (int k = S.nb; k >= 1; k--) {
-        const cplx u0 = tb[k - 1], u1 = tb[k];
-        tb[k - 1] = conj(q11) * u0 + conj(q21) * u1;
-        tb[k] = conj(q12) * u0 + conj(q22) * u1;
-    }
-    // L \ (Q'b): sub[i-1] = L[j+i, j] = X[2, m-i], i = 1..N; diagonal X[1,m-1] (first column) / X[2,m] (others)
-    cplx sub[N];
+    cplx X2[N + 1];
 #pragma unroll
-    for (int i = 1; i <= N; i++) sub[i - 1] = tl(M + (M - 1 - i));
-    const cplx dtail = tl(M + M - 1);
-    auto rcp = [&](cplx d) { const double r2 = 1.0 / abs2(d); return r2 * conj(d); };
-    const cplx r_first = rcp(l11), r_tail = rcp(dtail);
-    cplx r[N + 1];   // r[0] = current row, r[k] = pending value of row j + k
-#pragma unroll
-    for (int k = 0; k <= N; k++) r[k] = tb[k <= kSolveMaxB ? k : kSolveMaxB];
-    for (int64_t j = 0; j < nout; j++) {
-        const cplx xj = r[0] * (j == 0 ? r_first : r_tail);
-        put(j, xj);
-        const int64_t nx = j + N + 1;   // row entering the window
-        const cplx tin = (nx <= S.nb) ? tb[nx] : mk(0.0, 0.0);
-#pragma unroll
-        for (int k = 0; k < N; k++) r[k] = r[k + 1] - sub[k] * xj;
-        r[N] = tin;
-    }
+    for (int k = 0; k <= N; k++) X2[k] = tl(M + k);
+    tz_solve_rows<N, REAL_PATH>(S, tl(N - 1), tl(N), X2, tl(2 * M), tl(2 * M + 1), nout, n, idx, x);
 }
 
 template <bool REAL_PATH>
@@ -952,6 +986,23 @@ static int launch_solve_any(int l, const TzSolveParams &S, int64_t n, const doub
     count_launch();
     ILA_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+// fused form: one launch of the K3 kernel that solves from its registers (no tail record in memory)
+int launch_ql_toeplitz_solve_fused(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
+                                   int64_t n, int nb, const double *b_host, int64_t nout, double *d_L11, double *d_x,
+                                   int32_t *d_status, cudaStream_t stream)
+{
+    if (nb < 1 || nb > kSolveMaxB) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz_solve: right-hand side length must be in 1..16");
+    if (nout < 1) return set_error(ILA_ERR_ARG, "ql_toeplitz_solve: nout must be positive");
+    TzSolveArgs SV;
+    SV.S.nb = nb;
+    for (int k = 0; k < kSolveMaxB; k++)
+        SV.S.b[k] = k < nb ? (real_path ? cplx{b_host[k], 0.0} : cplx{b_host[2 * k], b_host[2 * k + 1]}) : cplx{0.0, 0.0};
+    SV.nout = nout;
+    SV.x = d_x;
+    return launch_ql_toeplitz_ex(real_path, l, u, a_host, branch_rank, d_lambda, n, d_L11, nullptr, d_status, stream,
+                                 TzGrid{nullptr, nullptr, 0, nullptr}, SV);
 }
 
 // b_host: nb scalars (real or interleaved complex, like the symbol); d_tail: the `tail` output of launch_ql_toeplitz
