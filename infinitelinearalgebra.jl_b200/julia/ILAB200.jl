@@ -5,6 +5,8 @@
 #   ql(A - λ*I).L[1,1]            -> ILAB200.ql_L11(A, [λ])[1]
 #   ℓ11.(Ref(A), x' .+ y.*im)     -> ILAB200.ql_L11(A, vec(x' .+ y.*im))        (examples/toeplitz.jl:14-33)
 #   A \ b  (∞ banded, affine bands) -> ILAB200.qr_solve(...)                     (src/infqr.jl:370-374)
+#   ql(A - λ*I) \ b                -> ILAB200.ql_solve(A, λs, b, nout)           (src/infql.jl:266-289)
+#   ql(::PertToeplitz), ql(::BlockTriPertToeplitz) -> ql_pert_L11, blocktri_L11   (src/infql.jl:70-93,189-209)
 # Exceptions of the reference are rebuilt from status[] (SURVEY §5).
 module ILAB200
 
@@ -78,6 +80,82 @@ function qr_solve(l::Integer, u::Integer, p::Matrix{Float64}, q::Matrix{Float64}
                 l, u, batch, pT, qT, rT, sh, hp, hT, size(b, 2), bT, tol, colgrowth, ncap, C_NULL, x, xcap, xoff, ncols,
                 nconv, C_NULL, C_NULL, C_NULL, status, ngpus))
     [x[xoff[i]+1:xoff[i+1]] for i in 1:batch], ncols, nconv, status
+end
+
+"""
+    absl11_grid(datacolumn, x, y; branch_rank=1, ngpus=1) -> Matrix{Float64}
+
+The example's `ℓ11.(Ref(A), x' .+ y.*im)` (examples/toeplitz.jl:14-33): `abs(L[1,1])`, or `-1.0` where the QL does not
+exist.  Shifts are formed on the device; the result is `length(y) × length(x)` (row-major on the C side = the
+transpose of what Julia stores, hence the final `permutedims`).
+"""
+function absl11_grid(datacolumn::AbstractVector, x::AbstractVector{<:Real}, y::AbstractVector{<:Real};
+                     branch_rank::Integer=1, ngpus::Integer=1)
+    a = Vector{ComplexF64}(datacolumn); xs = Vector{Float64}(x); ys = Vector{Float64}(y)
+    out = Matrix{Float64}(undef, length(xs), length(ys))
+    check(ccall((:ila_ql_toeplitz_absl11_grid_c64, lib), Cint,
+                (Cint, Cint, Ptr{ComplexF64}, Ptr{Float64}, Cint, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Cint),
+                length(a) - 2, 1, a, xs, length(xs), ys, length(ys), branch_rank, out, ngpus))
+    permutedims(out)
+end
+
+"""
+    ql_solve(datacolumn, λs, b, nout; branch_rank=1, ngpus=1) -> (X::Matrix, status)
+
+`X[i, 1:nout] = (ql(A - λs[i]*I) \\ b)[1:nout]` for a pure Toeplitz `A` (u == 1) and a finitely supported `b`
+(`length(b) ≤ 16`).  Replaces `ldiv!(F.L, lmul!(F.Q', b))` (src/infql.jl:266-289, src/banded/hessenbergq.jl:125-135).
+The library writes `X` column-major n × nout — exactly Julia's `Matrix` layout.
+"""
+function ql_solve(datacolumn::AbstractVector, λs::AbstractVector, b::AbstractVector, nout::Integer;
+                  branch_rank::Integer=1, ngpus::Integer=1)
+    a = Vector{ComplexF64}(datacolumn); λ = Vector{ComplexF64}(λs); bb = Vector{ComplexF64}(b)
+    n = length(λ)
+    X = Matrix{ComplexF64}(undef, n, nout); status = Vector{Int32}(undef, n)
+    check(ccall((:ila_ql_toeplitz_solve_c64, lib), Cint,
+                (Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Int64, Cint, Cint, Ptr{ComplexF64}, Int64, Ptr{ComplexF64},
+                 Ptr{Int32}, Cint),
+                length(a) - 2, 1, a, λ, n, branch_rank, length(bb), bb, nout, X, status, ngpus))
+    X, status
+end
+
+"""
+    ql_pert_L11(head, datacolumn, λs; branch_rank=1, ngpus=1) -> (L11, status)
+
+`ql(A - λ*I).L[1,1]` for a perturbed Toeplitz operator: `head` is the p × p top-left corner of `A` (unshifted), the
+tail symbol as in `ql_L11`.  Replaces `ql_hessenberg!` (src/infql.jl:70-93).
+"""
+function ql_pert_L11(head::AbstractMatrix, datacolumn::AbstractVector, λs::AbstractVector; branch_rank::Integer=1,
+                     ngpus::Integer=1)
+    a = Vector{ComplexF64}(datacolumn); λ = Vector{ComplexF64}(λs); h = Matrix{ComplexF64}(head)
+    n = length(λ); p = size(h, 1)
+    L11 = Vector{ComplexF64}(undef, n); status = Vector{Int32}(undef, n)
+    check(ccall((:ila_ql_perttoeplitz_l11_c64, lib), Cint,
+                (Cint, Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Int64, Cint, Ptr{ComplexF64},
+                 Ptr{ComplexF64}, Ptr{Int32}, Cint),
+                length(a) - 2, 1, p, h, a, λ, n, branch_rank, L11, C_NULL, status, ngpus))
+    L11, status
+end
+
+"""
+    blocktri_L11(dl_head, d_head, du_head, c, a, b, energies; atol=1e-10, maxit=1_000_000, ngpus=1)
+
+`ql(A - x*I).L[1,1]` over `energies` for `A = BlockTridiagonal(Vcat(dl_head, Fill(c,∞)), Vcat(d_head, Fill(a,∞)),
+Vcat(du_head, Fill(b,∞)))` with n × n real blocks (n ≤ 4).  Replaces `_blocktripert_ql` / `blocktailiterate`
+(src/infql.jl:166-209).  Returns `(L11, iters, status)`; status 3 = "Did not converge" (src/infql.jl:181).
+(`ila_ql_blocktri_l11_c64` is the same call with `ComplexF64` blocks / energies.)
+"""
+function blocktri_L11(dl_head::Vector{Matrix{Float64}}, d_head::Vector{Matrix{Float64}}, du_head::Vector{Matrix{Float64}},
+                      c::Matrix{Float64}, a::Matrix{Float64}, b::Matrix{Float64}, energies::AbstractVector{<:Real};
+                      atol::Real=1e-10, maxit::Integer=1_000_000, ngpus::Integer=1)
+    n = size(c, 1); e = Vector{Float64}(energies); m = length(e)
+    cat3(v) = isempty(v) ? Float64[] : reduce(vcat, vec.(v))      # blocks are column-major already
+    L11 = Vector{Float64}(undef, m); iters = Vector{Int32}(undef, m); status = Vector{Int32}(undef, m)
+    check(ccall((:ila_ql_blocktri_l11_f64, lib), Cint,
+                (Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64},
+                 Ptr{Float64}, Int64, Float64, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Cint),
+                n, c, a, b, length(dl_head), cat3(dl_head), length(d_head), cat3(d_head), length(du_head), cat3(du_head),
+                e, m, atol, maxit, L11, iters, status, ngpus))
+    L11, iters, status
 end
 
 "Bessel recurrence of README.md:41-43: `A \\ [besselj(1,z); Zeros(∞)]` for many z at once."
