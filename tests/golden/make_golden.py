@@ -4,6 +4,9 @@
 
 bullhead_64x64.npz : Bull-head L[1,1]/status on a 64x64 sub-grid of BASELINE config C3 (numpy/LAPACK oracle)
 bessel_z1000.npz   : A \\ [besselj(1,z); 0...] for z = 1000 (C oracle), with ncols/nconv
+chol_pentadiag.npz : BASELINE config C4 operator at 4 shifts: adaptive Cholesky solve (C oracle)
+blocktri.npz       : periodic Schrödinger block QL at 16 energies (C5) + the complex `-5im*I` case (numpy oracle)
+ql_solve.npz       : ql(A - λI) \\ b for the tridiagonal symbol of test/test_infql.jl:143-145 and the Bull-head symbol
 """
 import os
 import sys
@@ -28,4 +31,31 @@ o = ob.qr_banded_solve(1, 1, p, q, r, b=[jv(1, z)], ncap=8000)
 n = int(o["ncols"][0])
 np.savez_compressed(os.path.join(HERE, "bessel_z1000.npz"), z=z, b=jv(1, z), x=o["x"][0, :n], ncols=n,
                     nconv=int(o["nconv"][0]))
+
+sigma = np.array([0.01, 1.0, 5.0, 10.0])
+p4 = np.tile(np.array([1.0, -4.0, 6.0]), (4, 1)); p4[:, 2] += sigma
+q4 = np.zeros((4, 3)); q4[:, 2] = 1e-4
+o = ob.chol_banded_solve(2, p4, q4, b=[1.0], ncap=8000)
+nmax = int(o["ncols"].max())
+np.savez_compressed(os.path.join(HERE, "chol_pentadiag.npz"), sigma=sigma, x=o["x"][:, :nmax], ncols=o["ncols"],
+                    nconv=o["nconv"], status=o["status"])
+
+from oracle import block_ql as bq        # noqa: E402
+xs = np.concatenate([np.linspace(-0.95, 0.95, 8), np.linspace(2.25, 4.0, 8)])
+res = [bq.periodic_schrodinger(x) for x in xs]
+c2, a2, b2 = np.array([[0, 0.5], [0, 0]]), np.array([[0, 2.0], [0.5, 0]]), np.array([[0, 0.0], [2.0, 0]])
+xc = np.array([5j, 2.0 + 4.0j, -0.5 - 3.0j])
+resc = [bq.blocktri_ql_l11([c2], [a2], [b2], c2, a2, b2, shift=x, maxit=5000) for x in xc]
+np.savez_compressed(os.path.join(HERE, "blocktri.npz"), energies=xs, L11=np.array([r[0] for r in res]),
+                    iters=np.array([r[1] for r in res]), status=np.array([r[2] for r in res]),
+                    c_energies=xc, c_L11=np.array([r[0] for r in resc]), c_iters=np.array([r[1] for r in resc]))
+
+col3 = np.array([0.5, 5.0, 2.0])
+x3, s3 = tq.ql_toeplitz_solve(col3, np.array([0.0, 1.0, -2.5]), np.array([1.0]), 64)
+colb = np.array([2j, 0, 0, 1, 0.7])
+lamb = np.array([5.0 + 1j, -3 - 0.1j, 2 + 3j, 0.1 + 0.1j])
+xb, sb = tq.ql_toeplitz_solve(colb, lamb, np.array([1.0, 0.5j, -0.25]), 32)
+np.savez_compressed(os.path.join(HERE, "ql_solve.npz"), tri_col=col3, tri_lam=np.array([0.0, 1.0, -2.5]), tri_x=x3,
+                    tri_status=s3, bull_col=colb, bull_lam=lamb, bull_b=np.array([1.0, 0.5j, -0.25]), bull_x=xb,
+                    bull_status=sb)
 print("wrote fixtures")
