@@ -183,6 +183,15 @@ int ila_ql_toeplitz_solve_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 
 int ila_ql_toeplitz_solve_f64_dev(int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank, int nb,
                                   const double *b, int64_t nout, double *d_work, double *d_x, int32_t *d_status, void *stream);
 
+/* Perturbed-Toeplitz form of the solve: head / a / p as in ila_ql_perttoeplitz_l11_*.  Replaces the assembly of
+ * ql_hessenberg! (src/infql.jl:70-93: head factors, the l' extension rows (Q∞')[2:l'+1,1:l'+1] T[l':2l',1:l'], Toeplitz tail
+ * columns; Q = Vcat(LowerHessenbergQ(F.Q).q, F∞.q), src/banded/hessenbergq.jl:182-190) followed by F \ b
+ * (src/infql.jl:266-289).  Pinned by test/test_infql.jl:147-160. */
+int ila_ql_perttoeplitz_solve_c64(int l, int u, int p, const ila_c64 *head, const ila_c64 *a, const ila_c64 *lambda, int64_t n,
+                                  int branch_rank, int nb, const ila_c64 *b, int64_t nout, ila_c64 *x, int32_t *status, int ngpus);
+int ila_ql_perttoeplitz_solve_f64(int l, int u, int p, const double *head, const double *a, const double *lambda, int64_t n,
+                                  int branch_rank, int nb, const double *b, int64_t nout, double *x, int32_t *status, int ngpus);
+
 /* ---- K6: block-tridiagonal perturbed-Toeplitz QL,  L11[i] = ql(A - energy[i]*I).L[1,1] ----------------------------
  * A = BlockTridiagonal(Vcat(dl_head, Fill(c,∞)), Vcat(d_head, Fill(a,∞)), Vcat(du_head, Fill(b,∞))) with n x n blocks
  * (column-major; dl = A[Block(k+1,k)], du = A[Block(k,k+1)]; head tables hold n_dl / n_d / n_du blocks, n <= 4,

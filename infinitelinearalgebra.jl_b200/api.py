@@ -230,10 +230,15 @@ class QLHessenberg:
 
     def solve(self, b, n=1000):
         """First n entries of `F \\ b` (ldiv!(F.L, lmul!(F.Q', b)), src/infql.jl:266-289) for a pure Toeplitz operator."""
-        if self._source is None:
-            raise NotImplementedError("F \\ b is implemented for pure Toeplitz operators (no head perturbation)")
-        col, lam, branch = self._source
         bb = np.atleast_1d(np.asarray(b.head if isinstance(b, Vcat) else b))
+        if self._source is None:
+            raise NotImplementedError("F \\ b needs the operator the factorization came from")
+        if isinstance(self._source[0], str) and self._source[0] == "pert":
+            _, head, col, lam, branch = self._source
+            x, st = _b.ql_perttoeplitz_solve(head, col, np.array([lam]), bb, int(n), branch_rank=branch)
+            _raise_status(st[0], "ql(A) \\ b")
+            return x[0]
+        col, lam, branch = self._source
         x, st = _b.ql_toeplitz_solve(col, np.array([lam]), bb, int(n), branch_rank=branch)
         _raise_status(st[0], "ql(A) \\ b")
         return x[0]
@@ -321,7 +326,7 @@ def ql(A, branch=1):
     L, st, hf = _b.ql_perttoeplitz_l11(head, col, np.array([lam]), branch_rank=branch, want_head_factors=True,
                                        real_path=not (cplx or np.iscomplexobj(head)))
     _raise_status(st[0], "ql")
-    return QLHessenberg(l, None, None, head_factors=hf[0], head_l11=L[0])
+    return QLHessenberg(l, None, None, head_factors=hf[0], head_l11=L[0], source=("pert", head, col, lam, branch))
 
 
 def ql_L11(A, lambdas, branch=1, ngpus=1):

@@ -126,6 +126,33 @@ def ql_perttoeplitz_l11(head, data_column, lambdas, branch_rank: int = 1, want_h
     return res
 
 
+def ql_perttoeplitz_solve(head, data_column, lambdas, b, nout: int, branch_rank: int = 1, ngpus: int = 1,
+                          real_path: bool | None = None):
+    """First `nout` entries of x = ql(A - λI) \\ b for the perturbed Toeplitz A of `ql_perttoeplitz_l11`
+    (reference: ql_hessenberg! assembly, src/infql.jl:70-93, and F \\ b, src/infql.jl:266-289; test/test_infql.jl:147-160).
+    Returns (x [shape lambdas.shape + (nout,)], status)."""
+    col = np.asarray(data_column)
+    head = np.asarray(head)
+    lam = np.asarray(lambdas)
+    bb = np.asarray(b)
+    if real_path is None:
+        real_path = not (np.iscomplexobj(col) or np.iscomplexobj(lam) or np.iscomplexobj(head) or np.iscomplexobj(bb))
+    dt = np.float64 if real_path else np.complex128
+    col = np.ascontiguousarray(col, dtype=dt)
+    bb = np.ascontiguousarray(bb, dtype=dt).reshape(-1)
+    p = head.shape[0]
+    hflat = np.ascontiguousarray(np.asarray(head, dtype=dt).reshape(-1, order="F"))
+    shape = lam.shape
+    lam = np.ascontiguousarray(lam, dtype=dt).reshape(-1)
+    n = lam.size
+    x = np.empty((int(nout), n), dtype=dt)            # column-major n x nout
+    status = np.empty(n, dtype=np.int32)
+    fn = lib().ila_ql_perttoeplitz_solve_f64 if real_path else lib().ila_ql_perttoeplitz_solve_c64
+    check(fn(col.size - 2, 1, p, ptr(hflat), ptr(col), ptr(lam), n, branch_rank, bb.size, ptr(bb), int(nout), ptr(x),
+             ptr(status), ngpus))
+    return np.ascontiguousarray(x.T).reshape(shape + (int(nout),)), status.reshape(shape)
+
+
 # ------------------------------------------------------------------------------------------------
 # K6: block-tridiagonal Toeplitz-tail QL
 # ------------------------------------------------------------------------------------------------

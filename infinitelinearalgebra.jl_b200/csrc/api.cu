@@ -25,6 +25,9 @@ int launch_ql_toeplitz_grid(int l, int u, const double *a_host, int branch_rank,
 int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
                         int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
                         cudaStream_t stream);
+int launch_ql_pert_head_ex(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
+                           int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
+                           int nb, const double *b_host, int64_t nout, double *d_x, cudaStream_t stream);
 
 // from qr_banded.cu
 struct QrFwdArgs {
@@ -511,9 +514,11 @@ int ila_ql_toeplitz_solve_f64_dev(int l, int u, const double *a, const double *d
 // ================================ K4: perturbed-Toeplitz head ==========================================
 
 static int ql_pert_host(bool real_path, int l, int u, int p, const double *head, const double *a, const double *lambda,
-                        int64_t n, int branch_rank, double *L11, double *head_factors_opt, int32_t *status, int ngpus)
+                        int64_t n, int branch_rank, double *L11, double *head_factors_opt, int32_t *status, int ngpus,
+                        int nb = 0, const double *b = nullptr, int64_t nout = 0, double *x = nullptr)
 {
-    if (n < 0 || !a || !head || (n > 0 && (!lambda || !L11 || !status))) return set_error(ILA_ERR_ARG, "ql_perttoeplitz: bad arguments");
+    if (n < 0 || !a || !head || (n > 0 && (!lambda || !status || (!L11 && !x)))) return set_error(ILA_ERR_ARG, "ql_perttoeplitz: bad arguments");
+    if (x && (!b || nb < 1 || nout < 1)) return set_error(ILA_ERR_ARG, "ql_perttoeplitz_solve: bad right-hand side / nout");
     int G = 0;
     int rc = resolve_ngpus(ngpus, &G);
     if (rc) return rc;
@@ -528,18 +533,22 @@ static int ql_pert_host(bool real_path, int l, int u, int p, const double *head,
         if (cnt <= 0) continue;
         const int pd = phys(d, G);
         if ((rc = dev_init(pd))) return rc;
-        double *d_lam, *d_L, *d_tail, *d_hf = nullptr;
+        double *d_lam, *d_L, *d_tail, *d_hf = nullptr, *d_x = nullptr;
         int32_t *d_st;
         if ((rc = dev_buf_t(pd, 0, (size_t)cnt * w, &d_lam))) return rc;
         if ((rc = dev_buf_t(pd, 1, (size_t)cnt * w, &d_L))) return rc;
         if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
         if ((rc = dev_buf_t(pd, 3, (size_t)cnt * tl * w, &d_tail))) return rc;
         if (head_factors_opt && (rc = dev_buf_t(pd, 23, (size_t)cnt * p * p * w, &d_hf))) return rc;
+        if (x && (rc = dev_buf_t(pd, 4, (size_t)cnt * nout * w, &d_x))) return rc;
         cudaStream_t s = g_dev[pd].stream;
         ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam, lambda + lo * w, sizeof(double) * cnt * w, cudaMemcpyHostToDevice, s));
         if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam, cnt, d_L, d_tail, d_st, s))) return rc;
-        if ((rc = launch_ql_pert_head(real_path, l, p, a, head, d_lam, cnt, d_tail, d_st, d_L, d_hf, s))) return rc;
-        ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + lo * w, d_L, sizeof(double) * cnt * w, cudaMemcpyDeviceToHost, s));
+        if ((rc = launch_ql_pert_head_ex(real_path, l, p, a, head, d_lam, cnt, d_tail, d_st, d_L, d_hf, nb, b, nout, d_x, s))) return rc;
+        if (L11) ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + lo * w, d_L, sizeof(double) * cnt * w, cudaMemcpyDeviceToHost, s));
+        if (x)
+            ILA_CUDA_CHECK(cudaMemcpy2DAsync(x + lo * w, sizeof(double) * n * w, d_x, sizeof(double) * cnt * w,
+                                             sizeof(double) * cnt * w, (size_t)nout, cudaMemcpyDeviceToHost, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
         if (head_factors_opt)
             ILA_CUDA_CHECK(cudaMemcpyAsync(head_factors_opt + lo * p * p * w, d_hf, sizeof(double) * cnt * p * p * w, cudaMemcpyDeviceToHost, s));
@@ -565,6 +574,19 @@ int ila_ql_perttoeplitz_l11_f64(int l, int u, int p, const double *head, const d
                                 int branch_rank, double *L11, double *head_factors_opt, int32_t *status, int ngpus)
 {
     return ql_pert_host(true, l, u, p, head, a, lambda, n, branch_rank, L11, head_factors_opt, status, ngpus);
+}
+
+int ila_ql_perttoeplitz_solve_c64(int l, int u, int p, const ila_c64 *head, const ila_c64 *a, const ila_c64 *lambda, int64_t n,
+                                  int branch_rank, int nb, const ila_c64 *b, int64_t nout, ila_c64 *x, int32_t *status, int ngpus)
+{
+    return ql_pert_host(false, l, u, p, (const double *)head, (const double *)a, (const double *)lambda, n, branch_rank,
+                        nullptr, nullptr, status, ngpus, nb, (const double *)b, nout, (double *)x);
+}
+
+int ila_ql_perttoeplitz_solve_f64(int l, int u, int p, const double *head, const double *a, const double *lambda, int64_t n,
+                                  int branch_rank, int nb, const double *b, int64_t nout, double *x, int32_t *status, int ngpus)
+{
+    return ql_pert_host(true, l, u, p, head, a, lambda, n, branch_rank, nullptr, nullptr, status, ngpus, nb, b, nout, x);
 }
 
 // ================================ K6: block-tridiagonal Toeplitz-tail QL ================================

@@ -839,7 +839,8 @@ struct TzHeadParams {
 template <bool REAL_PATH>
 __global__ void __launch_bounds__(128)
 ql_pert_head_kernel(TzHeadParams H, const double *__restrict__ lambda, int64_t n, const double *__restrict__ tail,
-                    const int32_t *__restrict__ status, double *__restrict__ L11, double *__restrict__ head_factors)
+                    const int32_t *__restrict__ status, double *__restrict__ L11, double *__restrict__ head_factors,
+                    TzSolveArgs SV)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
@@ -849,7 +850,16 @@ ql_pert_head_kernel(TzHeadParams H, const double *__restrict__ lambda, int64_t n
         if (REAL_PATH) L11[idx] = v.re;
         else reinterpret_cast<double2 *>(L11)[idx] = make_double2(v.re, v.im);
     };
-    if (status[idx] != ILA_OK) { put(mk(qnan, qnan)); return; }
+    auto putx = [&](int64_t j, cplx val) {
+        if (REAL_PATH) SV.x[j * n + idx] = val.re;
+        else reinterpret_cast<double2 *>(SV.x)[j * n + idx] = make_double2(val.re, val.im);
+    };
+    if (status[idx] != ILA_OK) {
+        put(mk(qnan, qnan));
+        if (SV.x)
+            for (int64_t j = 0; j < SV.nout; j++) putx(j, mk(qnan, qnan));
+        return;
+    }
     const double *t = tail + idx * (2 * M + 2) * W;
     auto tl = [&](int k) -> cplx { return REAL_PATH ? mk(t[k], 0.0) : mk(t[2 * k], t[2 * k + 1]); };
     const cplx lam = REAL_PATH ? mk(lambda[idx], 0.0) : mk(lambda[2 * idx], lambda[2 * idx + 1]);
@@ -878,6 +888,8 @@ ql_pert_head_kernel(TzHeadParams H, const double *__restrict__ lambda, int64_t n
         }
     }
     // finite Householder QL of the head (reference loop: k = p..1 complex, p..2 real)
+    cplx ftau[kHeadMax];
+    for (int k = 0; k < kHeadMax; k++) ftau[k] = mk(0.0, 0.0);
     for (int k = p; k >= (REAL_PATH ? 2 : 1); k--) {
         double s = abs2(B[k - 1][k - 1]);
         for (int i = 1; i < k; i++) s += abs2(B[k - 1 - i][k - 1]);
@@ -892,6 +904,7 @@ ql_pert_head_kernel(TzHeadParams H, const double *__restrict__ lambda, int64_t n
             for (int i = 1; i < k; i++) B[k - 1 - i][k - 1] = r2 * (B[k - 1 - i][k - 1] * conj(xi1));
             tk = (1.0 / nu) * xi1;
         }
+        ftau[k - 1] = tk;
         for (int j = 0; j < k - 1; j++) {
             cplx vA = B[k - 1][j];
             for (int i = 1; i < k; i++) vA = vA + conj(B[k - 1 - i][k - 1]) * B[k - 1 - i][j];
@@ -901,6 +914,84 @@ ql_pert_head_kernel(TzHeadParams H, const double *__restrict__ lambda, int64_t n
         }
     }
     put(B[0][0]);
+    if (SV.x) {
+        // ---- F \ b for the perturbed operator (src/infql.jl:70-93 assembly, :266-289 solve) ----
+        // 2x2 blocks: head n <= p-1 from the packed head factors (hessenbergq.jl:182-190), n >= p the tail block q∞
+        const cplx q12 = -(v * tau2), q22 = one - tau2;
+        auto block = [&](int nblk, cplx &b11, cplx &b12, cplx &b21, cplx &b22) {   // 1-based block index
+            if (nblk <= p - 1) {
+                const cplx vv = B[nblk - 1][nblk], tb_ = ftau[nblk];           // reflector of column nblk+1
+                const cplx sa = (nblk == 1) ? (one - ftau[0]) : one;
+                b11 = (one - abs2(vv) * tb_) * sa;
+                b21 = (-(conj(vv) * tb_)) * sa;
+                b12 = -(vv * tb_);
+                b22 = one - tb_;
+            } else {
+                b11 = q11; b12 = q12; b21 = q21; b22 = q22;
+            }
+        };
+        constexpr int KW = kHeadMax + kMaxDeg + kSolveMaxB + 2;
+        cplx tw[KW];
+        for (int k = 0; k < KW; k++) tw[k] = (k < SV.S.nb) ? SV.S.b[k] : mk(0.0, 0.0);
+        for (int k = SV.S.nb; k >= 1; k--) {
+            cplx b11, b12, b21, b22;
+            block(k, b11, b12, b21, b22);
+            const cplx u0 = tw[k - 1], u1 = tw[k];
+            tw[k - 1] = conj(b11) * u0 + conj(b21) * u1;
+            tw[k] = conj(b12) * u0 + conj(b22) * u1;
+        }
+        // extension block E = (Q∞')[2:l'+1, 1:l'+1] T[l':2l', 1:l']  (rows p+1..p+l', columns p-l'+1..p; src/infql.jl:87)
+        constexpr int QD = kMaxDeg + 3;
+        cplx Qd[QD][QD];
+        const int qd = N + 3;
+        for (int i = 0; i < qd; i++)
+            for (int j = 0; j < qd; j++) Qd[i][j] = (i == j) ? one : mk(0.0, 0.0);
+        for (int nb_ = 0; nb_ <= N + 1; nb_++)
+            for (int j = 0; j < qd; j++) {
+                const cplx r0 = Qd[nb_][j], r1 = Qd[nb_ + 1][j];
+                Qd[nb_][j] = q11 * r0 + q12 * r1;
+                Qd[nb_ + 1][j] = q21 * r0 + q22 * r1;
+            }
+        cplx a_sh[kMaxDeg + 1];
+        for (int k = 0; k < M; k++) a_sh[k] = H.a_rev[k];
+        a_sh[M - 2] = a_sh[M - 2] - lam;
+        auto Tent = [&](int i, int j) -> cplx {   // 1-based entry of the shifted Toeplitz tail
+            const int k = (j - i) + M - 2;
+            return (k >= 0 && k < M) ? a_sh[k] : mk(0.0, 0.0);
+        };
+        cplx E[kMaxDeg][kMaxDeg];
+        for (int r = 0; r < N; r++)
+            for (int c = 0; c < N; c++) {
+                cplx acc = mk(0.0, 0.0);
+                for (int k = 0; k <= N; k++) acc = acc + conj(Qd[k][r + 1]) * Tent(N + k, 1 + c);   // Qadj[r+1][k]
+                E[r][c] = acc;
+            }
+        auto rcpc = [&](cplx d) { const double r2 = 1.0 / abs2(d); return r2 * conj(d); };
+        // columns of the head (rows up to p + l' - 1 all live in tw), then the Toeplitz tail through a sliding window
+        const int64_t jhead = SV.nout < p ? SV.nout : p;
+        for (int j = 0; j < p; j++) {
+            const cplx xj = tw[j] * rcpc(B[j][j]);
+            tw[j] = xj;
+            if (j < jhead) putx(j, xj);
+            for (int i = j + 1; i < p; i++) tw[i] = tw[i] - B[i][j] * xj;
+            const int c = j - (p - N);
+            if (c >= 0)
+                for (int r = 0; r < N; r++) tw[p + r] = tw[p + r] - E[r][c] * xj;
+        }
+        const cplx r_tail = rcpc(tl(M + M - 1));
+        cplx sub[kMaxDeg];
+        for (int i = 1; i <= N; i++) sub[i - 1] = tl(M + (M - 1 - i));
+        cplx rw[kMaxDeg + 1];
+        for (int k = 0; k <= N; k++) rw[k] = tw[p + k];
+        for (int64_t j = p; j < SV.nout; j++) {
+            const cplx xj = rw[0] * r_tail;
+            putx(j, xj);
+            const int64_t nx = j + N + 1;
+            const cplx tin = (nx < KW) ? tw[nx] : mk(0.0, 0.0);
+            for (int k = 0; k < N; k++) rw[k] = rw[k + 1] - sub[k] * xj;
+            rw[N] = tin;
+        }
+    }
     if (head_factors) {
         double *o = head_factors + idx * (int64_t)p * p * W;
         for (int j = 0; j < p; j++)
@@ -912,9 +1003,22 @@ ql_pert_head_kernel(TzHeadParams H, const double *__restrict__ lambda, int64_t n
 }
 
 // head_host: p x p column-major top-left corner of A (no shift), same scalar type as the symbol
+int launch_ql_pert_head_ex(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
+                           int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
+                           int nb, const double *b_host, int64_t nout, double *d_x, cudaStream_t stream);
+
 int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
                         int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
                         cudaStream_t stream)
+{
+    return launch_ql_pert_head_ex(real_path, l, p, a_host, head_host, d_lambda, n, d_tail, d_status, d_L11, d_head_factors, 0,
+                                  nullptr, 0, nullptr, stream);
+}
+
+// with d_x != nullptr the kernel also solves F \ b (b_host: nb <= 16 scalars) and writes x column-major n x nout
+int launch_ql_pert_head_ex(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
+                           int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
+                           int nb, const double *b_host, int64_t nout, double *d_x, cudaStream_t stream)
 {
     if (p < l + 1 || p > kHeadMax) return set_error(ILA_ERR_UNSUPPORTED, "ql_perttoeplitz: head size p must satisfy l+1 <= p <= 8");
     TzHeadParams H;
@@ -927,11 +1031,21 @@ int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, cons
         H.a_rev[j] = real_path ? cplx{a_host[src], 0.0} : cplx{a_host[2 * src], a_host[2 * src + 1]};
     }
     for (int k = 0; k < p * p; k++) H.h[k] = real_path ? cplx{head_host[k], 0.0} : cplx{head_host[2 * k], head_host[2 * k + 1]};
+    TzSolveArgs SV{};
+    if (d_x) {
+        if (nb < 1 || nb > kSolveMaxB) return set_error(ILA_ERR_UNSUPPORTED, "ql_perttoeplitz_solve: right-hand side length must be in 1..16");
+        if (nout < 1) return set_error(ILA_ERR_ARG, "ql_perttoeplitz_solve: nout must be positive");
+        SV.S.nb = nb;
+        for (int k = 0; k < kSolveMaxB; k++)
+            SV.S.b[k] = k < nb ? (real_path ? cplx{b_host[k], 0.0} : cplx{b_host[2 * k], b_host[2 * k + 1]}) : cplx{0.0, 0.0};
+        SV.nout = nout;
+        SV.x = d_x;
+    }
     if (n <= 0) return 0;
     const int threads = 128;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    if (real_path) ql_pert_head_kernel<true><<<blocks, threads, 0, stream>>>(H, d_lambda, n, d_tail, d_status, d_L11, d_head_factors);
-    else ql_pert_head_kernel<false><<<blocks, threads, 0, stream>>>(H, d_lambda, n, d_tail, d_status, d_L11, d_head_factors);
+    if (real_path) ql_pert_head_kernel<true><<<blocks, threads, 0, stream>>>(H, d_lambda, n, d_tail, d_status, d_L11, d_head_factors, SV);
+    else ql_pert_head_kernel<false><<<blocks, threads, 0, stream>>>(H, d_lambda, n, d_tail, d_status, d_L11, d_head_factors, SV);
     count_launch();
     ILA_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -359,6 +359,71 @@ def ql_pert_toeplitz(head, a_rev, real_path=None, branch_rank=1):
     return dict(L11=F[0, 0], head_factors=F, head_tau=ftau, tail=tail, status=0)
 
 
+def _hessenberg_q_dense(blocks, K):
+    """Leading rows of Q = ... q_3 q_2 q_1 (LowerHessenbergQ, hessenbergq.jl:111-123): dense (K+2) x (K+2), rows < K+1 final."""
+    dt = np.result_type(*[b.dtype for b in blocks])
+    Q = np.eye(K + 2, dtype=dt)
+    for n in range(K + 1):
+        Q[n:n + 2, :] = blocks[n] @ Q[n:n + 2, :]
+    return Q
+
+
+def ql_pert_toeplitz_solve(head, a_rev, b, nout, real_path=None, branch_rank=1):
+    """First `nout` entries of x = ql(A) \\ b for the perturbed Toeplitz A of `ql_pert_toeplitz` (u == 1).
+
+    Reference: ql_hessenberg! (src/infql.jl:70-93) assembles
+      L: columns 1..p from the factored head B~ (p x p) extended by the l' rows
+         B~[p+1:p+l', p-l'+1:p] = (Q∞')[2:l'+1, 1:l'+1] T[l':2l', 1:l']            (:87)
+         and the Toeplitz tail columns [X[2,m:-1:1]] after them                    (:91-92);
+      Q: Vcat(LowerHessenbergQ(F.Q).q, F∞.q) — p-1 head blocks (hessenbergq.jl:182-190) then the constant tail block;
+    and F \\ b = ldiv!(F.L, lmul!(F.Q', b)) (src/infql.jl:266-289).  Pinned by test/test_infql.jl:147-160
+    ((Q'b)[1] ≈ 0.9892996329463546, (A*(F\\b))[1:10] ≈ e1).  Returns (x, status, qtb) with qtb = Q'b (leading part).
+    """
+    res = ql_pert_toeplitz(head, a_rev, real_path, branch_rank)
+    if res["status"] != 0:
+        return np.full(nout, np.nan), res["status"], None
+    F, ftau, tail = res["head_factors"], res["head_tau"], res["tail"]
+    dt = F.dtype
+    a_rev = np.asarray(a_rev).astype(dt)
+    p = F.shape[0]
+    m = len(a_rev)
+    lp = m - 1
+    X, tau = tail["X"].astype(dt), tail["tau"].astype(dt)
+    qinf = ql_packed_Q(X[:, m - 2:m], tau)
+    # head blocks: q_1 = QLPackedQ(F[1:2,1:2], tau[1:2]); q_j = QLPackedQ(F[j:j+1,j:j+1], [0, tau[j+1]]), j = 2..p-1
+    hq = []
+    if p >= 2:
+        hq.append(ql_packed_Q(F[0:2, 0:2], ftau[0:2]))
+        for j in range(2, p):
+            hq.append(ql_packed_Q(F[j - 1:j + 1, j - 1:j + 1], np.array([0, ftau[j]], dtype=dt)))
+    blk = lambda n: hq[n - 1] if n <= p - 1 else qinf                    # 1-based block index
+    b = np.asarray(b, dtype=dt)
+    nb = b.shape[0]
+    size = max(nb + 1, nout, p + lp) + lp + 1
+    t = np.zeros(size, dtype=dt)
+    t[:nb] = b
+    for n in range(nb, 0, -1):
+        t[n - 1:n + 1] = blk(n).conj().T @ t[n - 1:n + 1]
+    qtb = t[:nb + 1].copy()
+    # extension block E (l' x l'): rows p+1..p+l', columns p-l'+1..p
+    Qd = _hessenberg_q_dense([qinf] * (lp + 2), lp + 1)
+    Qadj = Qd.conj().T
+    Tblk = np.array([[_toeplitz_entry(a_rev, lp + ii, 1 + jj) for jj in range(lp)] for ii in range(lp + 1)], dtype=dt)
+    E = Qadj[1:lp + 1, 0:lp + 1] @ Tblk
+    sub = X[1, m - 2::-1]                                                 # tail column below its diagonal
+    for j in range(nout):
+        if j < p:
+            t[j] = t[j] / F[j, j]
+            t[j + 1:p] -= F[j + 1:p, j] * t[j]
+            c = j - (p - lp)
+            if c >= 0:
+                t[p:p + lp] -= E[:, c] * t[j]
+        else:
+            t[j] = t[j] / X[1, m - 1]
+            t[j + 1:j + 1 + lp] -= sub[:lp] * t[j]
+    return t[:nout].copy(), 0, qtb
+
+
 def pert_toeplitz_head(head_data, a_col, p=None):
     """Dense p x p top-left corner from BandedMatrices data (l+2) x p_head (rows: +1, 0, -1, ..., -l), continued by
     the Toeplitz column a_col when p exceeds the head width."""

@@ -71,3 +71,50 @@ def test_resolvent_entry_full_grid_property(ila):
     scale = 1.0 + np.abs(lam[ok]) * np.abs(x[ok, 0]) + 2 * np.abs(x[ok, 1])
     assert np.max(np.abs(res) / scale) <= 1e-12
     assert np.all(np.isnan(x[~ok]))
+
+
+def test_perturbed_jacobi_reference_case(ila):
+    # test/test_infql.jl:147-160 through the Julia-interface mirror: F = ql(J - 3.5I); u = F \ b; (A*u)[1:10] ≈ e1
+    from oracle import toeplitz_ql as tq
+    from ila_b200.api import BandedMatrix, Fill, I, Vcat, Zeros, ql
+    z = 3.5
+    J = BandedMatrix({0: Vcat([1.0], Fill(0.0)), 1: Fill(0.5), -1: Fill(0.5)})
+    F = ql(J - z * I)
+    u = F.solve(Vcat([1.0], Zeros()), n=60)
+    N = 60
+    A = np.diag(np.full(N, -z)) + np.diag(np.full(N - 1, 0.5), 1) + np.diag(np.full(N - 1, 0.5), -1)
+    A[0, 0] = 1 - z
+    assert np.allclose((A @ u)[:10], np.eye(10)[0], rtol=0, atol=1e-14)
+    xo, st, _ = tq.ql_pert_toeplitz_solve(np.array([[1 - z, 0.5], [0.5, -z]]), np.array([0.5, -z, 0.5]), np.array([1.0]), 60)
+    assert np.abs(u - xo).max() <= 1e-12 * np.abs(xo).max()
+
+
+def test_perturbed_hessenberg_batch_vs_oracle(ila):
+    from oracle import toeplitz_ql as tq
+    rng = np.random.default_rng(7)
+    col = np.array([2j, 0, 0, 1, 0.7])                  # Bull-head tail, data-column order
+    l, p = 3, 6
+    a_rev0 = col[::-1].copy()
+    N = 12
+    A0 = np.zeros((N, N), complex)
+    for i in range(N):
+        for j in range(max(0, i - l), min(N, i + 2)):
+            A0[i, j] = tq._toeplitz_entry(a_rev0, i + 1, j + 1)
+    for i in range(p - 1):
+        for j in range(max(0, i - l), min(p - 1, i + 2)):
+            A0[i, j] += 0.3 * (rng.normal() + 1j * rng.normal())
+    head = A0[:p, :p].copy()
+    lam = np.array([5.0 + 1j, -3 - 0.1j, 2 + 3j, 0.1 + 0.1j, -6 + 2j])
+    b = rng.normal(size=8) + 1j * rng.normal(size=8)
+    xg, sg = ila.ql_perttoeplitz_solve(head, col, lam, b, 48)
+    for i, lm in enumerate(lam):
+        a = a_rev0.copy(); a[3] -= lm
+        xo, so, _ = tq.ql_pert_toeplitz_solve(head - lm * np.eye(p), a, b, 48)
+        assert sg[i] == so
+        if so == 0:
+            assert np.abs(xg[i] - xo).max() <= 1e-12 * np.abs(xo).max()
+        else:
+            assert np.all(np.isnan(xg[i]))
+    # nout smaller than the head
+    xs, ss = ila.ql_perttoeplitz_solve(head, col, lam[:1], b, 3)
+    assert np.abs(xs[0] - xg[0][:3]).max() == 0.0

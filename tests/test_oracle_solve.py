@@ -42,3 +42,39 @@ def test_complex_hessenberg_vs_finite_section():
     # outside the domain of existence: NaN row, status 1
     x, st = tq.ql_toeplitz_solve(col, np.array([0.1 + 0.1j]), b, 5)
     assert st[0] == 1 and np.all(np.isnan(x[0]))
+
+
+def test_perturbed_jacobi_golden_qtb_and_residual():
+    # test/test_infql.jl:147-160: J = (0 => [1, 0, ...], ±1 => 0.5), A = J - 3.5I, b = e1:
+    #   (Q'b)[1] ≈ 0.9892996329463546 ;  u = F \ b ;  (A*u)[1:10] ≈ [1; zeros(9)]
+    z = 3.5
+    head = np.array([[1.0 - z, 0.5], [0.5, -z]])
+    a_rev = np.array([0.5, -z, 0.5])
+    x, st, qtb = tq.ql_pert_toeplitz_solve(head, a_rev, np.array([1.0]), 40)
+    assert st == 0
+    assert np.isclose(qtb[0], 0.9892996329463546, rtol=1e-13, atol=0)
+    N = 40
+    A = np.diag(np.full(N, -z)) + np.diag(np.full(N - 1, 0.5), 1) + np.diag(np.full(N - 1, 0.5), -1)
+    A[0, 0] = 1 - z
+    r = (A @ x)[:10]
+    assert np.allclose(r, np.eye(10)[0], rtol=0, atol=1e-15)
+
+
+def test_perturbed_hessenberg_vs_finite_section():
+    rng = np.random.default_rng(3)
+    a = np.array([0.7, 1, 0, -(5.0 + 1j), 2j])         # shifted Bull-head symbol, reversed order [a_-3 .. a_+1]
+    m, l, p = 5, 3, 6
+    N = 500
+    A = np.zeros((N, N), complex)
+    for i in range(N):
+        for j in range(max(0, i - l), min(N, i + 2)):
+            A[i, j] = tq._toeplitz_entry(a, i + 1, j + 1)
+    for i in range(p - 1):
+        for j in range(max(0, i - l), min(p - 1, i + 2)):
+            A[i, j] += 0.3 * (rng.normal() + 1j * rng.normal())
+    head = A[:p, :p].copy()
+    b = rng.normal(size=8) + 1j * rng.normal(size=8)    # right-hand side longer than the head
+    x, st, _ = tq.ql_pert_toeplitz_solve(head, a, b, 40)
+    rhs = np.zeros(N, complex); rhs[:8] = b
+    ref = np.linalg.solve(A, rhs)
+    assert st == 0 and np.abs(x - ref[:40]).max() <= 1e-13 * np.abs(ref).max()
