@@ -166,6 +166,16 @@ int ila_chol_banded_factor_f64_dev(int u, int64_t batch, const double *d_p, cons
                                    const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
                                    int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int full_sweep, void *stream);
 
+/* Complex eltype of the adaptive QR solve (e.g. a real operator minus a complex shift: the resolvent (A - λI) \ b by QR).
+ * p, q, shift, head, b and x are complex; r (the per-diagonal denominators) is real; everything else as in
+ * ila_qr_banded_solve_f64 (no factor export).  Same reference path with LinearAlgebra.reflector!/reflectorApply! in their
+ * complex form; complex products are the four-multiply form and quotients Smith's algorithm, unfused, so the result equals
+ * the C oracle (oracle/ila_oracle_c64.c) bit for bit.  Supported (l,u): (1,1),(1,2),(2,1),(2,2),(3,1),(1,3),(3,3). */
+int ila_qr_banded_solve_c64(int l, int u, int64_t batch, const ila_c64 *p, const ila_c64 *q, const double *r,
+                            const ila_c64 *shift, int hp, const ila_c64 *head, int nb, const ila_c64 *b, double tol,
+                            int colgrowth, int64_t ncap, const int64_t *ncap_per, ila_c64 *x, int64_t xcap, int64_t *xoff,
+                            int64_t *ncols, int64_t *nconv, int32_t *status, int ngpus);
+
 /* ---- K7: solve with the Toeplitz QL,  x[i, 0:nout] = (ql(A - lambda[i]*I) \ b)[1:nout] -------------------------------
  * Pure Toeplitz A (u == 1) as in K3; b has nb <= 16 leading entries, zero beyond.  Replaces
  * ldiv!(F, b) = ldiv!(F.L, lmul!(F.Q', b)) (src/infql.jl:266-267): UpperHessenbergQ apply for n = nb..1

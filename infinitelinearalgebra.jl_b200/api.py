@@ -357,10 +357,14 @@ class AdaptiveQR:
     def solve(self, b, tolerance=_b.FLOATMIN, ncap=None):
         p, q, r, head = self.A.generators()
         l, u = self.A.bandwidths
-        bb = np.atleast_1d(np.asarray(b.head if isinstance(b, Vcat) else b, dtype=float))
+        bb = np.atleast_1d(np.asarray(b.head if isinstance(b, Vcat) else b))
         ncap = int(ncap) if ncap else 400_000
-        out = _b.qr_banded_solve(l, u, p[None], q[None], r[None], shift=[self.A.shift] if self.A.shift else None,
-                                 head=head, b=bb[None], tol=tolerance, ncap=ncap)
+        cplx = any(np.iscomplexobj(np.asarray(v)) for v in (p, q, bb, self.A.shift) + (() if head is None else (head,)))
+        solver = _b.qr_banded_solve_c64 if cplx else _b.qr_banded_solve      # complex eltype (e.g. A - λI, λ complex)
+        if not cplx:
+            bb = bb.astype(float)
+        out = solver(l, u, p[None], q[None], r[None], shift=[self.A.shift] if self.A.shift else None,
+                     head=head, b=bb[None], tol=tolerance, ncap=ncap)
         _raise_status(out["status"][0], "qr(A) \\ b")
         return out["x"][0]
 

@@ -266,6 +266,43 @@ def qr_banded_solve(l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=FLO
     return out
 
 
+def qr_banded_solve_c64(l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=FLOATMIN, colgrowth=1000,
+                        ncap=200_000, ncap_per=None, batch=None, ngpus=1, xcap=None):
+    """Complex-eltype `A_i \\ b_i` by adaptive banded QR (same reference path as `qr_banded_solve`; p, q, shift, head, b
+    complex, r real): e.g. `(J - λ_i I) \\ b` for complex shifts.  Returns dict(x, xflat, xoff, ncols, nconv, status)."""
+    nd = l + u + 1
+    if batch is None:
+        batch = int(np.asarray(p).reshape(-1, nd).shape[0])
+    cz = np.complex128
+    p = np.ascontiguousarray(np.broadcast_to(np.asarray(p, dtype=cz), (batch, nd)))
+    q = np.ascontiguousarray(np.broadcast_to(np.asarray(q, dtype=cz), (batch, nd)))
+    r = None if r is None else np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64), (batch, nd)))
+    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=cz), (batch,)))
+    hp = 0
+    if head is not None:
+        head = np.ascontiguousarray(np.asarray(head, dtype=cz))
+        assert head.shape[0] == nd
+        hp = head.shape[1]
+    b = np.asarray(b, dtype=cz)
+    if b.ndim == 1:
+        b = np.broadcast_to(b, (batch, b.shape[0]))
+    b = np.ascontiguousarray(b)
+    nb = b.shape[1]
+    caps = None if ncap_per is None else np.ascontiguousarray(np.asarray(ncap_per, dtype=np.int64))
+    if xcap is None:
+        xcap = int(caps.sum()) if caps is not None else int(batch) * int(ncap)
+    x = np.empty(xcap, dtype=cz)
+    xoff = np.zeros(batch + 1, dtype=np.int64)
+    ncols = np.zeros(batch, dtype=np.int64)
+    nconv = np.zeros(batch, dtype=np.int64)
+    status = np.zeros(batch, dtype=np.int32)
+    check(lib().ila_qr_banded_solve_c64(l, u, batch, ptr(p), ptr(q), ptr(r), ptr(shift), hp, ptr(head), nb, ptr(b),
+                                        float(tol), int(colgrowth), int(ncap), ptr(caps), ptr(x), xcap, ptr(xoff),
+                                        ptr(ncols), ptr(nconv), ptr(status), ngpus))
+    return dict(xflat=x[:xoff[batch]], xoff=xoff, ncols=ncols, nconv=nconv, status=status,
+                x=[x[xoff[i]:xoff[i + 1]] for i in range(batch)])
+
+
 def chol_banded_solve(u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=FLOATMIN, colgrowth=1000, ncap=20_000,
                       ncap_per=None, batch=None, want_factors=False, ngpus=1, xcap=None):
     """Batched `cholesky(S_i) \\ b_i` by adaptive banded Cholesky (reference src/infcholesky.jl:42-59,94-140).

@@ -62,6 +62,26 @@ int launch_qr_export(int l, int u, int has_refl, int64_t batch, const int64_t *d
                      const int64_t *d_nswept, const int64_t *d_xoff, double *d_factors, double *d_tau, double *d_qtb,
                      cudaStream_t s);
 
+// from qr_banded_c64.cu
+struct QrC64FwdArgs {
+    int64_t batch;
+    const cplx *p, *q;
+    const double *r;
+    const cplx *shift, *head, *b;
+    int hp, nb, colgrowth;
+    double tol;
+    const int64_t *gbase;
+    const int64_t *ncap_per;
+    int64_t ncap;
+    double2 *work;
+    int64_t *ncols, *nconv, *nswept;
+    int32_t *status;
+};
+int qr_c64_record_chunks(int l, int u);
+int launch_qr_forward_c64(int l, int u, const QrC64FwdArgs &a, cudaStream_t s);
+int launch_qr_backsolve_c64(int l, int u, int64_t batch, const int64_t *gbase, const double2 *work, const int64_t *ncols,
+                            const int64_t *nswept, const int64_t *xoff, double2 *x, cudaStream_t s);
+
 // from chol_banded.cu
 struct CholFwdArgs {
     int64_t batch;
@@ -959,6 +979,122 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
 {
     return banded_solve_host(0, l, u, batch, p, q, r, shift, hp, head, nb, b, tol, colgrowth, ncap, ncap_per, x, xcap, xoff,
                              ncols, nconv, factors_opt, tau_opt, qtb_opt, status, ngpus);
+}
+
+// Complex eltype: p, q, shift, head, b complex; r real.  Contiguous shards; x ragged instance-major (xoff), complex.
+int ila_qr_banded_solve_c64(int l, int u, int64_t batch, const ila_c64 *p, const ila_c64 *q, const double *r,
+                            const ila_c64 *shift, int hp, const ila_c64 *head, int nb, const ila_c64 *b, double tol,
+                            int colgrowth, int64_t ncap, const int64_t *ncap_per, ila_c64 *x, int64_t xcap, int64_t *xoff,
+                            int64_t *ncols, int64_t *nconv, int32_t *status, int ngpus)
+{
+    if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0 || !p || !q || !b || !xoff || !ncols || !nconv || !status || (hp > 0 && !head))
+        return set_error(ILA_ERR_ARG, "qr_banded_solve_c64: bad arguments");
+    if (l < 1) return set_error(ILA_ERR_UNSUPPORTED, "qr_banded_solve_c64: l == 0 (triangular operator, Q = I) is not on the accelerated path");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (batch == 0) { xoff[0] = 0; return 0; }
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int nd = l + u + 1, REC = qr_c64_record_chunks(l, u);
+    const int64_t per = (batch + G - 1) / G;
+    struct Shard {
+        int64_t lo = 0, cnt = 0, total = 0;
+        std::vector<int64_t> gbase, xoff;
+        cplx *d_p, *d_q, *d_shift, *d_head, *d_b, *d_x;
+        double *d_r;
+        double2 *d_work;
+        int64_t *d_gbase, *d_caps, *d_ncols, *d_nconv, *d_nswept, *d_xoff;
+        int32_t *d_status;
+    };
+    std::vector<Shard> sh(G);
+    for (int d = 0; d < G; d++) {
+        Shard &S = sh[d];
+        S.lo = d * per;
+        S.cnt = (S.lo + per <= batch) ? per : batch - S.lo;
+        if (S.cnt <= 0) { S.cnt = 0; continue; }
+        const int64_t ng = (S.cnt + 31) / 32;
+        S.gbase.assign(ng + 1, 0);
+        for (int64_t g = 0; g < ng; g++) {
+            int64_t mx = 0;
+            for (int64_t j = g * 32; j < S.cnt && j < (g + 1) * 32; j++) {
+                const int64_t c = ncap_per ? ncap_per[S.lo + j] : ncap;
+                if (c < 1) return set_error(ILA_ERR_ARG, "qr_banded_solve_c64: non-positive capacity");
+                mx = c > mx ? c : mx;
+            }
+            S.gbase[g + 1] = S.gbase[g] + mx;
+        }
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        if ((rc = dev_buf_t(pd, 4, (size_t)S.cnt * nd, &S.d_p))) return rc;
+        if ((rc = dev_buf_t(pd, 5, (size_t)S.cnt * nd, &S.d_q))) return rc;
+        S.d_r = nullptr; S.d_shift = nullptr; S.d_head = nullptr; S.d_caps = nullptr;
+        if (r && (rc = dev_buf_t(pd, 6, (size_t)S.cnt * nd, &S.d_r))) return rc;
+        if (shift && (rc = dev_buf_t(pd, 7, (size_t)S.cnt, &S.d_shift))) return rc;
+        if (hp > 0 && (rc = dev_buf_t(pd, 8, (size_t)nd * hp, &S.d_head))) return rc;
+        if ((rc = dev_buf_t(pd, 9, (size_t)S.cnt * nb, &S.d_b))) return rc;
+        if ((rc = dev_buf_t(pd, 10, S.gbase.size(), &S.d_gbase))) return rc;
+        if (ncap_per && (rc = dev_buf_t(pd, 21, (size_t)S.cnt, &S.d_caps))) return rc;
+        if ((rc = dev_buf_t(pd, 11, (size_t)S.cnt, &S.d_ncols))) return rc;
+        if ((rc = dev_buf_t(pd, 12, (size_t)S.cnt, &S.d_nconv))) return rc;
+        if ((rc = dev_buf_t(pd, 13, (size_t)S.cnt, &S.d_nswept))) return rc;
+        if ((rc = dev_buf_t(pd, 14, (size_t)S.cnt + 1, &S.d_xoff))) return rc;
+        if ((rc = dev_buf_t(pd, 15, (size_t)S.cnt, &S.d_status))) return rc;
+        if ((rc = dev_buf_t(pd, 16, (size_t)S.gbase[ng] * REC * 32, &S.d_work))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_p, p + S.lo * nd, sizeof(cplx) * S.cnt * nd, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_q, q + S.lo * nd, sizeof(cplx) * S.cnt * nd, cudaMemcpyHostToDevice, s));
+        if (r) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_r, r + S.lo * nd, sizeof(double) * S.cnt * nd, cudaMemcpyHostToDevice, s));
+        if (shift) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_shift, shift + S.lo, sizeof(cplx) * S.cnt, cudaMemcpyHostToDevice, s));
+        if (hp > 0) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_head, head, sizeof(cplx) * nd * hp, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_b, b + S.lo * nb, sizeof(cplx) * S.cnt * nb, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_gbase, S.gbase.data(), sizeof(int64_t) * S.gbase.size(), cudaMemcpyHostToDevice, s));
+        if (ncap_per) ILA_CUDA_CHECK(cudaMemcpyAsync(S.d_caps, ncap_per + S.lo, sizeof(int64_t) * S.cnt, cudaMemcpyHostToDevice, s));
+        QrC64FwdArgs a{S.cnt, S.d_p, S.d_q, S.d_r, S.d_shift, S.d_head, S.d_b, hp, nb, colgrowth, tol, S.d_gbase, S.d_caps, ncap,
+                       S.d_work, S.d_ncols, S.d_nconv, S.d_nswept, S.d_status};
+        if ((rc = launch_qr_forward_c64(l, u, a, s))) return rc;
+        if ((rc = launch_qr_scan(S.d_ncols, S.cnt, S.d_xoff, s))) return rc;
+        S.xoff.resize(S.cnt + 1);
+        ILA_CUDA_CHECK(cudaMemcpyAsync(ncols + S.lo, S.d_ncols, sizeof(int64_t) * S.cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(nconv + S.lo, S.d_nconv, sizeof(int64_t) * S.cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + S.lo, S.d_status, sizeof(int32_t) * S.cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(S.xoff.data(), S.d_xoff, sizeof(int64_t) * (S.cnt + 1), cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        if (sh[d].cnt == 0) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(phys(d, G)));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[phys(d, G)].stream));
+    }
+    int64_t acc = 0;
+    for (int d = 0; d < G; d++) {
+        Shard &S = sh[d];
+        for (int64_t j = 0; j < S.cnt; j++) xoff[S.lo + j] = acc + S.xoff[j];
+        S.total = S.cnt ? S.xoff[S.cnt] : 0;
+        acc += S.total;
+    }
+    xoff[batch] = acc;
+    if (acc > xcap || !x) {
+        ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+        return set_error(ILA_ERR_CAPACITY, "qr_banded_solve_c64: x capacity too small; xoff[batch] holds the required number of scalars");
+    }
+    for (int d = 0; d < G; d++) {
+        Shard &S = sh[d];
+        if (S.cnt == 0) continue;
+        const int pd = phys(d, G);
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        cudaStream_t s = g_dev[pd].stream;
+        if ((rc = dev_buf_t(pd, 17, (size_t)S.total, &S.d_x))) return rc;
+        if ((rc = launch_qr_backsolve_c64(l, u, S.cnt, S.d_gbase, S.d_work, S.d_ncols, S.d_nswept, S.d_xoff, (double2 *)S.d_x, s))) return rc;
+        if (S.total > 0)
+            ILA_CUDA_CHECK(cudaMemcpyAsync(x + xoff[S.lo], S.d_x, sizeof(cplx) * S.total, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        if (sh[d].cnt == 0) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(phys(d, G)));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[phys(d, G)].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
 }
 
 int ila_chol_banded_solve_f64(int u, int64_t batch, const double *p, const double *q, const double *r,

@@ -23,7 +23,7 @@ _sp = C.POINTER(C.c_int32)
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the recipe in oracle/Makefile."""
-    src = [os.path.join(_HERE, f) for f in ("ila_oracle.c", "ila_oracle_impl.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ila_oracle.c", "ila_oracle_impl.h", "ila_oracle_c64.c", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -92,6 +92,44 @@ def qr_banded_solve(l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=np.
         C.c_int64(ncap), C.c_int64(ldx), _ptr(x, _dp), _ptr(ncols, _ip), _ptr(nconv, _ip), _ptr(fac, _dp),
         _ptr(tau, _dp), _ptr(qtb, _dp), _ptr(status, _sp), C.c_int(nthreads))
     return out
+
+
+def qr_banded_solve_c64(l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=np.finfo(np.float64).tiny,
+                        colgrowth=1000, ncap=200_000, batch=None, nthreads=0):
+    """Complex-eltype adaptive QR solve (oracle/ila_oracle_c64.c): p, q, shift, head, b complex; r real.
+    Returns dict(x (batch x ncap complex, zero padded), ncols, nconv, status)."""
+    nd = l + u + 1
+    if batch is None:
+        batch = int(np.asarray(p).reshape(-1, nd).shape[0])
+    cz = np.complex128
+    p = np.ascontiguousarray(np.broadcast_to(np.asarray(p, dtype=cz), (batch, nd)))
+    q = np.ascontiguousarray(np.broadcast_to(np.asarray(q, dtype=cz), (batch, nd)))
+    r = None if r is None else np.ascontiguousarray(np.broadcast_to(np.asarray(r, dtype=np.float64), (batch, nd)))
+    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=cz), (batch,)))
+    hp = 0
+    if head is not None:
+        head = np.ascontiguousarray(np.asarray(head, dtype=cz))
+        assert head.shape[0] == nd
+        hp = head.shape[1]
+    b = np.asarray(b, dtype=cz)
+    if b.ndim == 1:
+        b = np.broadcast_to(b, (batch, b.shape[0]))
+    b = np.ascontiguousarray(b)
+    nb = b.shape[1]
+    x = np.zeros((batch, ncap), dtype=cz)
+    ncols = np.zeros(batch, dtype=np.int64)
+    nconv = np.zeros(batch, dtype=np.int64)
+    status = np.zeros(batch, dtype=np.int32)
+    vp = C.c_void_p
+    pv = lambda a: None if a is None else vp(a.ctypes.data)
+    L = lib()
+    L.ila_oracle_qr_banded_solve_c64.restype = C.c_int
+    rc = L.ila_oracle_qr_banded_solve_c64(
+        C.c_int(l), C.c_int(u), C.c_int64(batch), pv(p), pv(q), pv(r), pv(shift), C.c_int(hp), pv(head), C.c_int(nb), pv(b),
+        C.c_double(tol), C.c_int(colgrowth), C.c_int64(ncap), pv(x), C.c_int64(ncap), _ptr(ncols, _ip), _ptr(nconv, _ip),
+        _ptr(status, _sp), C.c_int(nthreads))
+    assert rc == 0
+    return dict(x=x, ncols=ncols, nconv=nconv, status=status)
 
 
 def chol_banded_solve(u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=np.finfo(np.float64).tiny,
