@@ -227,6 +227,18 @@ int ila_ql_blocktri_l11_c64_dev(int n, const ila_c64 *c, const ila_c64 *a, const
                                 int64_t batch, double atol, int maxit, ila_c64 *d_L11, int32_t *d_iters, int32_t *d_status,
                                 void *stream);
 
+/* ---- K8: adaptive reverse Cholesky  A = L'L  of ∞ symmetric tridiagonal operators ------------------
+ * Replaces reversecholesky(::SymTridiagonal) -> LazySymTridiagonalReverseCholeskyFactors
+ * (src/banded/infreversecholeskytridiagonal.jl:66-141): finite reverse Cholesky of the N x N section (:118-129), convergence
+ * measure ξ (:81-110, tolerance eps), N doubled from 4n until ξ <= eps or N > 2^21 - 1 (status 3; the reference warns).
+ * Operator i: diagonal value(k) = c0 + (p + q k)/(r + s k) from ga[i*5 .. i*5+4] = (c0,p,q,r,s), minus shift[i];
+ * off-diagonal the same from gb; the first hp entries of both come from a_head / b_head when hp > 0 (shared).
+ * Output: la[i*n + k] = L[k+1,k+1], lb[i*n + k] = L[k+2,k+1] for k < n (0-based), N_used[i] the section size at which
+ * the test fired.  status 4 = non-positive pivot (DomainError upstream), rows NaN. */
+int ila_revchol_tridiag_f64(int64_t batch, const double *ga, const double *gb, const double *shift, int hp,
+                            const double *a_head, const double *b_head, int64_t n, double *la, double *lb, int64_t *N_used,
+                            int32_t *status, int ngpus);
+
 #ifdef __cplusplus
 }
 #endif

@@ -403,3 +403,79 @@ class AdaptiveCholesky:
 def cholesky(S):
     """cholesky(S) for a symmetric positive definite ∞ banded operator → adaptive Cholesky (src/infcholesky.jl:71-75)."""
     return AdaptiveCholesky(S)
+
+
+# ---- reversecholesky (symmetric tridiagonal) ------------------------------------------------------------------
+
+class Rational:
+    """Entry k (k = 0, 1, ...) = c0 + (p + q*k)/(r + s*k) — e.g. `1 ./ (2:∞)` = Rational(0, 1, 0, 2, 1)."""
+
+    def __init__(self, c0=0.0, p=0.0, q=0.0, r=1.0, s=0.0):
+        self.c = (c0, p, q, r, s)
+
+
+def _gen5(v):
+    if isinstance(v, Rational):
+        return list(v.c)
+    if isinstance(v, Affine):
+        return [0.0, v.p, v.q, v.r, 0.0] if (v.q != 0.0 or v.r != 1.0) else [v.p, 0.0, 0.0, 1.0, 0.0]
+    raise TypeError("SymTridiagonal entries must be Fill / Affine / Rational, optionally behind a Vcat head")
+
+
+class SymTridiagonal:
+    """SymTridiagonal(dv, ev) with lazy ∞ diagonals (test/test_infreversecholesky.jl); `A + c*I` / `A - c*I` shift it."""
+
+    def __init__(self, dv, ev, shift=0.0):
+        self.dv, self.ev, self.shift = dv, ev, shift
+
+    def __sub__(self, other):
+        return SymTridiagonal(self.dv, self.ev, self.shift + other.lam)
+
+    def __add__(self, other):
+        return SymTridiagonal(self.dv, self.ev, self.shift - other.lam)
+
+    __radd__ = __add__
+
+
+class ReverseCholesky:
+    """reversecholesky(A): A = U*U' = L'*L with L lower bidiagonal (src/banded/infreversecholeskytridiagonal.jl:66-74).
+    `.L[i, j]` / `.U[i, j]` (1-based) expand the factor adaptively like the reference's getindex (:53-64)."""
+
+    def __init__(self, A):
+        self.A = A
+        self._n = 0
+        self._la = self._lb = None
+        self.L = _OneBased(self._L)
+        self.U = _OneBased(lambda i, j: self._L(j, i))
+        self._expand(16)
+
+    def _expand(self, n):
+        if n <= self._n:
+            return
+        dv, ev = self.A.dv, self.A.ev
+        ah = list(dv.head) if isinstance(dv, Vcat) else []
+        bh = list(ev.head) if isinstance(ev, Vcat) else []
+        dt, et = (dv.tail if isinstance(dv, Vcat) else dv), (ev.tail if isinstance(ev, Vcat) else ev)
+        ga, gb = _gen5(dt), _gen5(et)
+        hp = max(len(ah), len(bh))
+        val = lambda g, k: g[0] + (g[1] + g[2] * k) / (g[3] + g[4] * k)
+        # the lazy tails count positions from the end of their own head (Vcat), the kernel from 0: shift the generators
+        def shifted(g, off):
+            c0, p, q, r, s = g
+            return [c0, p - q * off, q, r - s * off, s]
+        a_head = [ah[k] if k < len(ah) else val(shifted(ga, len(ah)), k) for k in range(hp)] if hp else None
+        b_head = [bh[k] if k < len(bh) else val(shifted(gb, len(bh)), k) for k in range(hp)] if hp else None
+        out = _b.revchol_tridiag(shifted(ga, len(ah)), shifted(gb, len(bh)), int(n), shift=[self.A.shift] if self.A.shift else None,
+                                 a_head=a_head, b_head=b_head)
+        _raise_status(out["status"][0], "reversecholesky(A)")
+        self._la, self._lb, self._n = out["la"][0], out["lb"][0], int(n)
+
+    def _L(self, i, j):
+        if j > i or i - j > 1:
+            return 0.0
+        self._expand(max(i, j) if max(i, j) <= self._n else 2 * max(i, j))
+        return self._la[i - 1] if i == j else self._lb[j - 1]
+
+
+def reversecholesky(A: SymTridiagonal):
+    return ReverseCholesky(A)

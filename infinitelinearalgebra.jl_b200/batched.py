@@ -340,6 +340,32 @@ def chol_banded_solve(u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=FLOA
     return out
 
 
+def revchol_tridiag(ga, gb, n, shift=None, a_head=None, b_head=None, batch=None, ngpus=1):
+    """Adaptive reverse Cholesky A = L'L of ∞ symmetric tridiagonal operators, batched
+    (reference src/banded/infreversecholeskytridiagonal.jl:66-141; test/test_infreversecholesky.jl).
+    ga, gb: (batch x) 5 generator coefficients (c0, p, q, r, s) of the diagonal / off-diagonal:
+    value(k) = c0 + (p + q k)/(r + s k); `shift` is subtracted from the diagonal; optional shared explicit heads.
+    Returns dict(la, lb (batch x n: diagonal and sub-diagonal of L), N, status)."""
+    ga = np.asarray(ga, dtype=np.float64).reshape(-1, 5)
+    gb = np.asarray(gb, dtype=np.float64).reshape(-1, 5)
+    if batch is None:
+        batch = max(ga.shape[0], gb.shape[0], 1 if shift is None else np.asarray(shift).size)
+    ga = np.ascontiguousarray(np.broadcast_to(ga, (batch, 5)))
+    gb = np.ascontiguousarray(np.broadcast_to(gb, (batch, 5)))
+    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=np.float64), (batch,)))
+    hp = 0
+    if a_head is not None:
+        a_head = np.ascontiguousarray(np.asarray(a_head, dtype=np.float64))
+        b_head = np.ascontiguousarray(np.asarray(b_head, dtype=np.float64))
+        assert a_head.shape == b_head.shape
+        hp = a_head.shape[0]
+    la = np.empty((batch, int(n))); lb = np.empty((batch, int(n)))
+    N = np.zeros(batch, dtype=np.int64); status = np.zeros(batch, dtype=np.int32)
+    check(lib().ila_revchol_tridiag_f64(batch, ptr(ga), ptr(gb), ptr(shift), hp, ptr(a_head), ptr(b_head), int(n), ptr(la),
+                                        ptr(lb), ptr(N), ptr(status), ngpus))
+    return dict(la=la, lb=lb, N=N, status=status)
+
+
 def pentadiagonal_operator(sigma, eps=1e-4):
     """BASELINE config C4: S_σ = pentadiag(diag 6+σ+ε·k, ±1: -4, ±2: 1), upper bands in data-row order (+2, +1, 0)."""
     sigma = np.atleast_1d(np.asarray(sigma, dtype=np.float64))

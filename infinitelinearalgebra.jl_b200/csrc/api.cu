@@ -82,6 +82,19 @@ int launch_qr_forward_c64(int l, int u, const QrC64FwdArgs &a, cudaStream_t s);
 int launch_qr_backsolve_c64(int l, int u, int64_t batch, const int64_t *gbase, const double2 *work, const int64_t *ncols,
                             const int64_t *nswept, const int64_t *xoff, double2 *x, cudaStream_t s);
 
+// from revchol_tridiag.cu
+struct RevCholArgs {
+    int64_t batch, n;
+    const double *ga, *gb;
+    const double *shift;
+    int hp;
+    const double *a_head, *b_head;
+    double *la, *lb;
+    int64_t *N_used;
+    int32_t *status;
+};
+int launch_revchol_tridiag(const RevCholArgs &a, cudaStream_t s);
+
 // from chol_banded.cu
 struct CholFwdArgs {
     int64_t batch;
@@ -607,6 +620,65 @@ int ila_ql_perttoeplitz_solve_f64(int l, int u, int p, const double *head, const
                                   int branch_rank, int nb, const double *b, int64_t nout, double *x, int32_t *status, int ngpus)
 {
     return ql_pert_host(true, l, u, p, head, a, lambda, n, branch_rank, nullptr, nullptr, status, ngpus, nb, b, nout, x);
+}
+
+// ================================ K8: adaptive reverse Cholesky (symmetric tridiagonal) =================
+
+int ila_revchol_tridiag_f64(int64_t batch, const double *ga, const double *gb, const double *shift, int hp,
+                            const double *a_head, const double *b_head, int64_t n, double *la, double *lb, int64_t *N_used,
+                            int32_t *status, int ngpus)
+{
+    if (batch < 0 || n < 1 || hp < 0 || !ga || !gb || (hp > 0 && (!a_head || !b_head)) ||
+        (batch > 0 && (!la || !lb || !N_used || !status)))
+        return set_error(ILA_ERR_ARG, "revchol_tridiag: bad arguments");
+    if (n > (1 << 19)) return set_error(ILA_ERR_UNSUPPORTED, "revchol_tridiag: n must not exceed 2^19 (N starts at 4n, MAX_TRIDIAG_CHOL_N = 2^21 - 1)");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int64_t per = (batch + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= batch ? per : batch - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        double *d_ga, *d_gb, *d_sh = nullptr, *d_ah = nullptr, *d_bh = nullptr, *d_la, *d_lb;
+        int64_t *d_N;
+        int32_t *d_st;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt * 5, &d_ga))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt * 5, &d_gb))) return rc;
+        if (shift && (rc = dev_buf_t(pd, 2, (size_t)cnt, &d_sh))) return rc;
+        if (hp > 0 && (rc = dev_buf_t(pd, 3, (size_t)hp, &d_ah))) return rc;
+        if (hp > 0 && (rc = dev_buf_t(pd, 4, (size_t)hp, &d_bh))) return rc;
+        if ((rc = dev_buf_t(pd, 5, (size_t)cnt * n, &d_la))) return rc;
+        if ((rc = dev_buf_t(pd, 6, (size_t)cnt * n, &d_lb))) return rc;
+        if ((rc = dev_buf_t(pd, 7, (size_t)cnt, &d_N))) return rc;
+        if ((rc = dev_buf_t(pd, 8, (size_t)cnt, &d_st))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_ga, ga + lo * 5, sizeof(double) * cnt * 5, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_gb, gb + lo * 5, sizeof(double) * cnt * 5, cudaMemcpyHostToDevice, s));
+        if (shift) ILA_CUDA_CHECK(cudaMemcpyAsync(d_sh, shift + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+        if (hp > 0) {
+            ILA_CUDA_CHECK(cudaMemcpyAsync(d_ah, a_head, sizeof(double) * hp, cudaMemcpyHostToDevice, s));
+            ILA_CUDA_CHECK(cudaMemcpyAsync(d_bh, b_head, sizeof(double) * hp, cudaMemcpyHostToDevice, s));
+        }
+        RevCholArgs a{cnt, n, d_ga, d_gb, d_sh, hp, d_ah, d_bh, d_la, d_lb, d_N, d_st};
+        if ((rc = launch_revchol_tridiag(a, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(la + lo * n, d_la, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(lb + lo * n, d_lb, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(N_used + lo, d_N, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
 }
 
 // ================================ K6: block-tridiagonal Toeplitz-tail QL ================================

@@ -23,7 +23,7 @@ _sp = C.POINTER(C.c_int32)
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the recipe in oracle/Makefile."""
-    src = [os.path.join(_HERE, f) for f in ("ila_oracle.c", "ila_oracle_impl.h", "ila_oracle_c64.c", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ila_oracle.c", "ila_oracle_impl.h", "ila_oracle_c64.c", "ila_oracle_revchol.c", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -130,6 +130,32 @@ def qr_banded_solve_c64(l, u, p, q, r=None, shift=None, head=None, b=(1.0,), tol
         _ptr(status, _sp), C.c_int(nthreads))
     assert rc == 0
     return dict(x=x, ncols=ncols, nconv=nconv, status=status)
+
+
+def revchol_tridiag(ga, gb, n, shift=None, a_head=None, b_head=None, batch=None, nthreads=0):
+    """Adaptive reverse Cholesky A = L'L of ∞ symmetric tridiagonal operators (oracle/ila_oracle_revchol.c).
+    ga, gb: batch x 5 generator coefficients (c0, p, q, r, s): value(k) = c0 + (p + q k)/(r + s k).
+    Returns dict(la (batch x n diagonal of L), lb (batch x n sub-diagonal of L), N, status)."""
+    ga = np.asarray(ga, dtype=np.float64).reshape(-1, 5)
+    gb = np.asarray(gb, dtype=np.float64).reshape(-1, 5)
+    if batch is None:
+        batch = max(ga.shape[0], gb.shape[0], 1 if shift is None else np.asarray(shift).size)
+    ga = np.ascontiguousarray(np.broadcast_to(ga, (batch, 5)))
+    gb = np.ascontiguousarray(np.broadcast_to(gb, (batch, 5)))
+    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=np.float64), (batch,)))
+    hp = 0
+    if a_head is not None:
+        a_head = np.ascontiguousarray(np.asarray(a_head, dtype=np.float64))
+        b_head = np.ascontiguousarray(np.asarray(b_head, dtype=np.float64))
+        assert a_head.shape == b_head.shape
+        hp = a_head.shape[0]
+    la = np.zeros((batch, n)); lb = np.zeros((batch, n))
+    N = np.zeros(batch, dtype=np.int64); status = np.zeros(batch, dtype=np.int32)
+    L = lib()
+    L.ila_oracle_revchol_tridiag_f64(C.c_int64(batch), _ptr(ga, _dp), _ptr(gb, _dp), _ptr(shift, _dp), C.c_int(hp),
+                                     _ptr(a_head, _dp), _ptr(b_head, _dp), C.c_int64(n), _ptr(la, _dp), _ptr(lb, _dp),
+                                     _ptr(N, _ip), _ptr(status, _sp), C.c_int(nthreads))
+    return dict(la=la, lb=lb, N=N, status=status)
 
 
 def chol_banded_solve(u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=np.finfo(np.float64).tiny,
