@@ -401,6 +401,22 @@ def run_ours(args, rank, local_rank, world):
             _lib.check(lib.ila_ql_toeplitz_solve_c64_dev(3, 1, _lib.ptr(BULLHEAD_COLUMN), _lib.ptr(d_lam), n, 1, 1, _lib.ptr(b7), 1,
                                                          _lib.ptr(d_w7), _lib.ptr(d_x7), _lib.ptr(d_st7), ctypes.c_void_p(stream)))
         ms7 = timed(step_k7, k4, 2) / k4
+        # K8 and the complex-eltype QR only have host entry points: wall time of the C-ABI call (copies included)
+        def wall(fn, reps=3):
+            fn()
+            best = 1e30
+            for _ in range(reps):
+                t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0)
+            return best * 1e3
+        sh8 = np.linspace(0.0, 0.99, 4096)
+        ms8 = wall(lambda: ila_b200.revchol_tridiag([3, 0, 0, 1, 0], [1, 0, 0, 1, 0], 256, shift=sh8))
+        lam9 = np.linspace(-2, 2, 512) + 0.2j
+        p9 = np.tile(np.array([0.5, 0.0, 0.5]), (512, 1)); q9 = np.zeros((512, 3))
+        res9 = {}
+        def run9():
+            res9["o"] = ila_b200.qr_banded_solve_c64(1, 1, p9, q9, None, shift=lam9, b=[1.0], ncap=20000)
+        ms9 = wall(run9)
+        cols9 = float(res9["o"]["ncols"].sum())
         line["other_configs"] = [
             {"metric": "adaptive_cholesky_columns_per_s", "value": cols4 * world / (ms4 * 1e-3), "unit": "columns/s",
              "ms_per_step": ms4, "config": {"workload": "C4 pentadiagonal adaptive Cholesky, 2048 shifts (per GPU)",
@@ -422,6 +438,15 @@ def run_ours(args, rank, local_rank, world):
                           "note": "16 B λ in, 16 B x + 16 B L11 + 4 B status out; one fused launch (K3 solves from registers); "
                                   "issue bound like K3"},
              "gpu_launches_per_step": 1},
+            {"metric": "revchol_tridiag_operators_per_s", "value": 4096 * world / (ms8 * 1e-3), "unit": "operators/s",
+             "ms_per_step": ms8, "config": {"workload": "K8 adaptive reverse Cholesky, SymTridiagonal(3 - s, 1), 4096 shifts s in "
+                                                        "[0, 0.99], leading 256 x 256 block (per GPU)",
+                                            "timing": "host C-ABI call, wall clock, copies included"},
+             "gpu_launches_per_step": 1},
+            {"metric": "adaptive_qr_c64_columns_per_s", "value": cols9 * world / (ms9 * 1e-3), "unit": "columns/s",
+             "ms_per_step": ms9, "config": {"workload": "complex-eltype adaptive QR, (J - λI) \\ e1, 512 shifts λ = x + 0.2i (per GPU)",
+                                            "columns": cols9, "timing": "host C-ABI call, wall clock, copies included"},
+             "gpu_launches_per_step": 3},
         ]
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
