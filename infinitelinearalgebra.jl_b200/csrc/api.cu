@@ -49,6 +49,8 @@ struct QrBwdArgs {
     double *xi;
     const int64_t *ncols, *nswept;
     const int32_t *status;
+    double *xdirect;
+    const int64_t *xoff;
 };
 int qr_record_doubles(int l, int u, bool refl);
 void qr_set_arith_mode(int mode);
@@ -808,9 +810,13 @@ int ila_ql_set_shifts_per_thread(int spt)
 
 // ================================ K1+K2: adaptive banded QR solve =======================================
 
+static int g_qr_direct_x = -1;   // -1 auto, 0 always interleaved + compaction, 1 always direct
+
 int ila_qr_set_arith_mode(int mode)
 {
-    if (mode != 0 && mode != 1) return set_error(ILA_ERR_ARG, "qr arith mode must be 0 (branch-free exact) or 1 (IEEE intrinsics)");
+    // 0 / 1: arithmetic of the sweeps; 2 / 3 / 4 (validation knobs): solution output auto / always compacted / always direct
+    if (mode >= 2 && mode <= 4) { g_qr_direct_x = mode == 2 ? -1 : (mode == 3 ? 0 : 1); return 0; }
+    if (mode != 0 && mode != 1) return set_error(ILA_ERR_ARG, "qr arith mode must be 0 (branch-free exact), 1 (IEEE intrinsics) or 2-4 (output path)");
     qr_set_arith_mode(mode);
     return 0;
 }
@@ -857,9 +863,17 @@ int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *
                                     const int32_t *d_status, double *d_x, int64_t xcap, int want_reflectors, void *stream)
 {
     if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
-    QrBwdArgs a{batch, d_gbase, (const double2 *)d_work, d_xi, d_ncols, d_nswept, d_status};
+    // few groups (latency-bound regime: at most two solver warps per SM): the solver writes x straight into the ragged
+    // output and the compaction pass disappears; many groups (HBM-bound regime): coalesced interleaved stream + compaction
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const bool direct = g_qr_direct_x >= 0 ? g_qr_direct_x != 0 : (batch + 31) / 32 <= 2 * (int64_t)sms;
+    QrBwdArgs a{batch, d_gbase, (const double2 *)d_work, d_xi, d_ncols, d_nswept, d_status, direct ? d_x : nullptr, d_xoff};
     int rc = launch_qr_backsolve(l, u, a, want_reflectors != 0, (cudaStream_t)stream);
-    if (rc) return rc;
+    if (rc || direct) return rc;
     return launch_qr_compact(batch, d_gbase, d_xi, d_ncols, d_nswept, d_xoff, d_x, xcap, (cudaStream_t)stream);
 }
 

@@ -115,3 +115,21 @@ def test_c2_full_size_properties(ila):
         assert x[1] == pytest.approx(jv(1, z), rel=1e-12)
         ref = jv(np.arange(len(x)), z)
         assert np.max(np.abs(x - ref)) <= 4 * z * np.finfo(float).eps * np.max(np.abs(ref)) + 1e-13
+
+
+def test_output_paths_identical(ila):
+    """The back-substitution delivers x either straight into the ragged output (small batches) or through the interleaved
+    stream + compaction (large batches): both must give the same bits, including the zero region up to datasize."""
+    from ila_b200 import _lib
+    from scipy.special import jv
+    z = np.linspace(50.0, 3000.0, 77)
+    p, q, r = ila.bessel_operator(z)
+    outs = []
+    for mode in (3, 4, 2):
+        _lib.check(_lib.lib().ila_qr_set_arith_mode(mode))
+        o = ila.qr_banded_solve(1, 1, p, q, r, b=jv(1, z)[:, None], ncap_per=ila.bessel_ncap(z))
+        outs.append((o["xflat"].copy(), o["ncols"].copy(), o["status"].copy()))
+    _lib.check(_lib.lib().ila_qr_set_arith_mode(2))
+    for k in (1, 2):
+        assert np.array_equal(outs[0][1], outs[k][1]) and np.array_equal(outs[0][2], outs[k][2])
+        assert np.array_equal(outs[0][0].view(np.int64), outs[k][0].view(np.int64))
