@@ -42,6 +42,7 @@ const char *ila_last_error(void);      /* text of the last error on the calling 
 int ila_set_device(int dev);           /* select the CUDA device single-GPU calls (ngpus == 1, `_dev`) run on */
 int ila_get_device(void);
 int64_t ila_kernel_launches(void);     /* number of kernels this library launched so far (process-wide) */
+int ila_release(void);                 /* frees the per-device buffer pools / streams the host entry points keep (re-created on demand) */
 /* DFMA throughput probe: runs a register-resident FP64 FMA loop on the current device and returns the
  * achieved TFLOP/s (2 flop per FMA) — the FP64 roofline denominator (MEASURED_PEAKS.json has none). */
 int ila_fp64_peak_probe(double *tflops_out, double *ms_out);

@@ -1,0 +1,133 @@
+// ila_kernels.cuh — argument structures and launcher prototypes shared by the kernel files and api.cu (one definition
+// each: api.cu used to restate them).
+#pragma once
+#include "ila_common.cuh"
+
+namespace ila {
+
+// from ql_toeplitz.cu
+int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
+                       int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream);
+
+void tz_set_spt(int v);
+int launch_ql_toeplitz_solve(bool real_path, int l, int nb, const double *b_host, int64_t n, const double *d_tail,
+                             const int32_t *d_status, int64_t nout, double *d_x, cudaStream_t stream);
+int launch_ql_toeplitz_solve_fused(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
+                                   int64_t n, int nb, const double *b_host, int64_t nout, double *d_L11, double *d_x,
+                                   int32_t *d_status, cudaStream_t stream);
+int launch_ql_toeplitz_grid(int l, int u, const double *a_host, int branch_rank, const double *d_gx, int nx,
+                            const double *d_gy, int64_t ny, double *d_absout, cudaStream_t stream);
+int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
+                        int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
+                        cudaStream_t stream);
+int launch_ql_pert_head_ex(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,
+                           int64_t n, const double *d_tail, const int32_t *d_status, double *d_L11, double *d_head_factors,
+                           int nb, const double *b_host, int64_t nout, double *d_x, cudaStream_t stream);
+
+// from qr_banded.cu
+struct QrFwdArgs {
+    int64_t batch;
+    const double *p, *q, *r, *shift, *head, *b;
+    int hp, nb, colgrowth;
+    double tol;
+    const int64_t *gbase;
+    const int64_t *ncap_per;
+    int64_t ncap;
+    double2 *work;
+    int64_t *ncols, *nconv, *nswept;
+    int32_t *status;
+};
+struct QrBwdArgs {
+    int64_t batch;
+    const int64_t *gbase;
+    const double2 *work;
+    double *xi;
+    const int64_t *ncols, *nswept;
+    const int32_t *status;
+    double *xdirect;
+    const int64_t *xoff;
+};
+int qr_record_doubles(int l, int u, bool refl);
+void qr_set_arith_mode(int mode);
+int qr_get_arith_mode();
+int launch_qr_forward(int l, int u, const QrFwdArgs &a, bool refl, cudaStream_t s);
+int launch_qr_scan(const int64_t *d_ncols, int64_t batch, int64_t *d_xoff, cudaStream_t s);
+int launch_qr_backsolve(int l, int u, const QrBwdArgs &a, bool refl, cudaStream_t s);
+int launch_qr_compact(int64_t batch, const int64_t *d_gbase, const double *d_xi, const int64_t *d_ncols,
+                      const int64_t *d_nswept, const int64_t *d_xoff, double *d_x, int64_t xcap, cudaStream_t s);
+int launch_qr_export(int l, int u, int has_refl, int64_t batch, const int64_t *d_gbase, const double2 *d_work, const int64_t *d_ncols,
+                     const int64_t *d_nswept, const int64_t *d_xoff, double *d_factors, double *d_tau, double *d_qtb,
+                     cudaStream_t s);
+
+// from qr_banded_c64.cu
+struct QrC64FwdArgs {
+    int64_t batch;
+    const cplx *p, *q;
+    const double *r;
+    const cplx *shift, *head, *b;
+    int hp, nb, colgrowth;
+    double tol;
+    const int64_t *gbase;
+    const int64_t *ncap_per;
+    int64_t ncap;
+    double2 *work;
+    int64_t *ncols, *nconv, *nswept;
+    int32_t *status;
+};
+int qr_c64_record_chunks(int l, int u);
+int launch_qr_forward_c64(int l, int u, const QrC64FwdArgs &a, cudaStream_t s);
+int launch_qr_backsolve_c64(int l, int u, int64_t batch, const int64_t *gbase, const double2 *work, const int64_t *ncols,
+                            const int64_t *nswept, const int64_t *xoff, double2 *x, cudaStream_t s);
+
+// from revchol_tridiag.cu
+struct RevCholArgs {
+    int64_t batch, n;
+    const double *ga, *gb;
+    const double *shift;
+    int hp;
+    const double *a_head, *b_head;
+    double *la, *lb;
+    int64_t *N_used;
+    int32_t *status;
+};
+int launch_revchol_tridiag(const RevCholArgs &a, cudaStream_t s);
+
+// from chol_banded.cu
+struct CholFwdArgs {
+    int64_t batch;
+    const double *p, *q, *r, *shift, *head, *b;
+    int hp, nb, colgrowth, full_sweep;
+    double tol;
+    const int64_t *gbase;
+    const int64_t *ncap_per;
+    int64_t ncap;
+    double2 *work;
+    int64_t *ncols, *nconv, *nswept;
+    int32_t *status;
+};
+int launch_chol_forward(int u, const CholFwdArgs &a, cudaStream_t s);
+
+// from ql_blocktri.cu
+constexpr int kBtMaxN = 4;
+constexpr int kBtMaxHead = 4;
+template <typename T>
+struct BlockTriParamsT {
+    int n, n_dl, n_d, n_du, maxit;
+    double atol;
+    T c[kBtMaxN * kBtMaxN], a[kBtMaxN * kBtMaxN], b[kBtMaxN * kBtMaxN];
+    T dl_head[kBtMaxHead][kBtMaxN * kBtMaxN];
+    T d_head[kBtMaxHead][kBtMaxN * kBtMaxN];
+    T du_head[kBtMaxHead][kBtMaxN * kBtMaxN];
+};
+using BlockTriParams = BlockTriParamsT<double>;
+using BlockTriParamsC = BlockTriParamsT<cplx>;
+int launch_ql_blocktri(const BlockTriParams &P, const double *d_energy, int64_t batch, double *d_L11, int32_t *d_iters,
+                       int32_t *d_status, cudaStream_t s);
+int launch_ql_blocktri_c(const BlockTriParamsC &P, const cplx *d_energy, int64_t batch, cplx *d_L11, int32_t *d_iters,
+                         int32_t *d_status, cudaStream_t s);
+static inline int launch_ql_blocktri_any(const BlockTriParams &P, const double *e, int64_t batch, double *L, int32_t *it,
+                                         int32_t *st, cudaStream_t s) { return launch_ql_blocktri(P, e, batch, L, it, st, s); }
+static inline int launch_ql_blocktri_any(const BlockTriParamsC &P, const cplx *e, int64_t batch, cplx *L, int32_t *it,
+                                         int32_t *st, cudaStream_t s) { return launch_ql_blocktri_c(P, e, batch, L, it, st, s); }
+
+} // namespace ila

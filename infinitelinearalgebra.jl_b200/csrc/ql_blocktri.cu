@@ -17,23 +17,11 @@
 // the reflector, tau is complex; checked against the oracle to 1e-12 (complex division/multiplication orders differ
 // between numpy, Julia and this file at the rounding level, so bit equality is not claimed there).
 #include "ila_common.cuh"
+#include "ila_kernels.cuh"
 
 namespace ila {
 
-constexpr int kBtMaxN = 4;      // block size n <= 4
-constexpr int kBtMaxHead = 4;   // head blocks N <= 4
 
-template <typename T>
-struct BlockTriParamsT {
-    int n, n_dl, n_d, n_du, maxit;
-    double atol;
-    T c[kBtMaxN * kBtMaxN], a[kBtMaxN * kBtMaxN], b[kBtMaxN * kBtMaxN];   // tail blocks, column-major n x n
-    T dl_head[kBtMaxHead][kBtMaxN * kBtMaxN];   // A[Block(k+1,k)], k = 1..n_dl
-    T d_head[kBtMaxHead][kBtMaxN * kBtMaxN];    // A[Block(k,k)]
-    T du_head[kBtMaxHead][kBtMaxN * kBtMaxN];   // A[Block(k,k+1)]
-};
-using BlockTriParams = BlockTriParamsT<double>;
-using BlockTriParamsC = BlockTriParamsT<cplx>;
 
 // ---- scalar layer: no fused multiply-add, IEEE sqrt/div; real overloads are the reference's operations one for one ----
 __device__ __forceinline__ double bmul(double a, double b) { return __dmul_rn(a, b); }

@@ -15,7 +15,6 @@
 // eigenvector in closed form from the companion structure (V_1 = 1, V_{i+1} = g_i - w V_i).
 // Everything is FP64/ComplexF64 on the CUDA cores; 36 B of HBM traffic per shift, so the kernel is FP64-pipe bound.
 #include "ila_common.cuh"
-#include <cstdlib>
 
 namespace ila {
 
@@ -732,7 +731,7 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
         P.unit[j] = cplx{cos(th), sin(th)};
     }
     if (n <= 0) return 0;
-    static const int threads = getenv("ILA_TZ_THREADS") ? atoi(getenv("ILA_TZ_THREADS")) : 128;   // tuning knob
+    const int threads = 128;
     // shifts per thread: consecutive shifts share a warm start (longer runs amortise the cold start), but the grid
     // should still fill every SM to its resident-block limit: the smallest spt for which the grid is one full wave
     static int wave_cache[2] = {0, 0};   // resident blocks of this instantiation over the whole GPU (tail / no tail)

@@ -15,25 +15,10 @@
 // back-substitution loads 512 contiguous bytes per chunk.  The oracle (oracle/ila_oracle_c64.c) issues the same
 // operations in the same order: results are compared bit for bit.
 #include "ila_common.cuh"
+#include "ila_kernels.cuh"
 
 namespace ila {
 
-struct QrC64FwdArgs {
-    int64_t batch;
-    const cplx *p, *q;         // batch x (l+u+1) generators, data-row order
-    const double *r;           // batch x (l+u+1) real denominators or NULL
-    const cplx *shift;         // batch or NULL
-    const cplx *head;          // (l+u+1) x hp shared explicit head or NULL
-    const cplx *b;             // batch x nb
-    int hp, nb, colgrowth;
-    double tol;
-    const int64_t *gbase;      // ngroups+1 group bases (rows)
-    const int64_t *ncap_per;   // per-instance capacity or NULL
-    int64_t ncap;
-    double2 *work;
-    int64_t *ncols, *nconv, *nswept;
-    int32_t *status;
-};
 
 __device__ __forceinline__ cplx zmul(cplx a, cplx b)
 {

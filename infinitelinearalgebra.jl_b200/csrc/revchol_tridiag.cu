@@ -12,21 +12,12 @@
 // arithmetic is IEEE and unfused in the reference's order, so la, lb and the N at which the test fires equal the
 // oracle's (oracle/ila_oracle_revchol.c) bit for bit.
 #include "ila_common.cuh"
+#include "ila_kernels.cuh"
 
 namespace ila {
 
 constexpr int kMaxTridiagCholN = (1 << 21) - 1;
 
-struct RevCholArgs {
-    int64_t batch, n;
-    const double *ga, *gb;    // batch x 5 generator coefficients (c0, p, q, r, s): value(k) = c0 + (p + q k)/(r + s k)
-    const double *shift;      // batch or NULL (subtracted from the diagonal)
-    int hp;
-    const double *a_head, *b_head;   // hp explicit leading entries (shared) or NULL
-    double *la, *lb;          // batch x n
-    int64_t *N_used;
-    int32_t *status;
-};
 
 __global__ void __launch_bounds__(32) revchol_tridiag_kernel(RevCholArgs A)
 {

@@ -68,3 +68,12 @@ def test_status_instead_of_exceptions(ila):
     p = np.array([[1.0, -4.0, 1.0]]); q = np.zeros((1, 3))
     out = ila.chol_banded_solve(2, p, q, b=[1.0], ncap=4000)
     assert out["status"][0] == 4
+
+
+def test_release_and_reuse(ila):
+    from ila_b200 import _lib
+    col = np.array([2j, 0, 0, 1, 0.7])
+    L0, _ = ila.ql_toeplitz_l11(col, np.array([1 + 1j, 5.0]))
+    _lib.check(_lib.lib().ila_release())
+    L1, _ = ila.ql_toeplitz_l11(col, np.array([1 + 1j, 5.0]))       # pools are re-created on demand
+    assert np.array_equal(L0, L1, equal_nan=True)
