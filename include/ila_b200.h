@@ -242,6 +242,20 @@ int ila_revchol_tridiag_f64(int64_t batch, const double *ga, const double *gb, c
                             const double *a_head, const double *b_head, int64_t n, double *la, double *lb, int64_t *N_used,
                             int32_t *status, int ngpus);
 
+/* ---- K9: adaptive finite-section QL of ∞ banded operators WITHOUT a Toeplitz tail (real eltype) -------
+ * Replaces ql(A::InfBandedMatrix, tol) (src/infql.jl:385-388) = initialadaptiveQLblock / cache_filldata! (:391-411,
+ * 440-458): the block L[2:j-checkinds+1, 2:j-checkinds+1] of ql(A[checkinds:N, checkinds:N]) is compared (Frobenius)
+ * between N and 2N, N doubling from j until the difference is <= tol (status 3 = "Reached max. iterations in adaptive QL
+ * without convergence to desired tolerance" once N >= maxN; reference: maxN = 10000 for j = 50); the result is the
+ * leading j x j part of ql(A[1:N/2, 1:N/2]).  Operator i: diagonal d = col - row (data row rr = u - d, +u first) has
+ * value(t) = c0 + (p + q t)/(r + s t), t = min(row, col) 0-based, from g[((i*(l+u+1) + rr)*5 ..+4] = (c0,p,q,r,s);
+ * optional shared explicit head (l+u+1) x hp; shift[i] subtracted from the main diagonal.
+ * Outputs: Lband[(i*j + k)*(l+u+1) + c] = L[k, k-c]; V[(i*j + k)*u + r-1] = reflector entry of column k at row k-r;
+ * tau[i*j + k]; N_used[i] = size of the final section.  Supported (l,u): (1,1),(1,2),(2,1),(2,2),(3,1),(1,3). */
+int ila_ql_finite_section_f64(int l, int u, int64_t batch, const double *g, const double *shift, int hp, const double *head,
+                              int64_t j, double tol, int64_t maxN, double *Lband, double *V, double *tau, int64_t *N_used,
+                              int32_t *status, int ngpus);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,7 +102,7 @@ class BandedMatrix:
     """∞ banded operator given by its diagonals `{d: diag}` (d = col - row, as in `BandedMatrix(d => v)`)."""
 
     def __init__(self, diags: dict, shift=0.0):
-        self.diags = {int(d): (v if isinstance(v, (Affine, Vcat)) else Fill(v)) for d, v in diags.items()}
+        self.diags = {int(d): (v if isinstance(v, (Affine, Vcat)) or type(v).__name__ == "Rational" else Fill(v)) for d, v in diags.items()}
         self.shift = shift
 
     @property
@@ -479,3 +479,46 @@ class ReverseCholesky:
 
 def reversecholesky(A: SymTridiagonal):
     return ReverseCholesky(A)
+
+
+# ---- adaptive finite-section QL (operators without a Toeplitz tail) -------------------------------------------
+
+class FiniteSectionQL:
+    """ql(A, tol) for an ∞ banded operator by adaptive finite sections (src/infql.jl:385-462): the leading j x j part of
+    the factors; `.L[i, j]` (1-based), `.tau[k]`."""
+
+    def __init__(self, out, l, u):
+        self._Lband, self._V, self.tau, self.N = out["Lband"][0], out["V"][0], out["tau"][0], int(out["N"][0])
+        self.l, self.u = l, u
+        self.L = _OneBased(self._L)
+
+    def _L(self, i, j):
+        c = i - j
+        if c < 0 or c > self.l + self.u:
+            return 0.0
+        if i > self._Lband.shape[0]:
+            raise IndexError("only the leading block is materialised; pass a larger j to ql_adaptive")
+        return self._Lband[i - 1, c]
+
+
+def ql_adaptive(A: BandedMatrix, tol=np.finfo(float).eps, j=50, maxN=10000):
+    """ql(A, tol) (src/infql.jl:385) for a banded operator whose diagonals are Fill / Affine / Rational (+ Vcat heads)."""
+    l, u = A.bandwidths
+    gens, heads = [], []
+    for d in range(u, -l - 1, -1):
+        v = A.diags.get(d, Fill(0.0))
+        h = list(v.head) if isinstance(v, Vcat) else []
+        t = v.tail if isinstance(v, Vcat) else v
+        c0, p, q, r, s = _gen5(t)
+        off = len(h)
+        gens.append([c0, p - q * off, q, r - s * off, s])      # the lazy tail counts from the end of its own head
+        heads.append(h)
+    hp = max(len(h) for h in heads)
+    head = None
+    if hp:
+        val = lambda g, k: g[0] + (g[1] + g[2] * k) / (g[3] + g[4] * k)
+        head = np.array([[heads[rr][k] if k < len(heads[rr]) else val(gens[rr], k) for k in range(hp)] for rr in range(l + u + 1)])
+    out = _b.ql_finite_section(l, u, gens, j=j, shift=[A.shift] if A.shift else None, head=head, tol=tol, maxN=maxN)
+    if int(out["status"][0]) == 3:
+        raise NotConvergedError("Reached max. iterations in adaptive QL without convergence to desired tolerance.")
+    return FiniteSectionQL(out, l, u)

@@ -583,6 +583,61 @@ int ila_revchol_tridiag_f64(int64_t batch, const double *ga, const double *gb, c
     return 0;
 }
 
+// ================================ K9: adaptive finite-section QL =========================================
+
+int ila_ql_finite_section_f64(int l, int u, int64_t batch, const double *g, const double *shift, int hp, const double *head,
+                              int64_t j, double tol, int64_t maxN, double *Lband, double *V, double *tau, int64_t *N_used,
+                              int32_t *status, int ngpus)
+{
+    if (batch < 0 || !g || hp < 0 || (hp > 0 && !head) || (batch > 0 && (!Lband || !V || !tau || !N_used || !status)))
+        return set_error(ILA_ERR_ARG, "ql_finite_section: bad arguments");
+    if (l < 1 || u < 1 || j < l + u + 2 || maxN < j) return set_error(ILA_ERR_ARG, "ql_finite_section: need l,u >= 1, j >= l+u+2, maxN >= j");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int nd = l + u + 1;
+    const int64_t per = (batch + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= batch ? per : batch - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        double *d_g, *d_sh = nullptr, *d_head = nullptr, *d_L, *d_V, *d_tau;
+        int64_t *d_N;
+        int32_t *d_st;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt * nd * 5, &d_g))) return rc;
+        if (shift && (rc = dev_buf_t(pd, 1, (size_t)cnt, &d_sh))) return rc;
+        if (hp > 0 && (rc = dev_buf_t(pd, 2, (size_t)nd * hp, &d_head))) return rc;
+        if ((rc = dev_buf_t(pd, 3, (size_t)cnt * j * nd, &d_L))) return rc;
+        if ((rc = dev_buf_t(pd, 4, (size_t)cnt * j * u, &d_V))) return rc;
+        if ((rc = dev_buf_t(pd, 5, (size_t)cnt * j, &d_tau))) return rc;
+        if ((rc = dev_buf_t(pd, 6, (size_t)cnt, &d_N))) return rc;
+        if ((rc = dev_buf_t(pd, 7, (size_t)cnt, &d_st))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_g, g + lo * nd * 5, sizeof(double) * cnt * nd * 5, cudaMemcpyHostToDevice, s));
+        if (shift) ILA_CUDA_CHECK(cudaMemcpyAsync(d_sh, shift + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+        if (hp > 0) ILA_CUDA_CHECK(cudaMemcpyAsync(d_head, head, sizeof(double) * nd * hp, cudaMemcpyHostToDevice, s));
+        FsqlArgs a{cnt, j, maxN, d_g, d_sh, hp, d_head, tol, d_L, d_V, d_tau, d_N, d_st};
+        if ((rc = launch_ql_finite_section(l, u, a, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(Lband + lo * j * nd, d_L, sizeof(double) * cnt * j * nd, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(V + lo * j * u, d_V, sizeof(double) * cnt * j * u, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(tau + lo * j, d_tau, sizeof(double) * cnt * j, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(N_used + lo, d_N, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
 // ================================ K6: block-tridiagonal Toeplitz-tail QL ================================
 
 } // extern "C" (templates below have C++ linkage)

@@ -23,7 +23,7 @@ _sp = C.POINTER(C.c_int32)
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the recipe in oracle/Makefile."""
-    src = [os.path.join(_HERE, f) for f in ("ila_oracle.c", "ila_oracle_impl.h", "ila_oracle_c64.c", "ila_oracle_revchol.c", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ila_oracle.c", "ila_oracle_impl.h", "ila_oracle_c64.c", "ila_oracle_revchol.c", "ila_oracle_fsql.c", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -156,6 +156,35 @@ def revchol_tridiag(ga, gb, n, shift=None, a_head=None, b_head=None, batch=None,
                                      _ptr(a_head, _dp), _ptr(b_head, _dp), C.c_int64(n), _ptr(la, _dp), _ptr(lb, _dp),
                                      _ptr(N, _ip), _ptr(status, _sp), C.c_int(nthreads))
     return dict(la=la, lb=lb, N=N, status=status)
+
+
+def ql_finite_section(l, u, g, j=50, shift=None, head=None, tol=np.finfo(np.float64).eps, maxN=10000, batch=None,
+                      nthreads=0):
+    """Adaptive finite-section QL of ∞ banded operators (oracle/ila_oracle_fsql.c; reference src/infql.jl:364-462).
+    g: (batch x) (l+u+1) x 5 generator coefficients (c0, p, q, r, s) per diagonal, data-row order (+u first):
+    value(t) = c0 + (p + q t)/(r + s t), t = min(row, col) 0-based.  Returns dict(Lband (batch x j x (l+u+1):
+    Lband[k, c] = L[k, k-c]), V (batch x j x u reflectors), tau (batch x j), N, status)."""
+    nd = l + u + 1
+    g = np.asarray(g, dtype=np.float64).reshape(-1, nd, 5)
+    if batch is None:
+        batch = max(g.shape[0], 1 if shift is None else np.asarray(shift).size)
+    g = np.ascontiguousarray(np.broadcast_to(g, (batch, nd, 5)))
+    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=np.float64), (batch,)))
+    hp = 0
+    if head is not None:
+        head = np.ascontiguousarray(np.asarray(head, dtype=np.float64))
+        assert head.shape[0] == nd
+        hp = head.shape[1]
+    Lband = np.zeros((batch, j, nd)); V = np.zeros((batch, j, u)); tau = np.zeros((batch, j))
+    N = np.zeros(batch, dtype=np.int64); status = np.zeros(batch, dtype=np.int32)
+    L = lib()
+    L.ila_oracle_ql_finite_section_f64.restype = C.c_int
+    rc = L.ila_oracle_ql_finite_section_f64(C.c_int(l), C.c_int(u), C.c_int64(batch), _ptr(g, _dp), _ptr(shift, _dp),
+                                            C.c_int(hp), _ptr(head, _dp), C.c_int64(j), C.c_double(tol), C.c_int64(maxN),
+                                            _ptr(Lband, _dp), _ptr(V, _dp), _ptr(tau, _dp), _ptr(N, _ip), _ptr(status, _sp),
+                                            C.c_int(nthreads))
+    assert rc == 0, rc
+    return dict(Lband=Lband, V=V, tau=tau, N=N, status=status)
 
 
 def chol_banded_solve(u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=np.finfo(np.float64).tiny,
