@@ -414,6 +414,12 @@ def run_ours(args, rank, local_rank, world):
             return best * 1e3
         sh8 = np.linspace(0.0, 0.99, 4096)
         ms8 = wall(lambda: ila_b200.revchol_tridiag([3, 0, 0, 1, 0], [1, 0, 0, 1, 0], 256, shift=sh8))
+        sh10 = np.linspace(-6.0, -3.0, 4096)
+        g10 = [[1.0, 0, 0, 1, 0], [0.0, 1, 0, 1, 1], [1.0, 0, 0, 1, 0]]          # off-diagonals 1, diagonal 1/(k+1) - λ
+        res10 = {}
+        def run10():
+            res10["o"] = ila_b200.ql_finite_section(1, 1, g10, shift=sh10)
+        ms10 = wall(run10)
         lam9 = np.linspace(-2, 2, 512) + 0.2j
         p9 = np.tile(np.array([0.5, 0.0, 0.5]), (512, 1)); q9 = np.zeros((512, 3))
         res9 = {}
@@ -446,6 +452,12 @@ def run_ours(args, rank, local_rank, world):
              "ms_per_step": ms8, "config": {"workload": "K8 adaptive reverse Cholesky, SymTridiagonal(3 - s, 1), 4096 shifts s in "
                                                         "[0, 0.99], leading 256 x 256 block (per GPU)",
                                             "timing": "host C-ABI call, wall clock, copies included"},
+             "gpu_launches_per_step": 1},
+            {"metric": "finite_section_ql_operators_per_s", "value": 4096 * world / (ms10 * 1e-3), "unit": "operators/s",
+             "ms_per_step": ms10, "config": {"workload": "K9 adaptive finite-section QL, Jacobi operator diag 1/(k+1) - λ, 4096 shifts λ in "
+                                                         "[-6, -3], leading 50 x 50 block (per GPU)",
+                                             "final_section_sizes": [int(res10["o"]["N"].min()), int(res10["o"]["N"].max())],
+                                             "timing": "host C-ABI call, wall clock, copies included"},
              "gpu_launches_per_step": 1},
             {"metric": "adaptive_qr_c64_columns_per_s", "value": cols9 * world / (ms9 * 1e-3), "unit": "columns/s",
              "ms_per_step": ms9, "config": {"workload": "complex-eltype adaptive QR, (J - λI) \\ e1, 512 shifts λ = x + 0.2i (per GPU)",
