@@ -500,6 +500,27 @@ class FiniteSectionQL:
             raise IndexError("only the leading block is materialised; pass a larger j to ql_adaptive")
         return self._Lband[i - 1, c]
 
+    def Qt_mul(self, b):
+        """(Q' * b)[1:len] for a finitely supported b (src/infql.jl:497-528: reflectors k = last(colsupport(b))+u down to 1,
+        each touching rows max(1,k-u)..k).  Host glue over the leading block's packed reflectors."""
+        bb = np.array(b.head if isinstance(b, Vcat) else b, dtype=float)
+        u, nz = self.u, len(bb)
+        top = nz + u
+        if top > self._V.shape[0]:
+            raise IndexError("right-hand side reaches beyond the materialised block; pass a larger j to ql_adaptive")
+        B = np.zeros(top)
+        B[:nz] = bb
+        for k in range(top, 0, -1):                      # 1-based column k; V[k-1, r-1] = F[k-r, k]
+            lo = max(1, k - u)
+            vB = B[k - 1]
+            for i in range(lo, k):
+                vB = vB + self._V[k - 1, k - i - 1] * B[i - 1]
+            vB = self.tau[k - 1] * vB
+            B[k - 1] = B[k - 1] - vB
+            for i in range(lo, k):
+                B[i - 1] = B[i - 1] - self._V[k - 1, k - i - 1] * vB
+        return B
+
 
 def ql_adaptive(A: BandedMatrix, tol=np.finfo(float).eps, j=50, maxN=10000):
     """ql(A, tol) (src/infql.jl:385) for a banded operator whose diagonals are Fill / Affine / Rational (+ Vcat heads)."""

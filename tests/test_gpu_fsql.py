@@ -67,6 +67,8 @@ def test_mirror_api_reference_case(ila):
     b = [1.0, 2.0, 3.0]
     Lb = [sum(F.L[i, jj] * b[jj - 1] for jj in range(1, 4)) for i in range(1, 7)]
     assert Lb == [0.0, -5.25, -7.833333333333333, -2.4166666666666666, -1.0, 0.0]
+    qtb = F.Qt_mul(b)
+    assert list(qtb[:2]) == [-0.0, -1.0]                       # (Q'*b)[1:2] == [-0., -1.]  (test_infql.jl:218)
     B = BandedMatrix({1: Affine(1.0, 1.0), 0: Affine(1.25, 1.0), -1: Fill(1 / 3)})
     with pytest.raises(NotConvergedError):
         ql_adaptive(B)
