@@ -255,6 +255,11 @@ int ila_revchol_tridiag_f64(int64_t batch, const double *ga, const double *gb, c
 int ila_ql_finite_section_f64(int l, int u, int64_t batch, const double *g, const double *shift, int hp, const double *head,
                               int64_t j, double tol, int64_t maxN, double *Lband, double *V, double *tau, int64_t *N_used,
                               int32_t *status, int ngpus);
+/* Complex eltype (test/test_infql.jl:257-262): coefficients c0, p, q, the head, the shift and the outputs are complex; the
+ * real parts of r, s are used; the QL loop then runs down to the section's first column. */
+int ila_ql_finite_section_c64(int l, int u, int64_t batch, const ila_c64 *g, const ila_c64 *shift, int hp, const ila_c64 *head,
+                              int64_t j, double tol, int64_t maxN, ila_c64 *Lband, ila_c64 *V, ila_c64 *tau, int64_t *N_used,
+                              int32_t *status, int ngpus);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,8 @@ SIGNATURES = {
     "ila_release": (C.c_int, []),
     "ila_ql_finite_section_f64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_double, C.c_int64,
                                             _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "ila_ql_finite_section_c64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_double, C.c_int64,
+                                            _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "ila_ql_set_shifts_per_thread": (C.c_int, [C.c_int]),
     "ila_qr_banded_solve_f64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp,
                                           C.c_double, C.c_int, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp,

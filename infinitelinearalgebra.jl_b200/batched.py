@@ -370,24 +370,28 @@ def ql_finite_section(l, u, g, j=50, shift=None, head=None, tol=np.finfo(np.floa
     """Adaptive finite-section QL of ∞ banded operators without a Toeplitz tail, batched (reference src/infql.jl:364-462:
     `ql(A::InfBandedMatrix, tol)`; test/test_infql.jl:208-271).  g: (batch x) (l+u+1) x 5 generator coefficients
     (c0, p, q, r, s) per diagonal in data-row order (+u first): value(t) = c0 + (p + q t)/(r + s t), t = min(row, col)
-    0-based; `shift` is subtracted from the main diagonal.  Returns dict(Lband (batch x j x (l+u+1): Lband[k, c] = L[k, k-c]),
-    V (batch x j x u), tau (batch x j), N, status); L[1,1] of operator i is Lband[i, 0, 0]."""
+    0-based; `shift` is subtracted from the main diagonal.  Complex g / shift / head select the complex eltype.
+    Returns dict(Lband (batch x j x (l+u+1): Lband[k, c] = L[k, k-c]), V (batch x j x u), tau (batch x j), N, status);
+    L[1,1] of operator i is Lband[i, 0, 0]."""
     nd = l + u + 1
-    g = np.asarray(g, dtype=np.float64).reshape(-1, nd, 5)
+    cplx = any(v is not None and np.iscomplexobj(np.asarray(v)) for v in (g, shift, head))
+    dt = np.complex128 if cplx else np.float64
+    g = np.asarray(g, dtype=dt).reshape(-1, nd, 5)
     if batch is None:
         batch = max(g.shape[0], 1 if shift is None else np.asarray(shift).size)
     g = np.ascontiguousarray(np.broadcast_to(g, (batch, nd, 5)))
-    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=np.float64), (batch,)))
+    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=dt), (batch,)))
     hp = 0
     if head is not None:
-        head = np.ascontiguousarray(np.asarray(head, dtype=np.float64))
+        head = np.ascontiguousarray(np.asarray(head, dtype=dt))
         assert head.shape[0] == nd
         hp = head.shape[1]
     j = int(j)
-    Lband = np.empty((batch, j, nd)); V = np.empty((batch, j, u)); tau = np.empty((batch, j))
+    Lband = np.empty((batch, j, nd), dtype=dt); V = np.empty((batch, j, u), dtype=dt); tau = np.empty((batch, j), dtype=dt)
     N = np.zeros(batch, dtype=np.int64); status = np.zeros(batch, dtype=np.int32)
-    check(lib().ila_ql_finite_section_f64(l, u, batch, ptr(g), ptr(shift), hp, ptr(head), j, float(tol), int(maxN), ptr(Lband),
-                                          ptr(V), ptr(tau), ptr(N), ptr(status), ngpus))
+    fn = lib().ila_ql_finite_section_c64 if cplx else lib().ila_ql_finite_section_f64
+    check(fn(l, u, batch, ptr(g), ptr(shift), hp, ptr(head), j, float(tol), int(maxN), ptr(Lband), ptr(V), ptr(tau), ptr(N),
+             ptr(status), ngpus))
     return dict(Lband=Lband, V=V, tau=tau, N=N, status=status)
 
 

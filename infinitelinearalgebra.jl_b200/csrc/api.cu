@@ -585,9 +585,14 @@ int ila_revchol_tridiag_f64(int64_t batch, const double *ga, const double *gb, c
 
 // ================================ K9: adaptive finite-section QL =========================================
 
-int ila_ql_finite_section_f64(int l, int u, int64_t batch, const double *g, const double *shift, int hp, const double *head,
-                              int64_t j, double tol, int64_t maxN, double *Lband, double *V, double *tau, int64_t *N_used,
-                              int32_t *status, int ngpus)
+} // extern "C" (templates below have C++ linkage)
+
+static inline int launch_fsql_any(int l, int u, const FsqlArgs &a, cudaStream_t s) { return launch_ql_finite_section(l, u, a, s); }
+static inline int launch_fsql_any(int l, int u, const FsqlArgsC &a, cudaStream_t s) { return launch_ql_finite_section_c(l, u, a, s); }
+
+template <typename T>
+static int fsql_host(int l, int u, int64_t batch, const T *g, const T *shift, int hp, const T *head, int64_t j, double tol,
+                     int64_t maxN, T *Lband, T *V, T *tau, int64_t *N_used, int32_t *status, int ngpus)
 {
     if (batch < 0 || !g || hp < 0 || (hp > 0 && !head) || (batch > 0 && (!Lband || !V || !tau || !N_used || !status)))
         return set_error(ILA_ERR_ARG, "ql_finite_section: bad arguments");
@@ -605,7 +610,7 @@ int ila_ql_finite_section_f64(int l, int u, int64_t batch, const double *g, cons
         if (cnt <= 0) continue;
         const int pd = phys(d, G);
         if ((rc = dev_init(pd))) return rc;
-        double *d_g, *d_sh = nullptr, *d_head = nullptr, *d_L, *d_V, *d_tau;
+        T *d_g, *d_sh = nullptr, *d_head = nullptr, *d_L, *d_V, *d_tau;
         int64_t *d_N;
         int32_t *d_st;
         if ((rc = dev_buf_t(pd, 0, (size_t)cnt * nd * 5, &d_g))) return rc;
@@ -617,14 +622,14 @@ int ila_ql_finite_section_f64(int l, int u, int64_t batch, const double *g, cons
         if ((rc = dev_buf_t(pd, 6, (size_t)cnt, &d_N))) return rc;
         if ((rc = dev_buf_t(pd, 7, (size_t)cnt, &d_st))) return rc;
         cudaStream_t s = g_dev[pd].stream;
-        ILA_CUDA_CHECK(cudaMemcpyAsync(d_g, g + lo * nd * 5, sizeof(double) * cnt * nd * 5, cudaMemcpyHostToDevice, s));
-        if (shift) ILA_CUDA_CHECK(cudaMemcpyAsync(d_sh, shift + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
-        if (hp > 0) ILA_CUDA_CHECK(cudaMemcpyAsync(d_head, head, sizeof(double) * nd * hp, cudaMemcpyHostToDevice, s));
-        FsqlArgs a{cnt, j, maxN, d_g, d_sh, hp, d_head, tol, d_L, d_V, d_tau, d_N, d_st};
-        if ((rc = launch_ql_finite_section(l, u, a, s))) return rc;
-        ILA_CUDA_CHECK(cudaMemcpyAsync(Lband + lo * j * nd, d_L, sizeof(double) * cnt * j * nd, cudaMemcpyDeviceToHost, s));
-        ILA_CUDA_CHECK(cudaMemcpyAsync(V + lo * j * u, d_V, sizeof(double) * cnt * j * u, cudaMemcpyDeviceToHost, s));
-        ILA_CUDA_CHECK(cudaMemcpyAsync(tau + lo * j, d_tau, sizeof(double) * cnt * j, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_g, g + lo * nd * 5, sizeof(T) * cnt * nd * 5, cudaMemcpyHostToDevice, s));
+        if (shift) ILA_CUDA_CHECK(cudaMemcpyAsync(d_sh, shift + lo, sizeof(T) * cnt, cudaMemcpyHostToDevice, s));
+        if (hp > 0) ILA_CUDA_CHECK(cudaMemcpyAsync(d_head, head, sizeof(T) * nd * hp, cudaMemcpyHostToDevice, s));
+        FsqlArgsT<T> a{cnt, j, maxN, d_g, d_sh, hp, d_head, tol, d_L, d_V, d_tau, d_N, d_st};
+        if ((rc = launch_fsql_any(l, u, a, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(Lband + lo * j * nd, d_L, sizeof(T) * cnt * j * nd, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(V + lo * j * u, d_V, sizeof(T) * cnt * j * u, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(tau + lo * j, d_tau, sizeof(T) * cnt * j, cudaMemcpyDeviceToHost, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(N_used + lo, d_N, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
     }
@@ -636,6 +641,23 @@ int ila_ql_finite_section_f64(int l, int u, int64_t batch, const double *g, cons
     }
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
+}
+
+extern "C" {
+
+int ila_ql_finite_section_f64(int l, int u, int64_t batch, const double *g, const double *shift, int hp, const double *head,
+                              int64_t j, double tol, int64_t maxN, double *Lband, double *V, double *tau, int64_t *N_used,
+                              int32_t *status, int ngpus)
+{
+    return fsql_host<double>(l, u, batch, g, shift, hp, head, j, tol, maxN, Lband, V, tau, N_used, status, ngpus);
+}
+
+int ila_ql_finite_section_c64(int l, int u, int64_t batch, const ila_c64 *g, const ila_c64 *shift, int hp, const ila_c64 *head,
+                              int64_t j, double tol, int64_t maxN, ila_c64 *Lband, ila_c64 *V, ila_c64 *tau, int64_t *N_used,
+                              int32_t *status, int ngpus)
+{
+    return fsql_host<cplx>(l, u, batch, (const cplx *)g, (const cplx *)shift, hp, (const cplx *)head, j, tol, maxN,
+                           (cplx *)Lband, (cplx *)V, (cplx *)tau, N_used, status, ngpus);
 }
 
 // ================================ K6: block-tridiagonal Toeplitz-tail QL ================================

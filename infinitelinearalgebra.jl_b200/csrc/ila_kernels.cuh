@@ -93,18 +93,22 @@ struct RevCholArgs {
 int launch_revchol_tridiag(const RevCholArgs &a, cudaStream_t s);
 
 // from ql_finite_section.cu
-struct FsqlArgs {
+template <typename T>
+struct FsqlArgsT {
     int64_t batch, j, maxN;
-    const double *g;          // batch x (l+u+1) x 5 generator coefficients (c0, p, q, r, s), data-row order
-    const double *shift;      // batch or NULL
+    const T *g;               // batch x (l+u+1) x 5 generator coefficients (c0, p, q, r, s), data-row order (r, s: real parts used)
+    const T *shift;           // batch or NULL
     int hp;
-    const double *head;       // (l+u+1) x hp shared explicit head or NULL
+    const T *head;            // (l+u+1) x hp shared explicit head or NULL
     double tol;
-    double *Lband, *V, *tau;  // batch x j x (l+u+1), batch x j x u, batch x j
+    T *Lband, *V, *tau;       // batch x j x (l+u+1), batch x j x u, batch x j
     int64_t *N_used;
     int32_t *status;
 };
+using FsqlArgs = FsqlArgsT<double>;
+using FsqlArgsC = FsqlArgsT<cplx>;
 int launch_ql_finite_section(int l, int u, const FsqlArgs &a, cudaStream_t s);
+int launch_ql_finite_section_c(int l, int u, const FsqlArgsC &a, cudaStream_t s);
 
 // from chol_banded.cu
 struct CholFwdArgs {

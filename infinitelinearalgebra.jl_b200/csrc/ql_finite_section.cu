@@ -16,50 +16,49 @@
 // oracle's (oracle/ila_oracle_fsql.c) bit for bit.
 #include "ila_common.cuh"
 #include "ila_kernels.cuh"
+#include "ila_unfused.cuh"
 
 namespace ila {
 
-template <int L, int U>
-struct FsWindow {
-    static constexpr int NC = L + U + 1, NR = U + 1;
-    double W[NC][NR];   // W[c][r] = current A[k-r, k-c]
-};
-
-template <int L, int U>
-__global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgs A)
+template <typename T, int L, int U>
+__global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgsT<T> A)
 {
     const int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= A.batch) return;
     constexpr int NC = L + U + 1, NR = U + 1, MB = L + U;   // MB: largest test block
-    double g[NC][5];
+    // generator coefficients: c0, p, q of the scalar type, the denominator coefficients r, s real
+    T g0[NC], g1[NC], g2[NC];
+    double g3[NC], g4[NC];
 #pragma unroll
-    for (int rr = 0; rr < NC; rr++)
-#pragma unroll
-        for (int c = 0; c < 5; c++) g[rr][c] = A.g[(inst * NC + rr) * 5 + c];
-    const double shift = A.shift ? A.shift[inst] : 0.0;
+    for (int rr = 0; rr < NC; rr++) {
+        const T *gg = A.g + (inst * NC + rr) * 5;
+        g0[rr] = gg[0]; g1[rr] = gg[1]; g2[rr] = gg[2];
+        g3[rr] = zreal(gg[3]); g4[rr] = zreal(gg[4]);
+    }
+    const T shift = A.shift ? A.shift[inst] : zfrom<T>(0.0);
     const int hp = A.hp;
     const int64_t j = A.j;
 
-    auto entry = [&](int64_t row, int64_t col, int rr) -> double {   // rr = U - (col - row), inside the band by construction
-        if (row < 0 || col < 0) return 0.0;
+    auto entry = [&](int64_t row, int64_t col, int rr) -> T {   // rr = U - (col - row), inside the band by construction
+        if (row < 0 || col < 0) return zfrom<T>(0.0);
         const int64_t t = row < col ? row : col;
-        double v;
+        T v;
         if (t < hp) v = A.head[(int64_t)rr * hp + t];
         else {
-            const double num = __dadd_rn(g[rr][1], __dmul_rn(g[rr][2], (double)t));
-            const double den = __dadd_rn(g[rr][3], __dmul_rn(g[rr][4], (double)t));
-            v = __dadd_rn(g[rr][0], __ddiv_rn(num, den));
+            const T num = zadd(g1[rr], zmulr(g2[rr], (double)t));
+            const double den = __dadd_rn(g3[rr], __dmul_rn(g4[rr], (double)t));
+            v = zadd(g0[rr], zdivr(num, den));
         }
-        if (rr == U) v = __dsub_rn(v, shift);
+        if (rr == U) v = zsub(v, shift);
         return v;
     };
 
-    double blkS[MB][MB], blkL[MB][MB];
-    double *Lband = A.Lband + inst * j * NC, *V = A.V + inst * j * U, *tau_out = A.tau + inst * j;
+    T blkS[MB][MB], blkL[MB][MB];
+    T *Lband = A.Lband + inst * j * NC, *V = A.V + inst * j * U, *tau_out = A.tau + inst * j;
 
     // mode 0: fill blkS, 1: fill blkL (test block rows base..base+m-1), 2: write the leading j rows
     auto sweep = [&](int64_t lo, int64_t hi, int64_t kstop, int64_t krec, int mode, int64_t base, int m) {
-        double W[NC][NR];
+        T W[NC][NR];
         int64_t k = hi;
 #pragma unroll
         for (int c = 0; c < NC; c++)
@@ -67,37 +66,38 @@ __global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgs A)
             for (int r = 0; r < NR; r++) {
                 const int64_t row = k - r, col = k - c;
                 const int d = r - c;   // col - row
-                W[c][r] = (row >= lo && col >= lo && d >= -L && d <= U) ? entry(row, col, U - d) : 0.0;
+                W[c][r] = (row >= lo && col >= lo && d >= -L && d <= U) ? entry(row, col, U - d) : zfrom<T>(0.0);
             }
         for (; k >= kstop; k--) {
-            double x[NR], tau = 0.0;
+            T x[NR], tau = zfrom<T>(0.0);
 #pragma unroll
             for (int r = 0; r < NR; r++) x[r] = W[0][r];
-            if (k > lo) {
-                double s = __dmul_rn(x[0], x[0]);
+            if (k > lo || z_is_cplx<T>::value) {   // real eltype: the QL loop stops at the section's second column
+                double s = zabs2(x[0]);
 #pragma unroll
-                for (int r = 1; r < NR; r++) s = __dadd_rn(s, __dmul_rn(x[r], x[r]));
+                for (int r = 1; r < NR; r++) s = __dadd_rn(s, zabs2(x[r]));
                 const double normu = __dsqrt_rn(s);
                 if (normu != 0.0) {
-                    double xi1 = x[0];
-                    const double nu = copysign(normu, xi1);
-                    xi1 = __dadd_rn(xi1, nu);
-                    x[0] = -nu;
+                    T xi1 = x[0];
+                    const double nu = copysign(normu, zreal(xi1));
+                    xi1 = zaddr(xi1, nu);
+                    x[0] = zfrom<T>(-nu);
 #pragma unroll
-                    for (int r = 1; r < NR; r++) x[r] = __ddiv_rn(x[r], xi1);
-                    tau = __ddiv_rn(xi1, nu);
+                    for (int r = 1; r < NR; r++) x[r] = zdiv(x[r], xi1);
+                    tau = zdivr(xi1, nu);
                 }
+                const T tauc = zconj(tau);
 #pragma unroll
                 for (int r = 0; r < NR; r++) W[0][r] = x[r];
 #pragma unroll
                 for (int c = 1; c < NC; c++) {
-                    double vA = W[c][0];
+                    T vA = W[c][0];
 #pragma unroll
-                    for (int r = 1; r < NR; r++) vA = __dadd_rn(vA, __dmul_rn(x[r], W[c][r]));
-                    vA = __dmul_rn(tau, vA);
-                    W[c][0] = __dsub_rn(W[c][0], vA);
+                    for (int r = 1; r < NR; r++) vA = zadd(vA, zmul(zconj(x[r]), W[c][r]));
+                    vA = zmul(tauc, vA);
+                    W[c][0] = zsub(W[c][0], vA);
 #pragma unroll
-                    for (int r = 1; r < NR; r++) W[c][r] = __dsub_rn(W[c][r], __dmul_rn(x[r], vA));
+                    for (int r = 1; r < NR; r++) W[c][r] = zsub(W[c][r], zmul(x[r], vA));
                 }
             }
             if (k <= krec) {
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgs A)
 #pragma unroll
                         for (int jj = 0; jj < MB; jj++) {
                             const int cc = i - jj;
-                            double v = 0.0;
+                            T v = zfrom<T>(0.0);
 #pragma unroll
                             for (int c = 0; c < NC; c++)
                                 if (c == cc) v = W[c][0];
@@ -135,11 +135,11 @@ __global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgs A)
 #pragma unroll
                 for (int r = 0; r + 1 < NR; r++) W[c][r] = W[c + 1][r + 1];
 #pragma unroll
-            for (int r = 0; r + 1 < NR; r++) W[NC - 1][r] = 0.0;
+            for (int r = 0; r + 1 < NR; r++) W[NC - 1][r] = zfrom<T>(0.0);
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 const int64_t row = k - 1 - U, col = k - 1 - c;
-                W[c][U] = (row >= lo && col >= lo) ? entry(row, col, c) : 0.0;   // col - row = U - c -> data row c
+                W[c][U] = (row >= lo && col >= lo) ? entry(row, col, c) : zfrom<T>(0.0);   // col - row = U - c -> data row c
             }
         }
     };
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgs A)
 #pragma unroll
     for (int a = 0; a < MB; a++)
 #pragma unroll
-        for (int b = 0; b < MB; b++) { blkS[a][b] = 0.0; blkL[a][b] = 0.0; }
+        for (int b = 0; b < MB; b++) { blkS[a][b] = zfrom<T>(0.0); blkL[a][b] = zfrom<T>(0.0); }
     int64_t N = j;
     sweep(lo, N - 1, lo + 1, j - 1, 0, lo + 1, m);
     double Lerr = 1.0;
@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgs A)
 #pragma unroll
             for (int ri = 0; ri < MB; ri++)
                 if (cj < m && ri < m) {
-                    const double dlt = __dsub_rn(blkL[ri][cj], blkS[ri][cj]);
-                    s = __dadd_rn(s, __dmul_rn(dlt, dlt));
+                    const T dlt = zsub(blkL[ri][cj], blkS[ri][cj]);
+                    s = __dadd_rn(s, zabs2(dlt));
                 }
         Lerr = __dsqrt_rn(s);
         if (N >= A.maxN) { st = ILA_NOT_CONVERGED; break; }
@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgs A)
         sweep(0, N / 2 - 1, 0, j - 1, 2, 0, 0);
         A.N_used[inst] = N / 2;
     } else {
-        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        const double qn = __longlong_as_double(0x7ff8000000000000LL);
+        T qnan = zfrom<T>(qn);
+        if (z_is_cplx<T>::value) qnan = zaddr(zmul(qnan, qnan), 0.0);   // NaN in both parts
         for (int64_t k = 0; k < j * NC; k++) Lband[k] = qnan;
         for (int64_t k = 0; k < j * U; k++) V[k] = qnan;
         for (int64_t k = 0; k < j; k++) tau_out[k] = qnan;
@@ -187,26 +189,30 @@ __global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgs A)
     A.status[inst] = st;
 }
 
-template <int L, int U>
-static int launch_fsql_lu(const FsqlArgs &a, cudaStream_t s)
+template <typename T, int L, int U>
+static int launch_fsql_lu(const FsqlArgsT<T> &a, cudaStream_t s)
 {
     const unsigned blocks = (unsigned)((a.batch + 31) / 32);
-    ql_finite_section_kernel<L, U><<<blocks, 32, 0, s>>>(a);
+    ql_finite_section_kernel<T, L, U><<<blocks, 32, 0, s>>>(a);
     count_launch();
     ILA_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
-int launch_ql_finite_section(int l, int u, const FsqlArgs &a, cudaStream_t s)
+template <typename T>
+static int launch_fsql_t(int l, int u, const FsqlArgsT<T> &a, cudaStream_t s)
 {
     if (a.batch <= 0) return 0;
-    if (l == 1 && u == 1) return launch_fsql_lu<1, 1>(a, s);
-    if (l == 1 && u == 2) return launch_fsql_lu<1, 2>(a, s);
-    if (l == 2 && u == 1) return launch_fsql_lu<2, 1>(a, s);
-    if (l == 2 && u == 2) return launch_fsql_lu<2, 2>(a, s);
-    if (l == 3 && u == 1) return launch_fsql_lu<3, 1>(a, s);
-    if (l == 1 && u == 3) return launch_fsql_lu<1, 3>(a, s);
+    if (l == 1 && u == 1) return launch_fsql_lu<T, 1, 1>(a, s);
+    if (l == 1 && u == 2) return launch_fsql_lu<T, 1, 2>(a, s);
+    if (l == 2 && u == 1) return launch_fsql_lu<T, 2, 1>(a, s);
+    if (l == 2 && u == 2) return launch_fsql_lu<T, 2, 2>(a, s);
+    if (l == 3 && u == 1) return launch_fsql_lu<T, 3, 1>(a, s);
+    if (l == 1 && u == 3) return launch_fsql_lu<T, 1, 3>(a, s);
     return set_error(ILA_ERR_UNSUPPORTED, "ql_finite_section: bandwidths (l,u) not instantiated");
 }
+
+int launch_ql_finite_section(int l, int u, const FsqlArgs &a, cudaStream_t s) { return launch_fsql_t<double>(l, u, a, s); }
+int launch_ql_finite_section_c(int l, int u, const FsqlArgsC &a, cudaStream_t s) { return launch_fsql_t<cplx>(l, u, a, s); }
 
 } // namespace ila

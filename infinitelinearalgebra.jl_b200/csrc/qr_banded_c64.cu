@@ -16,27 +16,10 @@
 // operations in the same order: results are compared bit for bit.
 #include "ila_common.cuh"
 #include "ila_kernels.cuh"
+#include "ila_unfused.cuh"
 
 namespace ila {
 
-
-__device__ __forceinline__ cplx zmul(cplx a, cplx b)
-{
-    return cplx{__dsub_rn(__dmul_rn(a.re, b.re), __dmul_rn(a.im, b.im)), __dadd_rn(__dmul_rn(a.re, b.im), __dmul_rn(a.im, b.re))};
-}
-__device__ __forceinline__ cplx zadd(cplx a, cplx b) { return cplx{__dadd_rn(a.re, b.re), __dadd_rn(a.im, b.im)}; }
-__device__ __forceinline__ cplx zsub(cplx a, cplx b) { return cplx{__dsub_rn(a.re, b.re), __dsub_rn(a.im, b.im)}; }
-__device__ __forceinline__ cplx zconj(cplx a) { return cplx{a.re, -a.im}; }
-__device__ __forceinline__ double zabs2(cplx a) { return __dadd_rn(__dmul_rn(a.re, a.re), __dmul_rn(a.im, a.im)); }
-__device__ __forceinline__ cplx zdiv(cplx a, cplx b)
-{   // Smith
-    if (fabs(b.re) >= fabs(b.im)) {
-        const double r = __ddiv_rn(b.im, b.re), den = __dadd_rn(b.re, __dmul_rn(b.im, r));
-        return cplx{__ddiv_rn(__dadd_rn(a.re, __dmul_rn(a.im, r)), den), __ddiv_rn(__dsub_rn(a.im, __dmul_rn(a.re, r)), den)};
-    }
-    const double r = __ddiv_rn(b.re, b.im), den = __dadd_rn(__dmul_rn(b.re, r), b.im);
-    return cplx{__ddiv_rn(__dadd_rn(__dmul_rn(a.re, r), a.im), den), __ddiv_rn(__dsub_rn(__dmul_rn(a.im, r), a.re), den)};
-}
 
 template <int L, int U>
 __global__ void __launch_bounds__(32) qr_forward_c64_kernel(QrC64FwdArgs A)

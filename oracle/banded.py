@@ -162,27 +162,29 @@ def ql_finite_section(l, u, g, j=50, shift=None, head=None, tol=np.finfo(np.floa
                       nthreads=0):
     """Adaptive finite-section QL of ∞ banded operators (oracle/ila_oracle_fsql.c; reference src/infql.jl:364-462).
     g: (batch x) (l+u+1) x 5 generator coefficients (c0, p, q, r, s) per diagonal, data-row order (+u first):
-    value(t) = c0 + (p + q t)/(r + s t), t = min(row, col) 0-based.  Returns dict(Lband (batch x j x (l+u+1):
-    Lband[k, c] = L[k, k-c]), V (batch x j x u reflectors), tau (batch x j), N, status)."""
+    value(t) = c0 + (p + q t)/(r + s t), t = min(row, col) 0-based.  Complex g / shift / head select the complex eltype.
+    Returns dict(Lband (batch x j x (l+u+1): Lband[k, c] = L[k, k-c]), V (batch x j x u reflectors), tau (batch x j), N, status)."""
     nd = l + u + 1
-    g = np.asarray(g, dtype=np.float64).reshape(-1, nd, 5)
+    cplx = any(v is not None and np.iscomplexobj(np.asarray(v)) for v in (g, shift, head))
+    dt = np.complex128 if cplx else np.float64
+    g = np.asarray(g, dtype=dt).reshape(-1, nd, 5)
     if batch is None:
         batch = max(g.shape[0], 1 if shift is None else np.asarray(shift).size)
     g = np.ascontiguousarray(np.broadcast_to(g, (batch, nd, 5)))
-    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=np.float64), (batch,)))
+    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=dt), (batch,)))
     hp = 0
     if head is not None:
-        head = np.ascontiguousarray(np.asarray(head, dtype=np.float64))
+        head = np.ascontiguousarray(np.asarray(head, dtype=dt))
         assert head.shape[0] == nd
         hp = head.shape[1]
-    Lband = np.zeros((batch, j, nd)); V = np.zeros((batch, j, u)); tau = np.zeros((batch, j))
+    Lband = np.zeros((batch, j, nd), dtype=dt); V = np.zeros((batch, j, u), dtype=dt); tau = np.zeros((batch, j), dtype=dt)
     N = np.zeros(batch, dtype=np.int64); status = np.zeros(batch, dtype=np.int32)
     L = lib()
-    L.ila_oracle_ql_finite_section_f64.restype = C.c_int
-    rc = L.ila_oracle_ql_finite_section_f64(C.c_int(l), C.c_int(u), C.c_int64(batch), _ptr(g, _dp), _ptr(shift, _dp),
-                                            C.c_int(hp), _ptr(head, _dp), C.c_int64(j), C.c_double(tol), C.c_int64(maxN),
-                                            _ptr(Lband, _dp), _ptr(V, _dp), _ptr(tau, _dp), _ptr(N, _ip), _ptr(status, _sp),
-                                            C.c_int(nthreads))
+    fn = L.ila_oracle_ql_finite_section_c64 if cplx else L.ila_oracle_ql_finite_section_f64
+    fn.restype = C.c_int
+    pv = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+    rc = fn(C.c_int(l), C.c_int(u), C.c_int64(batch), pv(g), pv(shift), C.c_int(hp), pv(head), C.c_int64(j), C.c_double(tol),
+            C.c_int64(maxN), pv(Lband), pv(V), pv(tau), _ptr(N, _ip), _ptr(status, _sp), C.c_int(nthreads))
     assert rc == 0, rc
     return dict(Lband=Lband, V=V, tau=tau, N=N, status=status)
 

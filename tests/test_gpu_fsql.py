@@ -72,3 +72,17 @@ def test_mirror_api_reference_case(ila):
     B = BandedMatrix({1: Affine(1.0, 1.0), 0: Affine(1.25, 1.0), -1: Fill(1 / 3)})
     with pytest.raises(NotConvergedError):
         ql_adaptive(B)
+
+
+def test_complex_eltype_bit_exact(ila):
+    # test/test_infql.jl:257-262 and a complex-shift family; same unfused operations as the oracle: bit for bit
+    from oracle import banded as ob
+    head = 1j * np.array([[1.0, 2.0, 1.0], [1.0, 2.0, 3.0], [1.0, 2.0, 1.0]])
+    g = [C(1j), C(3j), C(1j)]
+    _same(ila.ql_finite_section(1, 1, g, j=51, head=head), ob.ql_finite_section(1, 1, g, j=51, head=head))
+    lam = np.linspace(-2.0, 2.0, 50) + 1.5j
+    g = [C(1.0), [0.0, 1, 0, 1, 1], C(1.0)]
+    o = ob.ql_finite_section(1, 1, g, shift=lam)
+    gg = ila.ql_finite_section(1, 1, g, shift=lam)
+    assert (o["status"] == 0).sum() >= 45 and np.iscomplexobj(gg["Lband"])     # (one shift sits where the sections do not settle)
+    _same(gg, o)

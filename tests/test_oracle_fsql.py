@@ -82,3 +82,22 @@ def test_non_tridiagonal_against_finite_section():
     F, t = tq.dense_ql(A)
     ref = np.array([[F[i, i - c] if i - c >= 0 else 0 for c in range(5)] for i in range(10)])
     assert np.allclose(ref, o["Lband"][0][:10], rtol=0, atol=1e-13) and np.allclose(t[:10], o["tau"][0][:10], rtol=0, atol=1e-13)
+
+
+def test_complex_entries_against_dense_ql():
+    # :257-262  A = im * Tridiagonal([[1,2]; Fill(1)], [[1,2]; Fill(3)], [[1,2]; Fill(1)]): (Q*L)[1:50,1:50] ≈ A  ->  here the
+    # factors against the dense complex Householder QL of the final section (numpy's complex division rounds differently: 1e-14)
+    head = 1j * np.array([[1.0, 2.0, 1.0], [1.0, 2.0, 3.0], [1.0, 2.0, 1.0]])
+    g = [C(1j), C(3j), C(1j)]
+    o = ob.ql_finite_section(1, 1, g, j=51, head=head)
+    assert o["status"][0] == 0 and np.iscomplexobj(o["Lband"])
+    N = int(o["N"][0])
+    A = np.zeros((N, N), complex)
+    d = [1, 2] + [3] * (N - 2); e = [1, 2] + [1] * (N - 3)
+    for k in range(N):
+        A[k, k] = 1j * d[k]
+        if k < N - 1:
+            A[k, k + 1] = 1j * e[k]; A[k + 1, k] = 1j * e[k]
+    F, t = tq.dense_ql(A)
+    ref = np.array([[F[i, i - c] if i - c >= 0 else 0 for c in range(3)] for i in range(51)])
+    assert np.abs(ref - o["Lband"][0]).max() <= 1e-14 and np.abs(t[:51] - o["tau"][0]).max() <= 1e-14
