@@ -15,13 +15,14 @@ __device__ __forceinline__ cplx zsub(cplx a, cplx b) { return cplx{__dsub_rn(a.r
 __device__ __forceinline__ cplx zconj(cplx a) { return cplx{a.re, -a.im}; }
 __device__ __forceinline__ double zabs2(cplx a) { return __dadd_rn(__dmul_rn(a.re, a.re), __dmul_rn(a.im, a.im)); }
 __device__ __forceinline__ cplx zdiv(cplx a, cplx b)
-{   // Smith
-    if (fabs(b.re) >= fabs(b.im)) {
-        const double r = __ddiv_rn(b.im, b.re), den = __dadd_rn(b.re, __dmul_rn(b.im, r));
-        return cplx{__ddiv_rn(__dadd_rn(a.re, __dmul_rn(a.im, r)), den), __ddiv_rn(__dsub_rn(a.im, __dmul_rn(a.re, r)), den)};
-    }
-    const double r = __ddiv_rn(b.re, b.im), den = __dadd_rn(__dmul_rn(b.re, r), b.im);
-    return cplx{__ddiv_rn(__dadd_rn(__dmul_rn(a.re, r), a.im), den), __ddiv_rn(__dsub_rn(__dmul_rn(a.im, r), a.re), den)};
+{   // Smith's algorithm, branch-free: when |b.im| > |b.re| both operands are multiplied by -i first (a/b is unchanged and
+    // every intermediate equals the textbook second branch bit for bit: r -> -r exactly, sums commute), so the 32 lanes of
+    // a warp never diverge on the operand shape
+    const bool sw = fabs(b.re) < fabs(b.im);
+    const cplx aa = sw ? cplx{a.im, -a.re} : a;
+    const cplx bb = sw ? cplx{b.im, -b.re} : b;
+    const double r = __ddiv_rn(bb.im, bb.re), den = __dadd_rn(bb.re, __dmul_rn(bb.im, r));
+    return cplx{__ddiv_rn(__dadd_rn(aa.re, __dmul_rn(aa.im, r)), den), __ddiv_rn(__dsub_rn(aa.im, __dmul_rn(aa.re, r)), den)};
 }
 
 // real overloads with the same names, so that kernels templated on the scalar type read the same

@@ -195,22 +195,36 @@ __global__ void __launch_bounds__(32) qr_backsolve_c64_kernel(int64_t batch, con
     cplx xw[UP + 1];
 #pragma unroll
     for (int j = 0; j <= UP; j++) xw[j] = mk(0.0, 0.0);
-    for (int64_t r = nsw - 1; r >= 0; r--) {
-        const double2 *src = rec + r * REC * 32;
-        cplx v[REC];
+    // records are fetched PF rows ahead of their use (register ring): the DRAM latency of a row overlaps the
+    // recurrence of the PF rows before it
+    constexpr int PF = 4;
+    double2 ring[PF][REC];
 #pragma unroll
-        for (int c = 0; c < REC; c++) {
-            const double2 w = src[c * 32];
-            v[c] = mk(w.x, w.y);
+    for (int p = 0; p < PF; p++) {
+        const int64_t rr = nsw - 1 - p;
+#pragma unroll
+        for (int c = 0; c < REC; c++) ring[p][c] = (rr >= 0) ? rec[(rr * REC + c) * 32] : make_double2(0.0, 0.0);
+    }
+    for (int64_t r0 = nsw - 1; r0 >= 0; r0 -= PF) {
+#pragma unroll
+        for (int p = 0; p < PF; p++) {
+            const int64_t r = r0 - p;
+            if (r < 0) break;
+            cplx v[REC];
+#pragma unroll
+            for (int c = 0; c < REC; c++) v[c] = mk(ring[p][c].x, ring[p][c].y);
+            const int64_t rn = r - PF;        // refill this slot with the row PF below
+#pragma unroll
+            for (int c = 0; c < REC; c++) ring[p][c] = (rn >= 0) ? rec[(rn * REC + c) * 32] : make_double2(0.0, 0.0);
+            cplx t = v[NC];
+#pragma unroll
+            for (int j = UP; j >= 1; j--) t = zsub(t, zmul(xw[j], v[j]));
+            const cplx xr = zdiv(t, v[0]);
+            xo[r] = make_double2(xr.re, xr.im);
+#pragma unroll
+            for (int j = UP; j >= 2; j--) xw[j] = xw[j - 1];
+            xw[1] = xr;
         }
-        cplx t = v[NC];
-#pragma unroll
-        for (int j = UP; j >= 1; j--) t = zsub(t, zmul(xw[j], v[j]));
-        const cplx xr = zdiv(t, v[0]);
-        xo[r] = make_double2(xr.re, xr.im);
-#pragma unroll
-        for (int j = UP; j >= 2; j--) xw[j] = xw[j - 1];
-        xw[1] = xr;
     }
 }
 
