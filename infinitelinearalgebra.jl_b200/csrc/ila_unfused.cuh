@@ -1,8 +1,9 @@
 // ila_unfused.cuh — unfused IEEE scalar layer shared by the bit-exact kernels: every product / sum is a separate
-// correctly rounded operation (no FMA contraction), quotients and square roots are the IEEE intrinsics; complex products are
+// correctly rounded operation (no FMA contraction), quotients and square roots are IEEE (ediv / esqrt of ila_exact.cuh: the exact fast sequences in range, the intrinsics outside); complex products are
 // the four-multiply form and complex quotients Smith's algorithm — the operation order of the C oracles.
 #pragma once
 #include "ila_common.cuh"
+#include "ila_exact.cuh"
 
 namespace ila {
 
@@ -21,8 +22,8 @@ __device__ __forceinline__ cplx zdiv(cplx a, cplx b)
     const bool sw = fabs(b.re) < fabs(b.im);
     const cplx aa = sw ? cplx{a.im, -a.re} : a;
     const cplx bb = sw ? cplx{b.im, -b.re} : b;
-    const double r = __ddiv_rn(bb.im, bb.re), den = __dadd_rn(bb.re, __dmul_rn(bb.im, r));
-    return cplx{__ddiv_rn(__dadd_rn(aa.re, __dmul_rn(aa.im, r)), den), __ddiv_rn(__dsub_rn(aa.im, __dmul_rn(aa.re, r)), den)};
+    const double r = ediv(bb.im, bb.re), den = __dadd_rn(bb.re, __dmul_rn(bb.im, r));
+    return cplx{ediv(__dadd_rn(aa.re, __dmul_rn(aa.im, r)), den), ediv(__dsub_rn(aa.im, __dmul_rn(aa.re, r)), den)};
 }
 
 // real overloads with the same names, so that kernels templated on the scalar type read the same
@@ -31,13 +32,13 @@ __device__ __forceinline__ double zadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double zsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double zconj(double a) { return a; }
 __device__ __forceinline__ double zabs2(double a) { return __dmul_rn(a, a); }
-__device__ __forceinline__ double zdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double zdiv(double a, double b) { return ediv(a, b); }
 __device__ __forceinline__ double zreal(double a) { return a; }
 __device__ __forceinline__ double zreal(cplx a) { return a.re; }
 __device__ __forceinline__ double zaddr(double a, double v) { return __dadd_rn(a, v); }          // a + (real) v
 __device__ __forceinline__ cplx zaddr(cplx a, double v) { return cplx{__dadd_rn(a.re, v), a.im}; }
-__device__ __forceinline__ double zdivr(double a, double v) { return __ddiv_rn(a, v); }          // a / (real) v
-__device__ __forceinline__ cplx zdivr(cplx a, double v) { return cplx{__ddiv_rn(a.re, v), __ddiv_rn(a.im, v)}; }
+__device__ __forceinline__ double zdivr(double a, double v) { return ediv(a, v); }          // a / (real) v
+__device__ __forceinline__ cplx zdivr(cplx a, double v) { return cplx{ediv(a.re, v), ediv(a.im, v)}; }
 __device__ __forceinline__ double zmulr(double a, double v) { return __dmul_rn(a, v); }          // a * (real) v
 __device__ __forceinline__ cplx zmulr(cplx a, double v) { return cplx{__dmul_rn(a.re, v), __dmul_rn(a.im, v)}; }
 template <typename T> __device__ __forceinline__ T zfrom(double v);

@@ -18,6 +18,7 @@
 // between numpy, Julia and this file at the rounding level, so bit equality is not claimed there).
 #include "ila_common.cuh"
 #include "ila_kernels.cuh"
+#include "ila_exact.cuh"
 
 namespace ila {
 
@@ -27,7 +28,8 @@ namespace ila {
 __device__ __forceinline__ double bmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double badd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double bsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double bdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double bdiv(double a, double b) { return ediv(a, b); }     // IEEE quotient (fast exact sequence in range)
+__device__ __forceinline__ double bsqrt(double a) { return esqrt(a); }               // IEEE square root
 __device__ __forceinline__ double bconj(double a) { return a; }
 __device__ __forceinline__ double babs2(double a) { return bmul(a, a); }
 __device__ __forceinline__ double breal(double a) { return a; }
@@ -71,7 +73,7 @@ __device__ __forceinline__ T ql_step(At &&at, int mu, int col)
 {
     double s = babs2(at(mu - 1, col));
     for (int i = 1; i < mu; i++) s = badd(s, babs2(at(mu - 1 - i, col)));
-    const double normu = __dsqrt_rn(s);
+    const double normu = bsqrt(s);
     T t = bzero<T>();
     if (normu != 0.0) {
         T xi1 = at(mu - 1, col);
@@ -106,7 +108,7 @@ __device__ __forceinline__ void dense_ql(T (&X)[R][C], T (&tau)[(R < C ? R : C)]
         double s = babs2(X[mu - 1][nu - 1]);
 #pragma unroll
         for (int i = 1; i < mu; i++) s = badd(s, babs2(X[mu - 1 - i][nu - 1]));
-        const double normu = __dsqrt_rn(s);
+        const double normu = bsqrt(s);
         T t = bzero<T>();
         if (normu != 0.0) {
             T xi1 = X[mu - 1][nu - 1];
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParamsT<T> 
             }
         const bool nan = (sd != sd) || (se != se);
         if (nan) { st = ILA_NAN; break; }
-        if (__dsqrt_rn(sd) <= P.atol && __dsqrt_rn(se) <= P.atol) { st = ILA_OK; break; }
+        if (bsqrt(sd) <= P.atol && bsqrt(se) <= P.atol) { st = ILA_OK; break; }
 #pragma unroll
         for (int i = 0; i < n; i++)
 #pragma unroll

@@ -16,6 +16,7 @@
 // oracle's (oracle/ila_oracle_fsql.c) bit for bit.
 #include "ila_common.cuh"
 #include "ila_kernels.cuh"
+#include "ila_exact.cuh"
 #include "ila_unfused.cuh"
 
 namespace ila {
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgsT<T> A)
                 double s = zabs2(x[0]);
 #pragma unroll
                 for (int r = 1; r < NR; r++) s = __dadd_rn(s, zabs2(x[r]));
-                const double normu = __dsqrt_rn(s);
+                const double normu = esqrt(s);
                 if (normu != 0.0) {
                     T xi1 = x[0];
                     const double nu = copysign(normu, zreal(xi1));
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(32) ql_finite_section_kernel(FsqlArgsT<T> A)
                     const T dlt = zsub(blkL[ri][cj], blkS[ri][cj]);
                     s = __dadd_rn(s, zabs2(dlt));
                 }
-        Lerr = __dsqrt_rn(s);
+        Lerr = esqrt(s);
         if (N >= A.maxN) { st = ILA_NOT_CONVERGED; break; }
 #pragma unroll
         for (int a = 0; a < MB; a++)

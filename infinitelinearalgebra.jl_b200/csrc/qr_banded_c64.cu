@@ -16,6 +16,7 @@
 // operations in the same order: results are compared bit for bit.
 #include "ila_common.cuh"
 #include "ila_kernels.cuh"
+#include "ila_exact.cuh"
 #include "ila_unfused.cuh"
 
 namespace ila {
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(32) qr_forward_c64_kernel(QrC64FwdArgs A)
         else {
             const cplx qt = mk(__dmul_rn(gq[rr].re, (double)t), __dmul_rn(gq[rr].im, (double)t));
             v = zadd(gp[rr], qt);
-            if (gr[rr] != 1.0) v = mk(__ddiv_rn(v.re, gr[rr]), __ddiv_rn(v.im, gr[rr]));
+            if (gr[rr] != 1.0) v = mk(ediv(v.re, gr[rr]), ediv(v.im, gr[rr]));
         }
         if (rr == U) v = zsub(v, shift);
         return v;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(32) qr_forward_c64_kernel(QrC64FwdArgs A)
                     bool nan = false;
 #pragma unroll
                     for (int i = 0; i < NR; i++) {
-                        const double a = __dsqrt_rn(zabs2(bw[i]));
+                        const double a = esqrt(zabs2(bw[i]));
                         nan |= (a != a);
                         mx = (a > mx) ? a : mx;
                     }
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(32) qr_forward_c64_kernel(QrC64FwdArgs A)
                 double s = zabs2(W[0][0]);
 #pragma unroll
                 for (int i = 1; i < NR; i++) s = __dadd_rn(s, zabs2(W[0][i]));
-                const double normu = __dsqrt_rn(s);
+                const double normu = esqrt(s);
                 if (normu != 0.0) {
                     cplx xi1 = W[0][0];
                     const double nu = copysign(normu, xi1.re);
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(32) qr_forward_c64_kernel(QrC64FwdArgs A)
                     W[0][0] = mk(-nu, 0.0);
 #pragma unroll
                     for (int i = 1; i < NR; i++) W[0][i] = zdiv(W[0][i], xi1);
-                    tau = mk(__ddiv_rn(xi1.re, nu), __ddiv_rn(xi1.im, nu));
+                    tau = mk(ediv(xi1.re, nu), ediv(xi1.im, nu));
                 }
             }
             const cplx tauc = zconj(tau);
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(32) qr_forward_c64_kernel(QrC64FwdArgs A)
 #pragma unroll
                 for (int i = 1; i < NR; i++) bw[i] = zsub(bw[i], zmul(W[0][i], vB));
             }
-            anybig |= __dsqrt_rn(zabs2(bw[0])) > A.tol;
+            anybig |= esqrt(zabs2(bw[0])) > A.tol;
             // stream out row k of R and (Q'b)_k
 #pragma unroll
             for (int j = 0; j < NC; j++) dst[j * 32] = make_double2(W[j][0].re, W[j][0].im);

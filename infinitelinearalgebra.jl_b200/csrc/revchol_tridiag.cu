@@ -13,6 +13,7 @@
 // oracle's (oracle/ila_oracle_revchol.c) bit for bit.
 #include "ila_common.cuh"
 #include "ila_kernels.cuh"
+#include "ila_exact.cuh"
 
 namespace ila {
 
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(32) revchol_tridiag_kernel(RevCholArgs A)
     auto gen = [&](const double (&g)[5], int64_t k) -> double {
         const double num = __dadd_rn(g[1], __dmul_rn(g[2], (double)k));
         const double den = __dadd_rn(g[3], __dmul_rn(g[4], (double)k));
-        return __dadd_rn(g[0], __ddiv_rn(num, den));
+        return __dadd_rn(g[0], ediv(num, den));
     };
     auto av = [&](int64_t k) -> double { return __dsub_rn(k < hp ? A.a_head[k] : gen(ga, k), shift); };
     auto bv = [&](int64_t k) -> double { return k < hp ? A.b_head[k] : gen(gb, k); };
@@ -45,16 +46,16 @@ __global__ void __launch_bounds__(32) revchol_tridiag_kernel(RevCholArgs A)
         N *= 2;
         const double aN = av(N - 1);
         if (!(aN >= 0.0)) { st = ILA_NOT_POSDEF; break; }
-        double la_next = __dsqrt_rn(aN);
-        double nu = __ddiv_rn(1.0, la_next);
+        double la_next = esqrt(aN);
+        double nu = ediv(1.0, la_next);
         double xi = 0.0;
         bool bad = false;
         for (int64_t i = N - 1; i >= 1; i--) {     // 1-based row i
-            const double lb = __ddiv_rn(bv(i - 1), la_next);
+            const double lb = ediv(bv(i - 1), la_next);
             const double t = __dsub_rn(av(i - 1), __dmul_rn(lb, lb));
             if (!(t >= 0.0)) { bad = true; break; }
-            const double la = __dsqrt_rn(t);
-            const double ratio = -__ddiv_rn(lb, la);
+            const double la = esqrt(t);
+            const double ratio = -ediv(lb, la);
             if (i > n) {
                 nu = __dmul_rn(nu, ratio);
             } else if (i == n) {
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(32) revchol_tridiag_kernel(RevCholArgs A)
         if (bad) { st = ILA_NOT_POSDEF; break; }
         const double bN = bv(N - 1);
         const double scale = (bN == 0.0) ? 1.0 : fabs(bN);
-        if (__dmul_rn(scale, __dsqrt_rn(xi)) <= eps) break;
+        if (__dmul_rn(scale, esqrt(xi)) <= eps) break;
     }
     if (st == ILA_NOT_POSDEF) {
         const double qnan = __longlong_as_double(0x7ff8000000000000LL);
