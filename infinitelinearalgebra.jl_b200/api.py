@@ -65,6 +65,13 @@ class Affine:
         return (self.p + self.q * k) / self.r
 
 
+class Rational:
+    """Entry k (k = 0, 1, ...) = c0 + (p + q*k)/(r + s*k) — e.g. `1 ./ (2:∞)` = Rational(0, 1, 0, 2, 1)."""
+
+    def __init__(self, c0=0.0, p=0.0, q=0.0, r=1.0, s=0.0):
+        self.c = (c0, p, q, r, s)
+
+
 def Fill(v):
     return Affine(v, 0.0, 1.0)
 
@@ -102,7 +109,7 @@ class BandedMatrix:
     """∞ banded operator given by its diagonals `{d: diag}` (d = col - row, as in `BandedMatrix(d => v)`)."""
 
     def __init__(self, diags: dict, shift=0.0):
-        self.diags = {int(d): (v if isinstance(v, (Affine, Vcat)) or type(v).__name__ == "Rational" else Fill(v)) for d, v in diags.items()}
+        self.diags = {int(d): (v if isinstance(v, (Affine, Rational, Vcat)) else Fill(v)) for d, v in diags.items()}
         self.shift = shift
 
     @property
@@ -406,13 +413,6 @@ def cholesky(S):
 
 
 # ---- reversecholesky (symmetric tridiagonal) ------------------------------------------------------------------
-
-class Rational:
-    """Entry k (k = 0, 1, ...) = c0 + (p + q*k)/(r + s*k) — e.g. `1 ./ (2:∞)` = Rational(0, 1, 0, 2, 1)."""
-
-    def __init__(self, c0=0.0, p=0.0, q=0.0, r=1.0, s=0.0):
-        self.c = (c0, p, q, r, s)
-
 
 def _gen5(v):
     if isinstance(v, Rational):
