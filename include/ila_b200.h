@@ -261,6 +261,38 @@ int ila_ql_finite_section_c64(int l, int u, int64_t batch, const ila_c64 *g, con
                               int64_t j, double tol, int64_t maxN, ila_c64 *Lband, ila_c64 *V, ila_c64 *tau, int64_t *N_used,
                               int32_t *status, int ngpus);
 
+/* ---- K10: tridiagonal conjugation  Y = Tridiagonal(U*X/U)  and bidiagonal conjugation ---------------------
+ * Replaces upper_mul_tri_triview! / tri_mul_invupper_triview! and TridiagonalConjugationData + resizedata!
+ * (src/banded/tridiagonalconjugation.jl:10-111, 114-215, 224-282): U upper triangular banded (the R of qr(A), the U of
+ * cholesky(S), or a connection matrix), X tridiagonal (a Jacobi matrix); the Jacobi matrix of the modified weight is the
+ * tridiagonal part of U*X*inv(U).  Every row is computed independently from rows k-1, k, k+1 of U with the reference's
+ * operation order (bit-identical to its two sequential sweeps).
+ *   U      batch x nbands x uld: U[(i*nbands + d)*uld + k] = U_i[k+1, k+1+d] (0-based k; nbands = 2 or 3), uld >= n+1
+ *   X      3 x xld (x_shared != 0) or batch x 3 x xld: rows dl (X[k+2,k+1]), d (X[k+1,k+1]), du (X[k+1,k+2]), xld >= n+1
+ *   Y      batch x 3 x n: rows dl, d, du of Y (what resizedata!(data, n) makes valid); UX_opt the same for Tridiagonal(U*X). */
+int ila_triconj_bands_f64(int nbands, int64_t batch, int64_t n, const double *U, int64_t uld, const double *X, int64_t xld,
+                          int x_shared, double *Y, double *UX_opt, int ngpus);
+int ila_triconj_bands_f64_dev(int nbands, int64_t batch, int64_t n, const double *d_U, int64_t uld, const double *d_X,
+                              int64_t xld, int x_shared, double *d_Y, double *d_UX_opt, void *stream);
+/* U read straight from the device-resident factor records of ila_qr_banded_factor_f64_dev / ila_chol_banded_factor_f64_dev
+ * (nch = 16-byte chunks per record: qr records ((l+u+1)+1 [+ l+1 reflector entries] rounded up to even)/2); the factorization
+ * must have swept at least n+1 columns.  Rows of operators whose d_status is not 0 are NaN (d_status may be NULL). */
+int ila_triconj_records_f64_dev(int nbands, int nch, int64_t batch, int64_t n, const int64_t *d_gbase, const void *d_work,
+                                const int32_t *d_status, const double *d_X, int64_t xld, int x_shared, double *d_Y, void *stream);
+/* cholesky(S_i).U -> Y_i in one call, U never leaves the device (TridiagonalConjugation(cholesky(S).U, X), e.g. S = W(X) a
+ * polynomial weight modification or S = shift_i*I - X): operator description as in ila_chol_banded_solve_f64.  The
+ * Cholesky blocking is two blocks of ceil((n+3)/2)+... columns (upstream the partition follows the caller's access
+ * history — 100 columns at construction, tridiagonalconjugation.jl:244 — so bits at block edges are not defined upstream);
+ * status 4 = not positive definite (rows NaN). */
+int ila_chol_triconj_f64(int u, int64_t batch, const double *p, const double *q, const double *r, const double *shift,
+                         int hp, const double *head, int64_t n, const double *X, int64_t xld, int x_shared, double *Y,
+                         int32_t *status, int ngpus);
+/* BidiagonalConjugation(U, X, V, uplo) (src/banded/bidiagonalconjugation.jl:19-60): bidiagonal part of inv(U)*X*V from the
+ * tridiagonal parts of U and C = X*V: U, C batch x 3 x ld with rows sub-diagonal ([k+2,k+1]), diagonal, super-diagonal
+ * ([k+1,k+2]), ld >= n+1.  upper != 0: dv[k] = B[k+1,k+1], ev[k] = B[k+1,k+2]; else ev[k] = B[k+2,k+1]; both batch x n. */
+int ila_biconj_bands_f64(int upper, int64_t batch, int64_t n, const double *U, const double *C, int64_t ld, double *dv,
+                         double *ev, int ngpus);
+
 #ifdef __cplusplus
 }
 #endif

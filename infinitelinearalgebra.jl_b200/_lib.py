@@ -68,6 +68,12 @@ SIGNATURES = {
     "ila_qr_banded_solve_c64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp,
                                           C.c_double, C.c_int, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int]),
     "ila_revchol_tridiag_f64": (C.c_int, [C.c_int64, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int]),
+    "ila_triconj_bands_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int]),
+    "ila_triconj_bands_f64_dev": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, _vp, _vp]),
+    "ila_triconj_records_f64_dev": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, _vp]),
+    "ila_chol_triconj_f64": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, C.c_int,
+                                       _vp, _vp, C.c_int]),
+    "ila_biconj_bands_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, C.c_int]),
     "ila_release": (C.c_int, []),
     "ila_ql_finite_section_f64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_double, C.c_int64,
                                             _vp, _vp, _vp, _vp, _vp, C.c_int]),

@@ -395,6 +395,55 @@ def ql_finite_section(l, u, g, j=50, shift=None, head=None, tol=np.finfo(np.floa
     return dict(Lband=Lband, V=V, tau=tau, N=N, status=status)
 
 
+def tridiagonal_conjugation(U, X, n, want_ux=False, ngpus=1):
+    """Y = Tridiagonal(U*X/U), batched (reference src/banded/tridiagonalconjugation.jl: TridiagonalConjugationData +
+    resizedata!(data, n)).  U: (batch x) nbands x m bands, U[d, k] = U[k+1, k+1+d] (nbands 2 or 3); X: 3 x m (shared) or
+    batch x 3 x m with rows dl, d, du; m >= n+1.  Returns Y (batch x 3 x n: dl, d, du) [and UX = Tridiagonal(U*X)]."""
+    U = np.ascontiguousarray(np.asarray(U, dtype=np.float64))
+    if U.ndim == 2:
+        U = U[None]
+    X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+    batch, nbands, uld = U.shape
+    shared = X.ndim == 2
+    assert shared or X.shape[0] == batch
+    n = int(n)
+    Y = np.empty((batch, 3, n)); UX = np.empty((batch, 3, n)) if want_ux else None
+    check(lib().ila_triconj_bands_f64(nbands, batch, n, ptr(U), uld, ptr(X), X.shape[-1], 1 if shared else 0, ptr(Y), ptr(UX), ngpus))
+    return (Y, UX) if want_ux else Y
+
+
+def chol_tridiagonal_conjugation(u, p, q, X, n, r=None, shift=None, head=None, batch=None, ngpus=1):
+    """TridiagonalConjugation(cholesky(S_i).U, X) for a batch of symmetric positive definite banded operators (generators as
+    in `chol_banded_solve`), the factor staying on the device between the Cholesky sweep (K5) and the conjugation (K10).
+    Returns dict(Y (batch x 3 x n), status)."""
+    nd = u + 1
+    if batch is None:
+        batch = max(np.atleast_2d(np.asarray(p)).shape[0], 1 if shift is None else np.asarray(shift).size)
+    p, q, r, shift, hp, head = _op_arrays(nd, batch, p, q, r, shift, head)
+    X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+    shared = X.ndim == 2
+    assert shared or X.shape[0] == batch
+    n = int(n)
+    Y = np.empty((batch, 3, n)); status = np.zeros(batch, dtype=np.int32)
+    check(lib().ila_chol_triconj_f64(u, batch, ptr(p), ptr(q), ptr(r), ptr(shift), hp, ptr(head), n, ptr(X), X.shape[-1],
+                                     1 if shared else 0, ptr(Y), ptr(status), ngpus))
+    return dict(Y=Y, status=status)
+
+
+def bidiagonal_conjugation(U, Cm, n, uplo="U", ngpus=1):
+    """Bidiagonal part of inv(U)*X*V from the tridiagonal parts of U and C = X*V (reference
+    src/banded/bidiagonalconjugation.jl:19-60).  U, Cm: (batch x) 3 x m (sub, main, super), m >= n+1.  Returns dv, ev."""
+    U = np.ascontiguousarray(np.asarray(U, dtype=np.float64)); Cm = np.ascontiguousarray(np.asarray(Cm, dtype=np.float64))
+    if U.ndim == 2:
+        U = U[None]; Cm = Cm[None]
+    batch, _, ld = U.shape
+    assert Cm.shape == U.shape
+    n = int(n)
+    dv = np.empty((batch, n)); ev = np.empty((batch, n))
+    check(lib().ila_biconj_bands_f64(1 if uplo in ("U", ":U") else 0, batch, n, ptr(U), ptr(Cm), ld, ptr(dv), ptr(ev), ngpus))
+    return dv, ev
+
+
 def pentadiagonal_operator(sigma, eps=1e-4):
     """BASELINE config C4: S_σ = pentadiag(diag 6+σ+ε·k, ±1: -4, ±2: 1), upper bands in data-row order (+2, +1, 0)."""
     sigma = np.atleast_1d(np.asarray(sigma, dtype=np.float64))

@@ -583,6 +583,110 @@ int ila_revchol_tridiag_f64(int64_t batch, const double *ga, const double *gb, c
     return 0;
 }
 
+// ================================ K10: tridiagonal / bidiagonal conjugation ==============================
+
+int ila_triconj_bands_f64_dev(int nbands, int64_t batch, int64_t n, const double *d_U, int64_t uld, const double *d_X,
+                              int64_t xld, int x_shared, double *d_Y, double *d_UX_opt, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    if (batch < 0 || n < 1 || uld < n + 1 || xld < n + 1 || !d_U || !d_X || !d_Y) return set_error(ILA_ERR_ARG, "triconj_bands: bad arguments (bands need n+1 entries)");
+    TriConjArgs a{};
+    a.batch = batch; a.n = n; a.nbands = nbands; a.U = d_U; a.uld = uld; a.X = d_X; a.xld = xld; a.xstride = x_shared ? 0 : 3 * xld;
+    a.Y = d_Y; a.UX = d_UX_opt;
+    return launch_triconj(a, (cudaStream_t)stream);
+}
+
+int ila_triconj_records_f64_dev(int nbands, int nch, int64_t batch, int64_t n, const int64_t *d_gbase, const void *d_work,
+                                const int32_t *d_status, const double *d_X, int64_t xld, int x_shared, double *d_Y, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    if (batch < 0 || n < 1 || nch < 1 || 2 * nch < nbands || xld < n + 1 || !d_gbase || !d_work || !d_X || !d_Y)
+        return set_error(ILA_ERR_ARG, "triconj_records: bad arguments");
+    TriConjArgs a{};
+    a.batch = batch; a.n = n; a.nbands = nbands; a.gbase = d_gbase; a.work = (const double2 *)d_work; a.nch = nch; a.status = d_status;
+    a.X = d_X; a.xld = xld; a.xstride = x_shared ? 0 : 3 * xld; a.Y = d_Y;
+    return launch_triconj(a, (cudaStream_t)stream);
+}
+
+int ila_triconj_bands_f64(int nbands, int64_t batch, int64_t n, const double *U, int64_t uld, const double *X, int64_t xld,
+                          int x_shared, double *Y, double *UX_opt, int ngpus)
+{
+    if (batch < 0 || n < 1 || uld < n + 1 || xld < n + 1 || !U || !X || (batch > 0 && !Y)) return set_error(ILA_ERR_ARG, "triconj_bands: bad arguments (bands need n+1 entries)");
+    if (nbands != 2 && nbands != 3) return set_error(ILA_ERR_UNSUPPORTED, "triconj_bands: nbands must be 2 or 3");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int64_t per = (batch + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= batch ? per : batch - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        double *d_U, *d_X, *d_Y, *d_UX = nullptr;
+        const size_t xcount = (size_t)(x_shared ? 1 : cnt) * 3 * xld;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt * nbands * uld, &d_U))) return rc;
+        if ((rc = dev_buf_t(pd, 1, xcount, &d_X))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt * 3 * n, &d_Y))) return rc;
+        if (UX_opt && (rc = dev_buf_t(pd, 3, (size_t)cnt * 3 * n, &d_UX))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_U, U + lo * nbands * uld, sizeof(double) * cnt * nbands * uld, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_X, X + (x_shared ? 0 : lo * 3 * xld), sizeof(double) * xcount, cudaMemcpyHostToDevice, s));
+        if ((rc = ila_triconj_bands_f64_dev(nbands, cnt, n, d_U, uld, d_X, xld, x_shared, d_Y, d_UX, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(Y + lo * 3 * n, d_Y, sizeof(double) * cnt * 3 * n, cudaMemcpyDeviceToHost, s));
+        if (UX_opt) ILA_CUDA_CHECK(cudaMemcpyAsync(UX_opt + lo * 3 * n, d_UX, sizeof(double) * cnt * 3 * n, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
+int ila_biconj_bands_f64(int upper, int64_t batch, int64_t n, const double *U, const double *Cm, int64_t ld, double *dv,
+                         double *ev, int ngpus)
+{
+    if (batch < 0 || n < 1 || ld < n + 1 || !U || !Cm || (batch > 0 && (!dv || !ev))) return set_error(ILA_ERR_ARG, "biconj_bands: bad arguments (bands need n+1 entries)");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int64_t per = (batch + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= batch ? per : batch - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        double *d_U, *d_C, *d_dv, *d_ev;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt * 3 * ld, &d_U))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt * 3 * ld, &d_C))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt * n, &d_dv))) return rc;
+        if ((rc = dev_buf_t(pd, 3, (size_t)cnt * n, &d_ev))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_U, U + lo * 3 * ld, sizeof(double) * cnt * 3 * ld, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_C, Cm + lo * 3 * ld, sizeof(double) * cnt * 3 * ld, cudaMemcpyHostToDevice, s));
+        BiConjArgs a{cnt, n, ld, upper ? 1 : 0, d_U, d_C, d_dv, d_ev};
+        if ((rc = launch_biconj(a, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(dv + lo * n, d_dv, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(ev + lo * n, d_ev, sizeof(double) * cnt * n, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
 // ================================ K9: adaptive finite-section QL =========================================
 
 } // extern "C" (templates below have C++ linkage)
@@ -1169,6 +1273,84 @@ int ila_chol_banded_solve_f64(int u, int64_t batch, const double *p, const doubl
     if (u < 1) return set_error(ILA_ERR_UNSUPPORTED, "chol_banded_solve: u == 0 (diagonal operator) is not on the accelerated path");
     return banded_solve_host(1, 0, u, batch, p, q, r, shift, hp, head, nb, b, tol, colgrowth, ncap, ncap_per, x, xcap, xoff,
                              ncols, nconv, factors_opt, nullptr, y_opt, status, ngpus);
+}
+
+// K5 -> K10 fused behind the device-resident factor records: cholesky(S_i).U never leaves the device.
+// The Cholesky sweep is driven through its adaptive entry with b = e1 and an infinite tolerance, so that the convergence test
+// passes at the first opportunity (column colgrowth+1) and full_sweep factorizes 2*colgrowth + u >= n + 3 columns; the
+// blocking of partialcholesky! is then two blocks of colgrowth (+u) columns (upstream the partition depends on the
+// caller's access history: 100 columns at construction, then up to n+3 — tridiagonalconjugation.jl:244-245, 276).
+int ila_chol_triconj_f64(int u, int64_t batch, const double *p, const double *q, const double *r, const double *shift,
+                         int hp, const double *head, int64_t n, const double *X, int64_t xld, int x_shared, double *Y,
+                         int32_t *status, int ngpus)
+{
+    if (batch < 0 || n < 1 || hp < 0 || !p || !q || !X || xld < n + 1 || (hp > 0 && !head) || (batch > 0 && (!Y || !status)))
+        return set_error(ILA_ERR_ARG, "chol_triconj: bad arguments (X bands need n+1 entries)");
+    if (u < 1 || u > 4) return set_error(ILA_ERR_UNSUPPORTED, "chol_triconj: upper bandwidth u must be in 1..4");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int nd = u + 1;
+    const int64_t cg = (n + 4) / 2, ncap = 2 * cg + 3 * u + 2;
+    const int nch = qr_record_doubles(0, u, false) / 2;
+    const double one = 1.0;
+    const int64_t per = (batch + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= batch ? per : batch - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        std::vector<int64_t> gbase((cnt + 31) / 32 + 1);
+        int64_t work_bytes = 0, xi_bytes = 0;
+        ila_qr_banded_work_layout(0, u, cnt, ncap, nullptr, gbase.data(), &work_bytes, &xi_bytes);
+        std::vector<double> bvec((size_t)cnt, one);
+        double *d_p, *d_q, *d_r = nullptr, *d_shift = nullptr, *d_head = nullptr, *d_b, *d_X, *d_Y;
+        int64_t *d_gbase, *d_ncols, *d_nconv, *d_nswept, *d_xoff;
+        int32_t *d_status;
+        char *d_work;
+        const size_t xcount = (size_t)(x_shared ? 1 : cnt) * 3 * xld;
+        if ((rc = dev_buf_t(pd, 4, (size_t)cnt * nd, &d_p))) return rc;
+        if ((rc = dev_buf_t(pd, 5, (size_t)cnt * nd, &d_q))) return rc;
+        if (r && (rc = dev_buf_t(pd, 6, (size_t)cnt * nd, &d_r))) return rc;
+        if (shift && (rc = dev_buf_t(pd, 7, (size_t)cnt, &d_shift))) return rc;
+        if (hp > 0 && (rc = dev_buf_t(pd, 8, (size_t)nd * hp, &d_head))) return rc;
+        if ((rc = dev_buf_t(pd, 9, (size_t)cnt, &d_b))) return rc;
+        if ((rc = dev_buf_t(pd, 10, gbase.size(), &d_gbase))) return rc;
+        if ((rc = dev_buf_t(pd, 11, (size_t)cnt, &d_ncols))) return rc;
+        if ((rc = dev_buf_t(pd, 12, (size_t)cnt, &d_nconv))) return rc;
+        if ((rc = dev_buf_t(pd, 13, (size_t)cnt, &d_nswept))) return rc;
+        if ((rc = dev_buf_t(pd, 14, (size_t)cnt + 1, &d_xoff))) return rc;
+        if ((rc = dev_buf_t(pd, 15, (size_t)cnt, &d_status))) return rc;
+        if ((rc = dev_buf_t(pd, 16, (size_t)work_bytes, &d_work))) return rc;
+        if ((rc = dev_buf_t(pd, 1, xcount, &d_X))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt * 3 * n, &d_Y))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_p, p + lo * nd, sizeof(double) * cnt * nd, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_q, q + lo * nd, sizeof(double) * cnt * nd, cudaMemcpyHostToDevice, s));
+        if (r) ILA_CUDA_CHECK(cudaMemcpyAsync(d_r, r + lo * nd, sizeof(double) * cnt * nd, cudaMemcpyHostToDevice, s));
+        if (shift) ILA_CUDA_CHECK(cudaMemcpyAsync(d_shift, shift + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+        if (hp > 0) ILA_CUDA_CHECK(cudaMemcpyAsync(d_head, head, sizeof(double) * nd * hp, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_b, bvec.data(), sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_gbase, gbase.data(), sizeof(int64_t) * gbase.size(), cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_X, X + (x_shared ? 0 : lo * 3 * xld), sizeof(double) * xcount, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(s));     // bvec / gbase are stack-scoped host buffers
+        if ((rc = ila_chol_banded_factor_f64_dev(u, cnt, d_p, d_q, d_r, d_shift, hp, d_head, 1, d_b, HUGE_VAL, (int)cg, ncap, nullptr,
+                                                 d_gbase, d_work, d_ncols, d_nconv, d_nswept, d_xoff, d_status, 1, s))) return rc;
+        if ((rc = ila_triconj_records_f64_dev(u + 1 > 3 ? 3 : u + 1, nch, cnt, n, d_gbase, d_work, d_status, d_X, xld, x_shared, d_Y, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(Y + lo * 3 * n, d_Y, sizeof(double) * cnt * 3 * n, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_status, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
 }
 
 } // extern "C"

@@ -92,6 +92,31 @@ struct RevCholArgs {
 };
 int launch_revchol_tridiag(const RevCholArgs &a, cudaStream_t s);
 
+// from triconj.cu
+struct TriConjArgs {
+    int64_t batch, n;
+    int nbands;               // 2 or 3 leading entries of every row of U are used (U[k,k], U[k,k+1], U[k,k+2])
+    // source 0: explicit bands U[i][d][k] (uld entries per band)
+    const double *U;
+    int64_t uld;
+    // source 1 (work != NULL): K1 / K5 factor records, nch 16-byte chunks per record
+    const int64_t *gbase;
+    const double2 *work;
+    int nch;
+    const int32_t *status;    // per-operator status of the factorization (rows of failed operators are NaN) or NULL
+    const double *X;          // [dl; d; du], xld entries per band; xstride = 0 (shared) or 3*xld
+    int64_t xld, xstride;
+    double *Y, *UX;           // batch x 3 x n (dl, d, du); UX optional (source 0 only)
+};
+int launch_triconj(const TriConjArgs &a, cudaStream_t s);
+struct BiConjArgs {
+    int64_t batch, n, ld;
+    int upper;
+    const double *U, *C;      // batch x 3 x ld: sub-, main, super-diagonal of U and of C = X*V
+    double *dv, *ev;          // batch x n
+};
+int launch_biconj(const BiConjArgs &a, cudaStream_t s);
+
 // from ql_finite_section.cu
 template <typename T>
 struct FsqlArgsT {

@@ -23,7 +23,7 @@ _sp = C.POINTER(C.c_int32)
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the recipe in oracle/Makefile."""
-    src = [os.path.join(_HERE, f) for f in ("ila_oracle.c", "ila_oracle_impl.h", "ila_oracle_c64.c", "ila_oracle_revchol.c", "ila_oracle_fsql.c", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ila_oracle.c", "ila_oracle_impl.h", "ila_oracle_c64.c", "ila_oracle_revchol.c", "ila_oracle_fsql.c", "ila_oracle_triconj.c", "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
@@ -218,6 +218,38 @@ def chol_banded_solve(u, p, q, r=None, shift=None, head=None, b=(1.0,), tol=np.f
         C.c_int64(ldx), _ptr(x, _dp), _ptr(ncols, _ip), _ptr(nconv, _ip), _ptr(fac, _dp), _ptr(y, _dp),
         _ptr(status, _sp), C.c_int(nthreads))
     return out
+
+
+def tridiagonal_conjugation(U, X, n, want_ux=False, nthreads=0):
+    """Y = Tridiagonal(U*X/U) by the reference's two sequential sweeps (oracle/ila_oracle_triconj.c;
+    src/banded/tridiagonalconjugation.jl:10-215, 260-282).  U: (batch x) nbands x m bands (U[d, k] = U[k+1, k+1+d]),
+    X: 3 x m shared or batch x 3 x m (dl, d, du), m >= n+1.  Returns Y (batch x 3 x n) [and UX]."""
+    U = np.ascontiguousarray(np.asarray(U, dtype=np.float64))
+    if U.ndim == 2:
+        U = U[None]
+    X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+    batch, nbands, uld = U.shape
+    shared = X.ndim == 2
+    xld = X.shape[-1]
+    assert uld >= n + 1 and xld >= n + 1 and nbands in (2, 3)
+    Y = np.zeros((batch, 3, n)); UX = np.zeros((batch, 3, n)) if want_ux else None
+    lib().ila_oracle_triconj_f64(C.c_int(nbands), C.c_int64(batch), C.c_int64(n), _ptr(U, _dp), C.c_int64(uld), _ptr(X, _dp),
+                                 C.c_int64(xld), C.c_int64(0 if shared else 3 * xld), _ptr(Y, _dp), _ptr(UX, _dp), C.c_int(nthreads))
+    return (Y, UX) if want_ux else Y
+
+
+def bidiagonal_conjugation(U, Cm, n, uplo="U", nthreads=0):
+    """Bidiagonal part of inv(U)*C (C = X*V) from the tridiagonal parts of U and C (src/banded/bidiagonalconjugation.jl:37-60).
+    U, Cm: (batch x) 3 x m (sub, main, super), m >= n+1.  Returns dv, ev (batch x n)."""
+    U = np.ascontiguousarray(np.asarray(U, dtype=np.float64)); Cm = np.ascontiguousarray(np.asarray(Cm, dtype=np.float64))
+    if U.ndim == 2:
+        U = U[None]; Cm = Cm[None]
+    batch, _, ld = U.shape
+    assert Cm.shape == U.shape and ld >= n + 1
+    dv = np.zeros((batch, n)); ev = np.zeros((batch, n))
+    lib().ila_oracle_biconj_f64(C.c_int(1 if uplo == "U" else 0), C.c_int64(batch), C.c_int64(n), _ptr(U, _dp), C.c_int64(ld),
+                                _ptr(Cm, _dp), _ptr(dv, _dp), _ptr(ev, _dp), C.c_int(nthreads))
+    return dv, ev
 
 
 def num_threads() -> int:
