@@ -293,6 +293,24 @@ int ila_chol_triconj_f64(int u, int64_t batch, const double *p, const double *q,
 int ila_biconj_bands_f64(int upper, int64_t batch, int64_t n, const double *U, const double *C, int64_t ld, double *dv,
                          double *ev, int ngpus);
 
+/* ---- K11: adaptive block-banded QR solve for ∞ operators with block sizes 1, 2, 3, ... ----------------------
+ * Replaces qr(A) \ b for block-banded A: AdaptiveQRData(::AbstractBlockLayout) (src/infqr.jl:23-28), partialqr!(F, ::Block)
+ * -> _blockbanded_qr! (:68-86), the Q'b driver with COLGROWTH = 300 and tolerance 1e-30 (:303-337), resizedata_chop!
+ * (:221-232) and the block back-substitution (:358-366).
+ * Operator i:  L_i = alpha[i] KronTrav(T1, I) + beta[i] KronTrav(I, T2) - lam[i] I,  T1, T2 tridiagonal, shared by the batch
+ * as 3 x tld bands (rows dl: T[k+2,k+1], d: T[k+1,k+1], du: T[k+1,k+2]; tld >= maxblocks+1); block K holds K entries and
+ * KronTrav(A,B)[Block(K,J)][k,j] = A[k,j] B[K-k+1,J-j+1] — the operators of test/test_infqr.jl:270-313 (Δ ⊗ I - 2I, I ⊗ Δ - 2I,
+ * their sum, 2X + Y - 8I).
+ *   b        batch x nb non-zero prefixes of the right-hand sides; tol, colgrowth: the reference's 1e-30 and 300
+ *   maxblocks  capacity in blocks, 3..64 (the active panel lives in shared memory); status 3 when it is reached
+ *   x        batch x xld, zero padded (xld >= maxblocks(maxblocks+1)/2); ncols[i] = length of the solution (the reference's
+ *            datasize after the chop); nblocks[i] = block columns whose reflectors were applied to b
+ *   qtb_opt  NULL or batch x xld: Q'b before the chop ((F.Q'*b)[1:6] of test_infqr.jl:276). */
+int ila_qr_blockbanded_solve_f64(int64_t batch, const double *alpha, const double *beta, const double *lam, const double *T1,
+                                 const double *T2, int64_t tld, int nb, const double *b, double tol, int colgrowth,
+                                 int maxblocks, double *x, int64_t xld, int64_t *ncols, int32_t *nblocks, double *qtb_opt,
+                                 int32_t *status, int ngpus);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,8 @@ SIGNATURES = {
     "ila_chol_triconj_f64": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, C.c_int,
                                        _vp, _vp, C.c_int]),
     "ila_biconj_bands_f64": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, C.c_int]),
+    "ila_qr_blockbanded_solve_f64": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_double, C.c_int,
+                                               C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int]),
     "ila_release": (C.c_int, []),
     "ila_ql_finite_section_f64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_double, C.c_int64,
                                             _vp, _vp, _vp, _vp, _vp, C.c_int]),

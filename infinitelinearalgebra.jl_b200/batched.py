@@ -444,6 +444,34 @@ def bidiagonal_conjugation(U, Cm, n, uplo="U", ngpus=1):
     return dv, ev
 
 
+def qr_blockbanded_solve(T1, T2, alpha, beta, lam, b=(1.0,), tol=1e-30, colgrowth=300, maxblocks=64, want_qtb=False, ngpus=1):
+    """Adaptive block-banded QR solve, batched over (alpha, beta, lam) (reference src/infqr.jl:23-28, 68-86, 303-337, 358-366;
+    test/test_infqr.jl:270-313):  (alpha KronTrav(T1, I) + beta KronTrav(I, T2) - lam I) \\ [b; 0; ...]  with T1, T2 tridiagonal
+    (3 x m bands dl, d, du, m >= maxblocks+1) and block sizes 1, 2, 3, ...  Returns dict(x (batch x maxblocks(maxblocks+1)/2,
+    zero padded), ncols, nblocks, status[, qtb])."""
+    alpha = np.atleast_1d(np.asarray(alpha, dtype=np.float64)); beta = np.atleast_1d(np.asarray(beta, dtype=np.float64))
+    lam = np.atleast_1d(np.asarray(lam, dtype=np.float64))
+    batch = max(alpha.size, beta.size, lam.size)
+    alpha = np.ascontiguousarray(np.broadcast_to(alpha, (batch,))); beta = np.ascontiguousarray(np.broadcast_to(beta, (batch,)))
+    lam = np.ascontiguousarray(np.broadcast_to(lam, (batch,)))
+    T1 = np.ascontiguousarray(np.asarray(T1, dtype=np.float64)); T2 = np.ascontiguousarray(np.asarray(T2, dtype=np.float64))
+    assert T1.shape == T2.shape and T1.shape[0] == 3
+    b = np.asarray(b, dtype=np.float64)
+    if b.ndim == 1:
+        b = np.broadcast_to(b, (batch, b.shape[0]))
+    b = np.ascontiguousarray(b)
+    xld = maxblocks * (maxblocks + 1) // 2
+    x = np.empty((batch, xld)); qtb = np.empty((batch, xld)) if want_qtb else None
+    ncols = np.zeros(batch, dtype=np.int64); nblocks = np.zeros(batch, dtype=np.int32); status = np.zeros(batch, dtype=np.int32)
+    check(lib().ila_qr_blockbanded_solve_f64(batch, ptr(alpha), ptr(beta), ptr(lam), ptr(T1), ptr(T2), T1.shape[1], b.shape[1], ptr(b),
+                                             float(tol), int(colgrowth), int(maxblocks), ptr(x), xld, ptr(ncols), ptr(nblocks),
+                                             ptr(qtb), ptr(status), ngpus))
+    out = dict(x=x, ncols=ncols, nblocks=nblocks, status=status)
+    if want_qtb:
+        out["qtb"] = qtb
+    return out
+
+
 def pentadiagonal_operator(sigma, eps=1e-4):
     """BASELINE config C4: S_σ = pentadiag(diag 6+σ+ε·k, ±1: -4, ±2: 1), upper bands in data-row order (+2, +1, 0)."""
     sigma = np.atleast_1d(np.asarray(sigma, dtype=np.float64))

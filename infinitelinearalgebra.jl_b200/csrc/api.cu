@@ -687,6 +687,76 @@ int ila_biconj_bands_f64(int upper, int64_t batch, int64_t n, const double *U, c
     return 0;
 }
 
+// ================================ K11: adaptive block-banded QR solve ====================================
+
+int ila_qr_blockbanded_solve_f64(int64_t batch, const double *alpha, const double *beta, const double *lam, const double *T1,
+                                 const double *T2, int64_t tld, int nb, const double *b, double tol, int colgrowth,
+                                 int maxblocks, double *x, int64_t xld, int64_t *ncols, int32_t *nblocks, double *qtb_opt,
+                                 int32_t *status, int ngpus)
+{
+    if (batch < 0 || !alpha || !beta || !lam || !T1 || !T2 || nb < 1 || !b || colgrowth < 1 ||
+        (batch > 0 && (!x || !ncols || !nblocks || !status)))
+        return set_error(ILA_ERR_ARG, "qr_blockbanded_solve: bad arguments");
+    if (maxblocks < 3 || maxblocks > 64) return set_error(ILA_ERR_UNSUPPORTED, "qr_blockbanded_solve: maxblocks must be in 3..64 (the panel lives in shared memory)");
+    const int64_t nmax = (int64_t)maxblocks * (maxblocks + 1) / 2;
+    if (tld < maxblocks + 1 || xld < nmax || nb > nmax) return set_error(ILA_ERR_ARG, "qr_blockbanded_solve: need tld >= maxblocks+1, xld >= maxblocks(maxblocks+1)/2 >= nb");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int64_t per = (batch + G - 1) / G;
+    const int64_t wstride = (int64_t)(maxblocks - 1) * maxblocks * (maxblocks + 1);
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= batch ? per : batch - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        double *d_al, *d_be, *d_la, *d_T1, *d_T2, *d_b, *d_work, *d_qtb, *d_x;
+        int64_t *d_ncols;
+        int32_t *d_nblk, *d_st;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt, &d_al))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt, &d_be))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_la))) return rc;
+        if ((rc = dev_buf_t(pd, 3, (size_t)3 * tld, &d_T1))) return rc;
+        if ((rc = dev_buf_t(pd, 4, (size_t)3 * tld, &d_T2))) return rc;
+        if ((rc = dev_buf_t(pd, 5, (size_t)cnt * nb, &d_b))) return rc;
+        if ((rc = dev_buf_t(pd, 16, (size_t)cnt * wstride, &d_work))) return rc;
+        if ((rc = dev_buf_t(pd, 6, (size_t)cnt * xld, &d_qtb))) return rc;
+        if ((rc = dev_buf_t(pd, 7, (size_t)cnt * xld, &d_x))) return rc;
+        if ((rc = dev_buf_t(pd, 8, (size_t)cnt, &d_ncols))) return rc;
+        if ((rc = dev_buf_t(pd, 9, (size_t)cnt, &d_nblk))) return rc;
+        if ((rc = dev_buf_t(pd, 10, (size_t)cnt, &d_st))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_al, alpha + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_be, beta + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_la, lam + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_T1, T1, sizeof(double) * 3 * tld, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_T2, T2, sizeof(double) * 3 * tld, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_b, b + lo * nb, sizeof(double) * cnt * nb, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemsetAsync(d_qtb, 0, sizeof(double) * cnt * xld, s));
+        BlockQrArgs a{};
+        a.batch = cnt; a.alpha = d_al; a.beta = d_be; a.lam = d_la; a.T1 = d_T1; a.T2 = d_T2; a.tld = tld; a.b = d_b; a.nb = nb;
+        a.tol = tol; a.colgrowth = colgrowth; a.maxblocks = maxblocks; a.work = d_work; a.work_stride = wstride; a.qtb = d_qtb;
+        a.x = d_x; a.xld = xld; a.ncols = d_ncols; a.nblocks = d_nblk; a.status = d_st;
+        if ((rc = launch_qr_blockbanded(a, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(x + lo * xld, d_x, sizeof(double) * cnt * xld, cudaMemcpyDeviceToHost, s));
+        if (qtb_opt) ILA_CUDA_CHECK(cudaMemcpyAsync(qtb_opt + lo * xld, d_qtb, sizeof(double) * cnt * xld, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(ncols + lo, d_ncols, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(nblocks + lo, d_nblk, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
 // ================================ K9: adaptive finite-section QL =========================================
 
 } // extern "C" (templates below have C++ linkage)

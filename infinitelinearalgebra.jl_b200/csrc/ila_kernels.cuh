@@ -117,6 +117,26 @@ struct BiConjArgs {
 };
 int launch_biconj(const BiConjArgs &a, cudaStream_t s);
 
+// from qr_blockbanded.cu
+struct BlockQrArgs {
+    int64_t batch;
+    const double *alpha, *beta, *lam;     // per operator: L = alpha KronTrav(T1,I) + beta KronTrav(I,T2) - lam I
+    const double *T1, *T2;                // shared 3 x tld bands (dl, d, du)
+    int64_t tld;
+    const double *b;                      // batch x nb
+    int nb;
+    double tol;
+    int colgrowth, maxblocks, hmax, wmax;
+    double *work;                         // batch x work_stride: R block rows
+    int64_t work_stride;
+    double *qtb, *x;                      // batch x xld
+    int64_t xld;
+    int64_t *ncols;
+    int32_t *nblocks, *status;
+};
+int qr_blockbanded_smem_bytes(int maxblocks, int *hmax_out, int *wmax_out);
+int launch_qr_blockbanded(BlockQrArgs a, cudaStream_t s);
+
 // from ql_finite_section.cu
 template <typename T>
 struct FsqlArgsT {

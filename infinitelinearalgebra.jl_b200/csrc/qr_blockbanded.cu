@@ -1,0 +1,298 @@
+// qr_blockbanded.cu — K11: adaptive block-banded QR solve for ∞ operators with block sizes 1, 2, 3, … (the KronTrav /
+// triangular-traversal operators of 2-D problems), one CTA per operator.
+//
+// Reference path replaced (InfiniteLinearAlgebra.jl v0.10.3):
+//   AdaptiveQRData(::AbstractBlockLayout, A)                 src/infqr.jl:23-28    block bandwidths (l, l+u)
+//   partialqr!(F, N::Block{1}) -> _blockbanded_qr!           src/infqr.jl:68-86    dense Householder QR of the rows of blocks
+//                                                            J..J+l per block column, applied to block columns J+1..J+l+u
+//   Q'b adaptive driver (COLGROWTH = 300, tolerance 1e-30)   src/infqr.jl:303-337
+//   resizedata_chop!(::BlockedVector, tol)                   src/infqr.jl:221-232
+//   ldiv!(R, B::BlockedArray)                                src/infqr.jl:358-366
+// Operator family: L_i = alpha_i KronTrav(T1, I) + beta_i KronTrav(I, T2) - lam_i I with T1, T2 tridiagonal (shared bands),
+// KronTrav(A, B)[Block(K,J)][k,j] = A[k,j] B[K-k+1,J-j+1]: block bandwidths (1,1), diagonal blocks diagonal, off-diagonal
+// blocks with two bands — every block-banded fixture of test/test_infqr.jl:270-313; the batch axis is (alpha, beta, lam),
+// e.g. the shifts of a 2-D resolvent.
+//
+// B200-first design (a different kernel class from K1: the work per operator is O(N^4) dense panel arithmetic, not a
+// scalar recurrence).  One CTA owns one operator.  The active panel — rows of blocks J, J+1, columns of blocks J..J+2 plus
+// the right-hand side as one more column, (2J+1) x (3J+4) doubles — lives in shared memory (up to 197 KB: the reason for
+// one CTA per SM) with CIRCULAR row and column indexing, so that moving from block column J to J+1 neither copies nor
+// shifts anything: the J+1 fresh rows of block J+2 are generated from (T1, T2, alpha, beta, lam) straight into the slots
+// the finished rows leave.  Per Householder column: warp 0 forms the norm with shuffles and publishes (tau, 1/(alpha-beta));
+// then one thread per trailing column does the dot product and the update (consecutive threads touch consecutive
+// shared-memory words; the reflector entry is a broadcast).  Q'b is the extra column, so the adaptive test (max|Q'b| over
+// the blocks J..J+l at the COLGROWTH cadence) is a shared-memory reduction — no host round trip.  Finished R rows stream
+// to the operator's slab of global memory (coalesced, L2-resident: ≤ 2.1 MB) and the back-substitution reads them back
+// block row by block row: warp-per-row dot products for the part right of the diagonal block, and ONE warp with the
+// diagonal block in shared memory and the right-hand side in registers for the triangular part (shuffle broadcast of each
+// new solution entry, no block-wide barrier inside a block row).
+#include "ila_common.cuh"
+#include "ila_kernels.cuh"
+
+namespace ila {
+
+namespace {
+
+__device__ __forceinline__ int bstart(int K) { return K * (K - 1) / 2; }            // 0-based first index of block K (1-based)
+__device__ __forceinline__ int findblock(int i)                                      // block holding the 1-based index i
+{
+    int K = (int)((sqrt(8.0 * (double)i + 1.0) - 1.0) * 0.5);
+    while (K * (K + 1) / 2 < i) K++;
+    while (K > 1 && (K - 1) * K / 2 >= i) K--;
+    return K;
+}
+
+constexpr int kThreads = 256;
+
+struct Panel {
+    double *P;        // HMAX x WMAX, row-major
+    double *bc;       // HMAX: the right-hand-side column
+    int hmask, wmax;
+    __device__ __forceinline__ int rs(int g) const { return g & hmask; }
+    __device__ __forceinline__ int cs(int c) const { return c % wmax; }
+    __device__ __forceinline__ double &at(int g, int c) { return P[rs(g) * wmax + cs(c)]; }
+};
+
+} // namespace
+
+__global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs A)
+{
+    extern __shared__ double smem[];
+    __shared__ double sc[4];
+    __shared__ int si[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t inst = blockIdx.x;
+    const int hmax = A.hmax, wmax = A.wmax;
+    Panel pn{smem, smem + (size_t)hmax * wmax, hmax - 1, wmax};
+    const double al = A.alpha[inst], be = A.beta[inst], lam = A.lam[inst];
+    const double *T1 = A.T1, *T2 = A.T2;
+    const int64_t tld = A.tld;
+    const double *bi = A.b + inst * A.nb;
+    const int nb = A.nb, cg = A.colgrowth, maxblocks = A.maxblocks;
+    double *Rw = A.work + inst * A.work_stride;
+    double *qtb = A.qtb + inst * A.xld;
+
+    // rows of block K (1-based) into the panel: zero the columns of blocks Klo..K+1, then the (at most five) entries per row
+    auto load_block_rows = [&](int K, int Klo) {
+        const int c_lo = bstart(Klo), c_hi = bstart(K + 2), w = c_hi - c_lo, r0 = bstart(K);
+        for (int idx = tid; idx < K * w; idx += kThreads) pn.at(r0 + idx / w, c_lo + idx % w) = 0.0;
+        __syncthreads();
+        if (tid < K) {
+            const int kk = tid + 1, g = r0 + tid;
+            pn.at(g, g) = al * T1[tld + kk - 1] + be * T2[tld + K - kk] - lam;
+            const int cn = bstart(K + 1);
+            pn.at(g, cn + kk) += al * T1[2 * tld + kk - 1];            // (kk, kk+1): T1[kk, kk+1]
+            pn.at(g, cn + kk - 1) += be * T2[2 * tld + K - kk];        // (kk, kk):   T2[K-kk+1, K-kk+2]
+            if (K > 1) {
+                const int cp = bstart(K - 1);
+                if (kk >= 2) pn.at(g, cp + kk - 2) += al * T1[kk - 2];            // (kk, kk-1): T1[kk, kk-1]
+                if (kk <= K - 1) pn.at(g, cp + kk - 1) += be * T2[K - kk - 1];    // (kk, kk):   T2[K-kk+1, K-kk]
+            }
+            pn.bc[pn.rs(g)] = g < nb ? bi[g] : 0.0;
+        }
+    };
+
+    int J0 = 1, J1 = findblock(cg), done = 0;
+    const int SB = findblock(nb);
+    int32_t st = ILA_OK;
+    load_block_rows(1, 1);
+    __syncthreads();
+
+    for (;;) {
+        // ---- adaptive test at the chunk start (infqr.jl:316-322): the rows of block J0+1 still hold raw b (zero past SB)
+        if (warp == 0) {
+            double mx = 0.0;
+            bool nan = false;
+            const int r0 = bstart(J0);
+            for (int k = lane; k < J0; k += 32) {
+                const double v = pn.bc[pn.rs(r0 + k)];
+                nan |= (v != v);
+                mx = fmax(mx, fabs(v));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            nan = __any_sync(0xffffffffu, nan);
+            if (lane == 0) si[0] = nan ? 2 : ((J0 > SB && mx <= A.tol) ? 1 : 0);
+        }
+        __syncthreads();
+        const int flag = si[0];
+        __syncthreads();
+        if (flag == 2) { st = ILA_NAN; break; }
+        if (flag == 1) break;
+        if (J1 + 1 > maxblocks) {
+            J1 = maxblocks - 1;
+            if (J1 < J0) { st = ILA_NOT_CONVERGED; break; }
+        }
+
+        for (int J = J0; J <= J1; J++) {
+            const int c0 = bstart(J), nrows = 2 * J + 1, ncols = 3 * J + 3;
+            // (a) fresh rows of block J+1; block column J+2 of the rows of block J starts at zero
+            {
+                const int c2 = bstart(J + 2), w2 = J + 2;
+                for (int idx = tid; idx < J * w2; idx += kThreads) pn.at(c0 + idx / w2, c2 + idx % w2) = 0.0;
+            }
+            load_block_rows(J + 1, J);
+            __syncthreads();
+            // (b) Householder QR of block column J
+            for (int j = 0; j < J; j++) {
+                const int c = c0 + j, m = nrows - j;          // pivot column, rows c .. c+m-1
+                const int csc = pn.cs(c);
+                if (warp == 0) {
+                    double ss = 0.0;
+                    for (int i = 1 + lane; i < m; i += 32) {
+                        const double v = pn.P[pn.rs(c + i) * wmax + csc];
+                        ss = fma(v, v, ss);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                    if (lane == 0) {
+                        double tau = 0.0, inv = 0.0;
+                        if (ss != 0.0) {
+                            const double alpha = pn.P[pn.rs(c) * wmax + csc];
+                            const double beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+                            tau = (beta - alpha) / beta;
+                            inv = 1.0 / (alpha - beta);
+                            pn.P[pn.rs(c) * wmax + csc] = beta;
+                        }
+                        sc[0] = tau; sc[1] = inv;
+                    }
+                }
+                __syncthreads();
+                const double tau = sc[0], inv = sc[1];
+                const int ntrail = ncols - j - 1;             // trailing panel columns; thread ntrail owns the right-hand side
+                if (tau != 0.0 && tid <= ntrail) {
+                    double *col;
+                    int stride;
+                    if (tid < ntrail) { col = pn.P + pn.cs(c + 1 + tid); stride = wmax; }
+                    else { col = pn.bc; stride = 1; }
+                    const double *piv = pn.P + csc;
+                    double dot = col[pn.rs(c) * stride];
+#pragma unroll 4
+                    for (int i = 1; i < m; i++) {
+                        const int r = pn.rs(c + i);
+                        dot = fma(piv[r * wmax] * inv, col[r * stride], dot);
+                    }
+                    const double w = tau * dot;
+                    col[pn.rs(c) * stride] -= w;
+#pragma unroll 4
+                    for (int i = 1; i < m; i++) {
+                        const int r = pn.rs(c + i);
+                        col[r * stride] = fma(-(piv[r * wmax] * inv), w, col[r * stride]);
+                    }
+                }
+                __syncthreads();
+            }
+            // (c) rows of block J are final: R[J, J..J+2] and (Q'b)[J] leave the panel
+            {
+                double *dst = Rw + (int64_t)(J - 1) * J * (J + 1);
+                for (int idx = tid; idx < J * ncols; idx += kThreads) dst[idx] = pn.at(c0 + idx / ncols, c0 + idx % ncols);
+                if (tid < J) qtb[c0 + tid] = pn.bc[pn.rs(c0 + tid)];
+            }
+            __syncthreads();
+        }
+        done = J1;
+        J0 = J1 + 1;
+        J1 = findblock(bstart(J1 + 1) + cg);
+    }
+
+    int n2 = 0;
+    if (st == ILA_OK && done > 0) {
+        // ---- chop (infqr.jl:221-232): Q'b lives in qtb (blocks 1..done) and in the panel (block done+1)
+        const int r0 = bstart(done + 1);
+        if (tid < done + 1) qtb[r0 + tid] = pn.bc[pn.rs(r0 + tid)];
+        __syncthreads();
+        const int len = bstart(done + 2);
+        int last = -1;
+        for (int i = tid; i < len; i += kThreads)
+            if (fabs(qtb[i]) > A.tol) last = i;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        if (tid == 0) si[1] = -1;
+        __syncthreads();
+        if (lane == 0) atomicMax(&si[1], last);
+        __syncthreads();
+        last = si[1];
+        if (last >= 0) {
+            const int K = findblock(last + 1);
+            n2 = bstart(K + 1);
+            // ---- back-substitution on the leading K x K blocks (infqr.jl:358-366)
+            double *Ts = smem;                           // diagonal block, stride ldt (odd)
+            double *cs_ = smem + 64 * 65;                // right-hand side of the current block row
+            double *xs = cs_ + 64;                       // solution
+            for (int Kc = K; Kc >= 1; Kc--) {
+                const int s = bstart(Kc), wrow = 3 * Kc + 3, ldt = Kc | 1;
+                const int wlim = min(wrow, n2 - s);
+                const double *src = Rw + (int64_t)(Kc - 1) * Kc * (Kc + 1);
+                for (int k = warp; k < Kc; k += kThreads / 32) {
+                    const double *row = src + (int64_t)k * wrow;
+                    double acc = 0.0;
+                    for (int ci = lane; ci < wlim; ci += 32) {
+                        const double v = row[ci];
+                        if (ci < Kc) Ts[k * ldt + ci] = v;
+                        else acc = fma(v, xs[s + ci], acc);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) cs_[k] = qtb[s + k] - acc;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    // rows lane and lane+32 of the block in registers; x_k broadcast from its owner
+                    double c_lo = lane < Kc ? cs_[lane] : 0.0, c_hi = lane + 32 < Kc ? cs_[lane + 32] : 0.0;
+                    for (int k = Kc - 1; k >= 0; k--) {
+                        const double num = __shfl_sync(0xffffffffu, k >= 32 ? c_hi : c_lo, k & 31);
+                        const double xk = num / Ts[k * ldt + k];
+                        if (lane < k) c_lo = fma(-Ts[lane * ldt + k], xk, c_lo);
+                        if (lane + 32 < k) c_hi = fma(-Ts[(lane + 32) * ldt + k], xk, c_hi);
+                        if (lane == 0) xs[s + k] = xk;
+                    }
+                }
+                __syncthreads();
+            }
+            double *xo = A.x + inst * A.xld;
+            for (int i = tid; i < A.xld; i += kThreads) xo[i] = i < n2 ? xs[i] : 0.0;
+        }
+    }
+    if (n2 == 0) {
+        double *xo = A.x + inst * A.xld;
+        for (int i = tid; i < A.xld; i += kThreads) xo[i] = 0.0;
+    }
+    if (tid == 0) {
+        A.ncols[inst] = n2;
+        A.nblocks[inst] = done;
+        A.status[inst] = st;
+    }
+}
+
+int qr_blockbanded_smem_bytes(int maxblocks, int *hmax_out, int *wmax_out)
+{
+    int hmax = 8;
+    while (hmax < 2 * maxblocks - 1) hmax <<= 1;
+    const int wmax = 3 * maxblocks;
+    if (hmax_out) *hmax_out = hmax;
+    if (wmax_out) *wmax_out = wmax;
+    size_t need = ((size_t)hmax * wmax + hmax) * sizeof(double);
+    const size_t backsub = (size_t)(64 * 65 + 64 + maxblocks * (maxblocks + 1) / 2 + 8) * sizeof(double);
+    if (need < backsub) need = backsub;
+    return (int)need;
+}
+
+int launch_qr_blockbanded(BlockQrArgs a, cudaStream_t s)
+{
+    if (a.batch <= 0) return 0;
+    if (a.maxblocks < 3 || a.maxblocks > 64) return set_error(ILA_ERR_UNSUPPORTED, "qr_blockbanded: maxblocks must be in 3..64 (the panel lives in shared memory)");
+    const int bytes = qr_blockbanded_smem_bytes(a.maxblocks, &a.hmax, &a.wmax);
+    int dev = 0;
+    ILA_CUDA_CHECK(cudaGetDevice(&dev));
+    static int opted[16] = {};
+    if (bytes > 48 * 1024 && (dev >= 16 || opted[dev] < bytes)) {        // the > 48 KB opt-in is per device
+        ILA_CUDA_CHECK(cudaFuncSetAttribute(qr_blockbanded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (dev < 16) opted[dev] = bytes;
+    }
+    qr_blockbanded_kernel<<<(unsigned)a.batch, kThreads, bytes, s>>>(a);
+    count_launch();
+    ILA_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+} // namespace ila
