@@ -310,6 +310,13 @@ int ila_qr_blockbanded_solve_f64(int64_t batch, const double *alpha, const doubl
                                  const double *T2, int64_t tld, int nb, const double *b, double tol, int colgrowth,
                                  int maxblocks, double *x, int64_t xld, int64_t *ncols, int32_t *nblocks, double *qtb_opt,
                                  int32_t *status, int ngpus);
+/* device-resident form: the caller owns every buffer; d_work holds batch x ila_qr_blockbanded_work_doubles(maxblocks) doubles
+ * (the R block rows), d_qtb and d_x batch x xld. */
+int ila_qr_blockbanded_work_doubles(int maxblocks, int64_t *per_operator);
+int ila_qr_blockbanded_solve_f64_dev(int64_t batch, const double *d_alpha, const double *d_beta, const double *d_lam,
+                                     const double *d_T1, const double *d_T2, int64_t tld, int nb, const double *d_b, double tol,
+                                     int colgrowth, int maxblocks, double *d_work, double *d_qtb, double *d_x, int64_t xld,
+                                     int64_t *d_ncols, int32_t *d_nblocks, int32_t *d_status, void *stream);
 
 #ifdef __cplusplus
 }

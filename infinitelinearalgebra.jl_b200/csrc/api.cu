@@ -689,6 +689,30 @@ int ila_biconj_bands_f64(int upper, int64_t batch, int64_t n, const double *U, c
 
 // ================================ K11: adaptive block-banded QR solve ====================================
 
+int ila_qr_blockbanded_work_doubles(int maxblocks, int64_t *per_operator)
+{
+    if (maxblocks < 3 || maxblocks > 64 || !per_operator) return set_error(ILA_ERR_ARG, "qr_blockbanded_work_doubles: bad arguments");
+    *per_operator = (int64_t)(maxblocks - 1) * maxblocks * (maxblocks + 1);
+    return 0;
+}
+
+int ila_qr_blockbanded_solve_f64_dev(int64_t batch, const double *d_alpha, const double *d_beta, const double *d_lam,
+                                     const double *d_T1, const double *d_T2, int64_t tld, int nb, const double *d_b, double tol,
+                                     int colgrowth, int maxblocks, double *d_work, double *d_qtb, double *d_x, int64_t xld,
+                                     int64_t *d_ncols, int32_t *d_nblocks, int32_t *d_status, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    if (batch < 0 || nb < 1 || colgrowth < 1 || !d_work || !d_qtb || !d_x) return set_error(ILA_ERR_ARG, "qr_blockbanded_solve_dev: bad arguments");
+    if (maxblocks < 3 || maxblocks > 64) return set_error(ILA_ERR_UNSUPPORTED, "qr_blockbanded_solve: maxblocks must be in 3..64 (the panel lives in shared memory)");
+    if (tld < maxblocks + 1 || xld < (int64_t)maxblocks * (maxblocks + 1) / 2) return set_error(ILA_ERR_ARG, "qr_blockbanded_solve_dev: tld / xld too small");
+    BlockQrArgs a{};
+    a.batch = batch; a.alpha = d_alpha; a.beta = d_beta; a.lam = d_lam; a.T1 = d_T1; a.T2 = d_T2; a.tld = tld; a.b = d_b; a.nb = nb;
+    a.tol = tol; a.colgrowth = colgrowth; a.maxblocks = maxblocks; a.work = d_work;
+    a.work_stride = (int64_t)(maxblocks - 1) * maxblocks * (maxblocks + 1); a.qtb = d_qtb;
+    a.x = d_x; a.xld = xld; a.ncols = d_ncols; a.nblocks = d_nblocks; a.status = d_status;
+    return launch_qr_blockbanded(a, (cudaStream_t)stream);
+}
+
 int ila_qr_blockbanded_solve_f64(int64_t batch, const double *alpha, const double *beta, const double *lam, const double *T1,
                                  const double *T2, int64_t tld, int nb, const double *b, double tol, int colgrowth,
                                  int maxblocks, double *x, int64_t xld, int64_t *ncols, int32_t *nblocks, double *qtb_opt,

@@ -42,16 +42,28 @@ __device__ __forceinline__ int findblock(int i)                                 
     return K;
 }
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 448;          // 14 warps x 16 column pairs = 224 >= 3*64 + 1 panel columns
+constexpr int kWarps = kThreads / 32;
 
 struct Panel {
-    double *P;        // HMAX x WMAX, row-major
-    double *bc;       // HMAX: the right-hand-side column
-    int hmask, wmax;
+    double *P;        // HMAX x LD, row-major; column slot wmax is the right-hand side
+    int hmask, wmax, ld;
     __device__ __forceinline__ int rs(int g) const { return g & hmask; }
     __device__ __forceinline__ int cs(int c) const { return c % wmax; }
-    __device__ __forceinline__ double &at(int g, int c) { return P[rs(g) * wmax + cs(c)]; }
+    __device__ __forceinline__ double &at(int g, int c) { return P[rs(g) * ld + cs(c)]; }
+    __device__ __forceinline__ double &rhs(int g) { return P[rs(g) * ld + wmax]; }
 };
+
+// LAPACK dlarfg from the pivot alpha and the sum of squares below it: (tau, 1/(alpha - beta), beta); tau = 0 <=> H = I
+__device__ __forceinline__ void reflector_scalars(double alpha, double ss, double &tau, double &inv, double &beta)
+{
+    tau = 0.0; inv = 0.0; beta = alpha;
+    if (ss != 0.0) {
+        beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+        tau = (beta - alpha) / beta;
+        inv = 1.0 / (alpha - beta);
+    }
+}
 
 } // namespace
 
@@ -62,8 +74,8 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     __shared__ int si[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t inst = blockIdx.x;
-    const int hmax = A.hmax, wmax = A.wmax;
-    Panel pn{smem, smem + (size_t)hmax * wmax, hmax - 1, wmax};
+    const int hmax = A.hmax, wmax = A.wmax, ld = wmax + 1;
+    Panel pn{smem, hmax - 1, wmax, ld};
     const double al = A.alpha[inst], be = A.beta[inst], lam = A.lam[inst];
     const double *T1 = A.T1, *T2 = A.T2;
     const int64_t tld = A.tld;
@@ -72,23 +84,31 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     double *Rw = A.work + inst * A.work_stride;
     double *qtb = A.qtb + inst * A.xld;
 
-    // rows of block K (1-based) into the panel: zero the columns of blocks Klo..K+1, then the (at most five) entries per row
+    // rows of block K (1-based) into the panel (one warp per row): zero the columns of blocks Klo..K+1, then the (at most
+    // five) entries of the row and its right-hand-side entry
     auto load_block_rows = [&](int K, int Klo) {
-        const int c_lo = bstart(Klo), c_hi = bstart(K + 2), w = c_hi - c_lo, r0 = bstart(K);
-        for (int idx = tid; idx < K * w; idx += kThreads) pn.at(r0 + idx / w, c_lo + idx % w) = 0.0;
-        __syncthreads();
-        if (tid < K) {
-            const int kk = tid + 1, g = r0 + tid;
-            pn.at(g, g) = al * T1[tld + kk - 1] + be * T2[tld + K - kk] - lam;
-            const int cn = bstart(K + 1);
-            pn.at(g, cn + kk) += al * T1[2 * tld + kk - 1];            // (kk, kk+1): T1[kk, kk+1]
-            pn.at(g, cn + kk - 1) += be * T2[2 * tld + K - kk];        // (kk, kk):   T2[K-kk+1, K-kk+2]
-            if (K > 1) {
-                const int cp = bstart(K - 1);
-                if (kk >= 2) pn.at(g, cp + kk - 2) += al * T1[kk - 2];            // (kk, kk-1): T1[kk, kk-1]
-                if (kk <= K - 1) pn.at(g, cp + kk - 1) += be * T2[K - kk - 1];    // (kk, kk):   T2[K-kk+1, K-kk]
+        const int c_lo = bstart(Klo), w = bstart(K + 2) - c_lo, r0 = bstart(K), s_lo = pn.cs(c_lo);
+        for (int k = warp; k < K; k += kWarps) {
+            double *row = pn.P + pn.rs(r0 + k) * ld;
+            for (int ci = lane; ci < w; ci += 32) {
+                int sl = s_lo + ci;
+                if (sl >= wmax) sl -= wmax;
+                row[sl] = 0.0;
             }
-            pn.bc[pn.rs(g)] = g < nb ? bi[g] : 0.0;
+            __syncwarp();
+            if (lane == 0) {
+                const int kk = k + 1, g = r0 + k;
+                row[pn.cs(g)] = al * T1[tld + kk - 1] + be * T2[tld + K - kk] - lam;
+                const int cn = bstart(K + 1);
+                row[pn.cs(cn + kk)] += al * T1[2 * tld + kk - 1];            // (kk, kk+1): T1[kk, kk+1]
+                row[pn.cs(cn + kk - 1)] += be * T2[2 * tld + K - kk];        // (kk, kk):   T2[K-kk+1, K-kk+2]
+                if (K > 1) {
+                    const int cp = bstart(K - 1);
+                    if (kk >= 2) row[pn.cs(cp + kk - 2)] += al * T1[kk - 2];            // (kk, kk-1): T1[kk, kk-1]
+                    if (kk <= K - 1) row[pn.cs(cp + kk - 1)] += be * T2[K - kk - 1];    // (kk, kk):   T2[K-kk+1, K-kk]
+                }
+                row[wmax] = g < nb ? bi[g] : 0.0;
+            }
         }
     };
 
@@ -98,6 +118,10 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     load_block_rows(1, 1);
     __syncthreads();
 
+    // column pair of this thread: 16 pairs per warp, the two lanes of a pair take alternate rows (a 64-bit shared-memory
+    // request is served per half-warp, so the two halves cost nothing extra)
+    const int tp = warp * 16 + (lane & 15), half = lane >> 4;
+
     for (;;) {
         // ---- adaptive test at the chunk start (infqr.jl:316-322): the rows of block J0+1 still hold raw b (zero past SB)
         if (warp == 0) {
@@ -105,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
             bool nan = false;
             const int r0 = bstart(J0);
             for (int k = lane; k < J0; k += 32) {
-                const double v = pn.bc[pn.rs(r0 + k)];
+                const double v = pn.rhs(r0 + k);
                 nan |= (v != v);
                 mx = fmax(mx, fabs(v));
             }
@@ -128,65 +152,106 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
             const int c0 = bstart(J), nrows = 2 * J + 1, ncols = 3 * J + 3;
             // (a) fresh rows of block J+1; block column J+2 of the rows of block J starts at zero
             {
-                const int c2 = bstart(J + 2), w2 = J + 2;
-                for (int idx = tid; idx < J * w2; idx += kThreads) pn.at(c0 + idx / w2, c2 + idx % w2) = 0.0;
+                const int s2 = pn.cs(bstart(J + 2)), w2 = J + 2;
+                for (int k = warp; k < J; k += kWarps) {
+                    double *row = pn.P + pn.rs(c0 + k) * ld;
+                    for (int ci = lane; ci < w2; ci += 32) {
+                        int sl = s2 + ci;
+                        if (sl >= wmax) sl -= wmax;
+                        row[sl] = 0.0;
+                    }
+                }
             }
             load_block_rows(J + 1, J);
             __syncthreads();
-            // (b) Householder QR of block column J
+            // (b) Householder QR of block column J.  The scalars of column j+1 are formed by the pair that updates it (the sum
+            // of squares rides on its update pass), so only the first column of a block column needs a reduction of its own
+            // and there is ONE barrier per column.
+            if (warp == 0) {
+                const int csc = pn.cs(c0);
+                double ss = 0.0;
+                for (int i = 1 + lane; i < nrows; i += 32) {
+                    const double v = pn.P[pn.rs(c0 + i) * ld + csc];
+                    ss = fma(v, v, ss);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (lane == 0) {
+                    double tau, inv, beta;
+                    reflector_scalars(pn.P[pn.rs(c0) * ld + csc], ss, tau, inv, beta);
+                    pn.P[pn.rs(c0) * ld + csc] = beta;
+                    sc[0] = tau; sc[1] = inv;
+                }
+            }
+            __syncthreads();
             for (int j = 0; j < J; j++) {
                 const int c = c0 + j, m = nrows - j;          // pivot column, rows c .. c+m-1
-                const int csc = pn.cs(c);
-                if (warp == 0) {
-                    double ss = 0.0;
-                    for (int i = 1 + lane; i < m; i += 32) {
-                        const double v = pn.P[pn.rs(c + i) * wmax + csc];
-                        ss = fma(v, v, ss);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                    if (lane == 0) {
-                        double tau = 0.0, inv = 0.0;
-                        if (ss != 0.0) {
-                            const double alpha = pn.P[pn.rs(c) * wmax + csc];
-                            const double beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
-                            tau = (beta - alpha) / beta;
-                            inv = 1.0 / (alpha - beta);
-                            pn.P[pn.rs(c) * wmax + csc] = beta;
-                        }
-                        sc[0] = tau; sc[1] = inv;
+                const double tau = sc[(j & 1) * 2], inv = sc[(j & 1) * 2 + 1];
+                const int ntrail = ncols - j - 1;             // trailing panel columns; pair ntrail owns the right-hand side
+                const bool act = tp <= ntrail;
+                const double *piv = pn.P + pn.cs(c);
+                double *col = pn.P + (tp < ntrail ? pn.cs(c + 1 + tp) : wmax);
+                const int mm = act ? m : 0;
+                const int rd = pn.rs(c) * ld;
+                double dot = 0.0;
+                {
+                    int r = pn.rs(c + 1 + half);
+#pragma unroll 4
+                    for (int i = 1 + half; i < mm; i += 2) {
+                        dot = fma(piv[r * ld], col[r * ld], dot);
+                        r = (r + 2) & pn.hmask;
                     }
                 }
-                __syncthreads();
-                const double tau = sc[0], inv = sc[1];
-                const int ntrail = ncols - j - 1;             // trailing panel columns; thread ntrail owns the right-hand side
-                if (tau != 0.0 && tid <= ntrail) {
-                    double *col;
-                    int stride;
-                    if (tid < ntrail) { col = pn.P + pn.cs(c + 1 + tid); stride = wmax; }
-                    else { col = pn.bc; stride = 1; }
-                    const double *piv = pn.P + csc;
-                    double dot = col[pn.rs(c) * stride];
+                dot += __shfl_xor_sync(0xffffffffu, dot, 16);
+                const double cd = act ? col[rd] : 0.0;
+                const double w = tau * fma(inv, dot, cd);
+                const double winv = -(w * inv);
+                if (act && half == 0) col[rd] = cd - w;
+                double ss = 0.0;
+                {
+                    int r = pn.rs(c + 1 + half);
+                    if (warp == 0) {
 #pragma unroll 4
-                    for (int i = 1; i < m; i++) {
-                        const int r = pn.rs(c + i);
-                        dot = fma(piv[r * wmax] * inv, col[r * stride], dot);
+                        for (int i = 1 + half; i < mm; i += 2) {
+                            const double v = fma(piv[r * ld], winv, col[r * ld]);
+                            col[r * ld] = v;
+                            if (i >= 2) ss = fma(v, v, ss);
+                            r = (r + 2) & pn.hmask;
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int i = 1 + half; i < mm; i += 2) {
+                            col[r * ld] = fma(piv[r * ld], winv, col[r * ld]);
+                            r = (r + 2) & pn.hmask;
+                        }
                     }
-                    const double w = tau * dot;
-                    col[pn.rs(c) * stride] -= w;
-#pragma unroll 4
-                    for (int i = 1; i < m; i++) {
-                        const int r = pn.rs(c + i);
-                        col[r * stride] = fma(-(piv[r * wmax] * inv), w, col[r * stride]);
+                }
+                if (warp == 0 && j + 1 < J) {
+                    ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+                    __syncwarp();
+                    if (lane == 0) {                          // pair 0 owns the next pivot column c+1
+                        double t2, i2, b2;
+                        const int rn = pn.rs(c + 1) * ld;
+                        reflector_scalars(col[rn], ss, t2, i2, b2);
+                        col[rn] = b2;
+                        sc[((j + 1) & 1) * 2] = t2; sc[((j + 1) & 1) * 2 + 1] = i2;
                     }
                 }
                 __syncthreads();
             }
-            // (c) rows of block J are final: R[J, J..J+2] and (Q'b)[J] leave the panel
+            // (c) rows of block J are final: R[J, J..J+2] and (Q'b)[J] leave the panel (one warp per row, coalesced)
             {
                 double *dst = Rw + (int64_t)(J - 1) * J * (J + 1);
-                for (int idx = tid; idx < J * ncols; idx += kThreads) dst[idx] = pn.at(c0 + idx / ncols, c0 + idx % ncols);
-                if (tid < J) qtb[c0 + tid] = pn.bc[pn.rs(c0 + tid)];
+                const int s0 = pn.cs(c0);
+                for (int k = warp; k < J; k += kWarps) {
+                    const double *row = pn.P + pn.rs(c0 + k) * ld;
+                    for (int ci = lane; ci < ncols; ci += 32) {
+                        int sl = s0 + ci;
+                        if (sl >= wmax) sl -= wmax;
+                        dst[k * ncols + ci] = row[sl];
+                    }
+                    if (lane == 0) qtb[c0 + k] = row[wmax];
+                }
             }
             __syncthreads();
         }
@@ -199,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     if (st == ILA_OK && done > 0) {
         // ---- chop (infqr.jl:221-232): Q'b lives in qtb (blocks 1..done) and in the panel (block done+1)
         const int r0 = bstart(done + 1);
-        if (tid < done + 1) qtb[r0 + tid] = pn.bc[pn.rs(r0 + tid)];
+        if (tid < done + 1) qtb[r0 + tid] = pn.rhs(r0 + tid);
         __syncthreads();
         const int len = bstart(done + 2);
         int last = -1;
@@ -223,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                 const int s = bstart(Kc), wrow = 3 * Kc + 3, ldt = Kc | 1;
                 const int wlim = min(wrow, n2 - s);
                 const double *src = Rw + (int64_t)(Kc - 1) * Kc * (Kc + 1);
-                for (int k = warp; k < Kc; k += kThreads / 32) {
+                for (int k = warp; k < Kc; k += kWarps) {
                     const double *row = src + (int64_t)k * wrow;
                     double acc = 0.0;
                     for (int ci = lane; ci < wlim; ci += 32) {
@@ -271,7 +336,7 @@ int qr_blockbanded_smem_bytes(int maxblocks, int *hmax_out, int *wmax_out)
     const int wmax = 3 * maxblocks;
     if (hmax_out) *hmax_out = hmax;
     if (wmax_out) *wmax_out = wmax;
-    size_t need = ((size_t)hmax * wmax + hmax) * sizeof(double);
+    size_t need = (size_t)hmax * (wmax + 1) * sizeof(double);
     const size_t backsub = (size_t)(64 * 65 + 64 + maxblocks * (maxblocks + 1) / 2 + 8) * sizeof(double);
     if (need < backsub) need = backsub;
     return (int)need;
