@@ -28,6 +28,7 @@
 // new solution entry, no block-wide barrier inside a block row).
 #include "ila_common.cuh"
 #include "ila_kernels.cuh"
+#include "ila_exact.cuh"
 
 namespace ila {
 
@@ -59,9 +60,9 @@ __device__ __forceinline__ void reflector_scalars(double alpha, double ss, doubl
 {
     tau = 0.0; inv = 0.0; beta = alpha;
     if (ss != 0.0) {
-        beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
-        tau = (beta - alpha) / beta;
-        inv = 1.0 / (alpha - beta);
+        beta = -copysign(esqrt(fma(alpha, alpha, ss)), alpha);
+        tau = ediv(beta - alpha, beta);
+        inv = ediv(1.0, alpha - beta);
     }
 }
 
@@ -112,6 +113,14 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
         }
     };
 
+#ifdef ILA_K11_PROFILE
+    long long tp_a = 0, tp_n = 0, tp_j = 0, tp_c = 0, tp_bs = 0, tp_t0;
+#define K11_T0() tp_t0 = clock64()
+#define K11_ACC(v) do { const long long t_ = clock64(); v += t_ - tp_t0; tp_t0 = t_; } while (0)
+#else
+#define K11_T0()
+#define K11_ACC(v)
+#endif
     int J0 = 1, J1 = findblock(cg), done = 0;
     const int SB = findblock(nb);
     int32_t st = ILA_OK;
@@ -151,6 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
         for (int J = J0; J <= J1; J++) {
             const int c0 = bstart(J), nrows = 2 * J + 1, ncols = 3 * J + 3;
             // (a) fresh rows of block J+1; block column J+2 of the rows of block J starts at zero
+            K11_T0();
             {
                 const int s2 = pn.cs(bstart(J + 2)), w2 = J + 2;
                 for (int k = warp; k < J; k += kWarps) {
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
             }
             load_block_rows(J + 1, J);
             __syncthreads();
+            K11_ACC(tp_a);
             // (b) Householder QR of block column J.  The scalars of column j+1 are formed by the pair that updates it (the sum
             // of squares rides on its update pass), so only the first column of a block column needs a reduction of its own
             // and there is ONE barrier per column.
@@ -184,24 +195,38 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                 }
             }
             __syncthreads();
+            K11_ACC(tp_n);
+            int csc = pn.cs(c0);                              // slot of the pivot column, advanced with j
             for (int j = 0; j < J; j++) {
                 const int c = c0 + j, m = nrows - j;          // pivot column, rows c .. c+m-1
                 const double tau = sc[(j & 1) * 2], inv = sc[(j & 1) * 2 + 1];
                 const int ntrail = ncols - j - 1;             // trailing panel columns; pair ntrail owns the right-hand side
                 const bool act = tp <= ntrail;
-                const double *piv = pn.P + pn.cs(c);
-                double *col = pn.P + (tp < ntrail ? pn.cs(c + 1 + tp) : wmax);
-                const int mm = act ? m : 0;
+                int scol = csc + 1 + tp;
+                if (scol >= wmax) scol -= wmax;
+                const double *__restrict__ piv = pn.P + csc;
+                double *__restrict__ col = pn.P + (tp < ntrail ? scol : wmax);
+                const int cnt = (act && m > half) ? (m - half) >> 1 : 0;      // this lane's rows: i = 1+half, 3+half, ...
+                const int hm = pn.hmask;
                 const int rd = pn.rs(c) * ld;
-                double dot = 0.0;
+                const int rfirst = pn.rs(c + 1 + half);
+                double dotA = 0.0, dotB = 0.0;
                 {
-                    int r = pn.rs(c + 1 + half);
-#pragma unroll 4
-                    for (int i = 1 + half; i < mm; i += 2) {
-                        dot = fma(piv[r * ld], col[r * ld], dot);
-                        r = (r + 2) & pn.hmask;
+                    int r = rfirst, k = 0;
+                    for (; k + 4 <= cnt; k += 4) {
+                        const int o0 = r * ld, o1 = ((r + 2) & hm) * ld, o2 = ((r + 4) & hm) * ld, o3 = ((r + 6) & hm) * ld;
+                        r = (r + 8) & hm;
+                        const double p0 = piv[o0], p1 = piv[o1], p2 = piv[o2], p3 = piv[o3];
+                        const double q0 = col[o0], q1 = col[o1], q2 = col[o2], q3 = col[o3];
+                        dotA = fma(p0, q0, dotA); dotB = fma(p1, q1, dotB);
+                        dotA = fma(p2, q2, dotA); dotB = fma(p3, q3, dotB);
+                    }
+                    for (; k < cnt; k++) {
+                        dotA = fma(piv[r * ld], col[r * ld], dotA);
+                        r = (r + 2) & hm;
                     }
                 }
+                double dot = dotA + dotB;
                 dot += __shfl_xor_sync(0xffffffffu, dot, 16);
                 const double cd = act ? col[rd] : 0.0;
                 const double w = tau * fma(inv, dot, cd);
@@ -209,21 +234,25 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                 if (act && half == 0) col[rd] = cd - w;
                 double ss = 0.0;
                 {
-                    int r = pn.rs(c + 1 + half);
-                    if (warp == 0) {
-#pragma unroll 4
-                        for (int i = 1 + half; i < mm; i += 2) {
-                            const double v = fma(piv[r * ld], winv, col[r * ld]);
-                            col[r * ld] = v;
-                            if (i >= 2) ss = fma(v, v, ss);
-                            r = (r + 2) & pn.hmask;
+                    int r = rfirst, k = 0;
+                    const bool first_is_diag = half == 0;         // row i = 1 is the next pivot's diagonal: not part of its norm
+                    for (; k + 4 <= cnt; k += 4) {
+                        const int o0 = r * ld, o1 = ((r + 2) & hm) * ld, o2 = ((r + 4) & hm) * ld, o3 = ((r + 6) & hm) * ld;
+                        r = (r + 8) & hm;
+                        const double p0 = piv[o0], p1 = piv[o1], p2 = piv[o2], p3 = piv[o3];
+                        const double q0 = col[o0], q1 = col[o1], q2 = col[o2], q3 = col[o3];
+                        const double v0 = fma(p0, winv, q0), v1 = fma(p1, winv, q1), v2 = fma(p2, winv, q2), v3 = fma(p3, winv, q3);
+                        col[o0] = v0; col[o1] = v1; col[o2] = v2; col[o3] = v3;
+                        if (warp == 0) {
+                            if (!(first_is_diag && k == 0)) ss = fma(v0, v0, ss);
+                            ss = fma(v1, v1, ss); ss = fma(v2, v2, ss); ss = fma(v3, v3, ss);
                         }
-                    } else {
-#pragma unroll 4
-                        for (int i = 1 + half; i < mm; i += 2) {
-                            col[r * ld] = fma(piv[r * ld], winv, col[r * ld]);
-                            r = (r + 2) & pn.hmask;
-                        }
+                    }
+                    for (; k < cnt; k++) {
+                        const double v = fma(piv[r * ld], winv, col[r * ld]);
+                        col[r * ld] = v;
+                        if (warp == 0 && !(first_is_diag && k == 0)) ss = fma(v, v, ss);
+                        r = (r + 2) & hm;
                     }
                 }
                 if (warp == 0 && j + 1 < J) {
@@ -237,9 +266,11 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                         sc[((j + 1) & 1) * 2] = t2; sc[((j + 1) & 1) * 2 + 1] = i2;
                     }
                 }
+                if (++csc == wmax) csc = 0;
                 __syncthreads();
             }
             // (c) rows of block J are final: R[J, J..J+2] and (Q'b)[J] leave the panel (one warp per row, coalesced)
+            K11_ACC(tp_j);
             {
                 double *dst = Rw + (int64_t)(J - 1) * J * (J + 1);
                 const int s0 = pn.cs(c0);
@@ -254,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                 }
             }
             __syncthreads();
+            K11_ACC(tp_c);
         }
         done = J1;
         J0 = J1 + 1;
@@ -261,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     }
 
     int n2 = 0;
+    K11_T0();
     if (st == ILA_OK && done > 0) {
         // ---- chop (infqr.jl:221-232): Q'b lives in qtb (blocks 1..done) and in the panel (block done+1)
         const int r0 = bstart(done + 1);
@@ -322,6 +355,13 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
         double *xo = A.x + inst * A.xld;
         for (int i = tid; i < A.xld; i += kThreads) xo[i] = 0.0;
     }
+#ifdef ILA_K11_PROFILE
+    K11_ACC(tp_bs);
+    if (tid == 0) {
+        double *xo = A.x + inst * A.xld + A.xld - 5;
+        xo[0] = (double)tp_a; xo[1] = (double)tp_n; xo[2] = (double)tp_j; xo[3] = (double)tp_c; xo[4] = (double)tp_bs;
+    }
+#endif
     if (tid == 0) {
         A.ncols[inst] = n2;
         A.nblocks[inst] = done;

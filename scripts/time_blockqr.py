@@ -39,3 +39,8 @@ flops = sum(sum(4.0 * (2 * J + 1 - j) * (3 * J + 3 - j) for j in range(J)) for K
 cols = int(sum(K * (K + 1) // 2 for K in nb_))
 print(f"batch {batch}: {ms:.3f} ms, blocks {nb_.min()}..{nb_.max()}, bad {int((st != 0).sum())}, {cols/ms/1e3:.2f} Mcolumns/s, "
       f"{flops/ms/1e9:.2f} TFLOP/s FP64 (Householder flops), {batch/ms*1e3:.0f} operators/s")
+
+if os.environ.get("K11_PROFILE"):
+    xc = x.cpu().numpy()
+    i = int(np.argmax(nb_))
+    print("phase cycles (operator with most blocks): load %.0f  first-norm %.0f  columns %.0f  write-out %.0f  back-substitution %.0f" % tuple(xc[i, -5:]))
