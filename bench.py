@@ -427,6 +427,48 @@ def run_ours(args, rank, local_rank, world):
             res9["o"] = ila_b200.qr_banded_solve_c64(1, 1, p9, q9, None, shift=lam9, b=[1.0], ncap=20000)
         ms9 = wall(run9)
         cols9 = float(res9["o"]["ncols"].sum())
+        # K10: tridiagonal conjugation Y = Tridiagonal(U*X/U), explicit bands, device resident
+        n10, b10 = 16384, 2048
+        gen = torch.Generator(device=dev); gen.manual_seed(1)
+        dU = torch.rand((b10, 3, n10 + 1), dtype=torch.float64, device=dev, generator=gen) * 0.3
+        dU[:, 0] += 1.0
+        dX = torch.rand((b10, 3, n10 + 1), dtype=torch.float64, device=dev, generator=gen)
+        dY = torch.empty((b10, 3, n10), dtype=torch.float64, device=dev)
+
+        def step_k10():
+            _lib.check(lib.ila_triconj_bands_f64_dev(3, b10, n10, _lib.ptr(dU), n10 + 1, _lib.ptr(dX), n10 + 1, 0, _lib.ptr(dY), None,
+                                                     ctypes.c_void_p(stream)))
+        ms_k10 = timed(step_k10, k4, 2) / k4
+        rows10 = float(b10) * n10
+        del dU, dX, dY
+        # K11: adaptive block-banded QR, (X + Y - λI) \ e1 for 592 shifts (4 CTAs per SM-slot), device resident
+        b11, mb11 = 592, 64
+        T11 = torch.tensor(np.stack([np.full(80, 0.5), np.zeros(80), np.full(80, 0.5)]), device=dev)
+        lam11 = torch.linspace(4.0, 9.0, b11, dtype=torch.float64, device=dev)
+        one11 = torch.ones(b11, dtype=torch.float64, device=dev)
+        rhs11 = torch.ones((b11, 1), dtype=torch.float64, device=dev)
+        per11 = np.zeros(1, dtype=np.int64)
+        _lib.check(lib.ila_qr_blockbanded_work_doubles(mb11, _lib.ptr(per11)))
+        xld11 = mb11 * (mb11 + 1) // 2
+        w11 = torch.empty(b11 * int(per11[0]), dtype=torch.float64, device=dev)
+        q11 = torch.zeros((b11, xld11), dtype=torch.float64, device=dev)
+        x11 = torch.empty((b11, xld11), dtype=torch.float64, device=dev)
+        nc11 = torch.zeros(b11, dtype=torch.int64, device=dev)
+        nb11 = torch.zeros(b11, dtype=torch.int32, device=dev)
+        st11 = torch.zeros(b11, dtype=torch.int32, device=dev)
+
+        def step_k11():
+            _lib.check(lib.ila_qr_blockbanded_solve_f64_dev(b11, _lib.ptr(one11), _lib.ptr(one11), _lib.ptr(lam11), _lib.ptr(T11),
+                                                            _lib.ptr(T11), 80, 1, _lib.ptr(rhs11), 1e-30, 300, mb11, _lib.ptr(w11),
+                                                            _lib.ptr(q11), _lib.ptr(x11), xld11, _lib.ptr(nc11), _lib.ptr(nb11),
+                                                            _lib.ptr(st11), ctypes.c_void_p(stream)))
+        ms_k11 = timed(step_k11, min(k4, 3), 1) / min(k4, 3)
+        if int((st11 != 0).sum().item()) != 0:
+            raise SystemExit("bench.py: K11 instances failed")
+        blk11 = nb11.cpu().numpy().astype(np.int64)
+        cols11 = float(sum(K * (K + 1) // 2 for K in blk11))
+        flops11 = float(sum(sum(4.0 * (2 * J + 1 - j) * (3 * J + 3 - j) for j in range(J)) for K in blk11 for J in range(1, K + 1)))
+        del w11
         line["other_configs"] = [
             {"metric": "adaptive_cholesky_columns_per_s", "value": cols4 * world / (ms4 * 1e-3), "unit": "columns/s",
              "ms_per_step": ms4, "config": {"workload": "C4 pentadiagonal adaptive Cholesky, 2048 shifts (per GPU)",
@@ -463,6 +505,23 @@ def run_ours(args, rank, local_rank, world):
              "ms_per_step": ms9, "config": {"workload": "complex-eltype adaptive QR, (J - λI) \\ e1, 512 shifts λ = x + 0.2i (per GPU)",
                                             "columns": cols9, "timing": "host C-ABI call, wall clock, copies included"},
              "gpu_launches_per_step": 3},
+            {"metric": "tridiagonal_conjugation_rows_per_s", "value": rows10 * world / (ms_k10 * 1e-3), "unit": "rows/s",
+             "ms_per_step": ms_k10, "config": {"workload": "K10 Y = Tridiagonal(U*X/U), 2048 operators x 16384 rows, three bands of U and "
+                                                          "X per operator (per GPU)"},
+             "roofline": {"bound": "hbm", "achieved": 72 * rows10 / (ms_k10 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": 72 * rows10 / (ms_k10 * 1e-3) / 1e9 / hbm_peak, "traffic": None, "bytes_per_unit": 72,
+                          "note": "per row: 3 U + 3 X doubles in, 3 Y doubles out; 5 IEEE divisions per row"},
+             "gpu_launches_per_step": 1},
+            {"metric": "blockbanded_qr_columns_per_s", "value": cols11 * world / (ms_k11 * 1e-3), "unit": "columns/s",
+             "ms_per_step": ms_k11, "config": {"workload": "K11 adaptive block-banded QR (X + Y - λI) \\ e1, KronTrav blocks 1,2,3,..., 592 "
+                                                          "shifts λ in [4, 9], tolerance 1e-30 (per GPU)",
+                                               "blocks_min_max": [int(blk11.min()), int(blk11.max())],
+                                               "operators_per_s": b11 * world / (ms_k11 * 1e-3)},
+             "roofline": {"bound": "fp64", "achieved": flops11 / (ms_k11 * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                          "frac": flops11 / (ms_k11 * 1e-3) / 1e12 / fp64_peak, "traffic": None,
+                          "note": "Householder flops 4(2J+1-j)(3J+3-j) per column; the rank-1 updates stream the panel through "
+                                  "shared memory (24 B per 2 flops), so the kernel is shared-memory-bandwidth bound, not FP64 bound"},
+             "gpu_launches_per_step": 1},
         ]
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------

@@ -543,3 +543,143 @@ def ql_adaptive(A: BandedMatrix, tol=np.finfo(float).eps, j=50, maxN=10000):
     if int(out["status"][0]) == 3:
         raise NotConvergedError("Reached max. iterations in adaptive QL without convergence to desired tolerance.")
     return FiniteSectionQL(out, l, u)
+
+
+# ---- tridiagonal / bidiagonal conjugation --------------------------------------------------------------------
+
+def _lazy_values(v, m):
+    """First m entries of a lazy ∞ vector (Fill / Affine / Rational, optionally behind a Vcat head) or of an array."""
+    if isinstance(v, Vcat):
+        h = np.asarray(v.head, dtype=float)
+        return np.concatenate([h, _lazy_values(v.tail, max(m - len(h), 0))])[:m]
+    k = np.arange(m, dtype=float)
+    if isinstance(v, Rational):
+        c0, p, q, r, s = v.c
+        return c0 + (p + q * k) / (r + s * k)
+    if isinstance(v, Affine):
+        return (v.p + v.q * k) / v.r + 0.0 * k
+    a = np.asarray(v, dtype=float)
+    if a.shape[0] < m:
+        raise ValueError("explicit diagonal shorter than the requested size")
+    return a[:m]
+
+
+class Tridiagonal:
+    """Tridiagonal(dl, d, du) with lazy ∞ diagonals (LazyBandedMatrices.Tridiagonal in test_bidiagonalconjugation.jl)."""
+
+    def __init__(self, dl, d, du):
+        self.dl, self.d, self.du = dl, d, du
+
+    def bands(self, m):
+        return np.stack([_lazy_values(self.dl, m), _lazy_values(self.d, m), _lazy_values(self.du, m)])
+
+
+class TridiagonalConjugation:
+    """TridiagonalConjugation(R, X): the ∞ tridiagonal matrix Tridiagonal(R*X/R), filled lazily like the reference's
+    TridiagonalConjugationData (src/banded/tridiagonalconjugation.jl:224-303).  R: an upper triangular BandedMatrix
+    (bandwidths (0, 1) or (0, 2); wider upper bands do not enter the tridiagonal part) or `cholesky(S)` of a symmetric
+    positive definite banded operator (the factor then stays on the device).  Indexing `Y[i, j]` is 1-based."""
+
+    def __init__(self, R, X: Tridiagonal):
+        self.R, self.X = R, X
+        self._n = 0
+        self._Y = None
+
+    def resizedata(self, n):
+        if n <= self._n:
+            return self
+        n = max(int(n), 2 * self._n, 100)
+        Xb = self.X.bands(n + 1)
+        if isinstance(self.R, AdaptiveCholesky):
+            A = self.R.A
+            p, q, r, head = A.generators()
+            _, u = A.bandwidths
+            sel = slice(0, u + 1)
+            out = _b.chol_tridiagonal_conjugation(u, p[None, sel], q[None, sel], Xb, n, r=r[None, sel],
+                                                  shift=[A.shift] if A.shift else None, head=None if head is None else head[sel])
+            _raise_status(out["status"][0], "TridiagonalConjugation(cholesky(S).U, X)")
+            self._Y = out["Y"][0]
+        else:
+            Rb = self.R
+            U = np.stack([_lazy_values(Rb._diag(d) if d in Rb.diags else Fill(0.0), n + 1) for d in (0, 1, 2)])
+            if Rb.shift:
+                U[0] -= Rb.shift
+            self._Y = _b.tridiagonal_conjugation(U, Xb, n)[0]
+        self._n = n
+        return self
+
+    def __getitem__(self, ij):
+        i, j = ij
+        if abs(i - j) > 1:
+            return 0.0
+        self.resizedata(max(i, j) + 1)
+        return self._Y[1 + (j - i), min(i, j) - 1]
+
+    def bands(self, n):
+        """(dl, d, du)[:, :n]."""
+        self.resizedata(n)
+        return self._Y[:, :n]
+
+
+def SymTridiagonalConjugation(R, X):
+    """Same data, read as a symmetric tridiagonal matrix (diagonal and super-diagonal; tridiagonalconjugation.jl:300-303)."""
+    return TridiagonalConjugation(R, X)
+
+
+def BidiagonalConjugation(U_bands, C_bands, n, uplo="U"):
+    """BidiagonalConjugation(U, X, V, uplo) from the tridiagonal parts of U and C = X*V (3 x m arrays: sub-, main,
+    super-diagonal): returns (dv, ev) of Bidiagonal(inv(U) X V) (src/banded/bidiagonalconjugation.jl:19-60)."""
+    dv, ev = _b.bidiagonal_conjugation(U_bands, C_bands, n, uplo)
+    return dv[0], ev[0]
+
+
+# ---- block-banded operators (KronTrav) -------------------------------------------------------------------------
+
+class KronTravSum:
+    """alpha*KronTrav(T1, Eye) + beta*KronTrav(Eye, T2) - lam*I with T1, T2 ∞ tridiagonal (`Tridiagonal` of lazy diagonals):
+    the block-banded operators of test/test_infqr.jl:270-313 (block sizes 1, 2, 3, ...).  `A - c*I` / `A + B` compose."""
+
+    def __init__(self, T1, T2, alpha=0.0, beta=0.0, lam=0.0):
+        self.T1, self.T2, self.alpha, self.beta, self.lam = T1, T2, alpha, beta, lam
+
+    def __sub__(self, other):
+        if isinstance(other, UniformScaling):
+            return KronTravSum(self.T1, self.T2, self.alpha, self.beta, self.lam + other.lam)
+        return NotImplemented
+
+    def __add__(self, other):
+        if isinstance(other, KronTravSum):
+            T1 = self.T1 if self.alpha != 0 else other.T1
+            T2 = self.T2 if self.beta != 0 else other.T2
+            return KronTravSum(T1, T2, self.alpha + other.alpha, self.beta + other.beta, self.lam + other.lam)
+        if isinstance(other, UniformScaling):
+            return KronTravSum(self.T1, self.T2, self.alpha, self.beta, self.lam - other.lam)
+        return NotImplemented
+
+    def __rmul__(self, s):
+        return KronTravSum(self.T1, self.T2, s * self.alpha, s * self.beta, s * self.lam)
+
+    def solve(self, b, tolerance=1e-30, maxblocks=64):
+        """`A \\ b` = qr(A) \\ b by the adaptive block-banded QR (src/infqr.jl:303-337, 358-366)."""
+        bb = np.atleast_1d(np.asarray(b.head if isinstance(b, Vcat) else b, dtype=float))
+        m = maxblocks + 2
+        out = _b.qr_blockbanded_solve(self.T1.bands(m), self.T2.bands(m), self.alpha, self.beta, self.lam, b=bb,
+                                      tol=tolerance, maxblocks=maxblocks)
+        _raise_status(out["status"][0], "qr(A) \\ b (block-banded)")
+        return out["x"][0][: int(out["ncols"][0])]
+
+
+def KronTrav(A, B):
+    """KronTrav(T, Eye) or KronTrav(Eye, T) (LazyBandedMatrices; test_infqr.jl:271, 287): one factor must be `Eye`."""
+    if B is Eye and A is not Eye:
+        return KronTravSum(A, A, alpha=1.0)
+    if A is Eye and B is not Eye:
+        return KronTravSum(B, B, beta=1.0)
+    raise TypeError("KronTrav: exactly one factor must be Eye")
+
+
+class _EyeType:
+    pass
+
+
+Eye = _EyeType()
