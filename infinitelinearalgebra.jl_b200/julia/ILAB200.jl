@@ -166,4 +166,45 @@ function bessel_solve(zs::AbstractVector{<:Real}, b1::AbstractVector{<:Real}; ng
     qr_solve(1, 1, p, q, r, reshape(Vector{Float64}(b1), batch, 1); ncap=ncap, ngpus=ngpus)
 end
 
+"""
+    triconj(U, X, n; ngpus=1) -> Y (3 x n: dl, d, du)
+
+`Tridiagonal(U*X/U)` for one operator: `U` is `nbands x m` (rows `U[k,k]`, `U[k,k+1]`[, `U[k,k+2]`]), `X` is `3 x m`
+(`dl`, `d`, `du`), `m >= n+1`.  Replaces `upper_mul_tri_triview!` + `tri_mul_invupper_triview!` as driven by
+`resizedata!(::TridiagonalConjugationData, n)` (src/banded/tridiagonalconjugation.jl:10-215, 260-282).
+"""
+function triconj(U::Matrix{Float64}, X::Matrix{Float64}, n::Integer; ngpus::Integer=1)
+    Ut = permutedims(U); Xt = permutedims(X)          # column-major m x nbands == the ABI's band-major rows
+    m = size(Ut, 1)
+    Y = Matrix{Float64}(undef, n, 3)
+    rc = ccall((:ila_triconj_bands_f64, lib), Cint,
+               (Cint, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Cint),
+               size(U, 1), 1, n, Ut, m, Xt, size(Xt, 1), 1, Y, C_NULL, ngpus)
+    check(rc)
+    permutedims(Y)
+end
+
+"""
+    blockbanded_solve(T1, T2, α, β, λs; b=[1.0], tol=1e-30, colgrowth=300, maxblocks=64, ngpus=1) -> (x, ncols, status)
+
+`(α KronTrav(T1, Eye) + β KronTrav(Eye, T2) - λ I) \ [b; zeros(∞)]` for every λ in `λs` by the adaptive block-banded QR
+(src/infqr.jl:23-28, 68-86, 303-337, 358-366).  `T1`, `T2`: `3 x m` bands (`dl`, `d`, `du`), `m >= maxblocks+1`.
+Column `i` of `x` is the zero-padded solution for `λs[i]`, `ncols[i]` its length.
+"""
+function blockbanded_solve(T1::Matrix{Float64}, T2::Matrix{Float64}, α::Real, β::Real, λs::AbstractVector{<:Real};
+                           b::Vector{Float64}=[1.0], tol::Real=1e-30, colgrowth::Integer=300, maxblocks::Integer=64,
+                           ngpus::Integer=1)
+    batch = length(λs); xld = maxblocks * (maxblocks + 1) ÷ 2
+    T1t = permutedims(T1); T2t = permutedims(T2)
+    x = Matrix{Float64}(undef, xld, batch); ncols = Vector{Int64}(undef, batch)
+    nblocks = Vector{Int32}(undef, batch); status = Vector{Int32}(undef, batch)
+    rc = ccall((:ila_qr_blockbanded_solve_f64, lib), Cint,
+               (Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Float64,
+                Cint, Cint, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Cint),
+               batch, fill(Float64(α), batch), fill(Float64(β), batch), Vector{Float64}(λs), T1t, T2t, size(T1t, 1), length(b),
+               repeat(b, batch), tol, colgrowth, maxblocks, x, xld, ncols, nblocks, C_NULL, status, ngpus)
+    check(rc)
+    x, ncols, status
+end
+
 end # module
