@@ -313,6 +313,8 @@ int ila_qr_blockbanded_solve_f64(int64_t batch, const double *alpha, const doubl
 /* device-resident form: the caller owns every buffer; d_work holds batch x ila_qr_blockbanded_work_doubles(maxblocks) doubles
  * (the R block rows), d_qtb and d_x batch x xld. */
 int ila_qr_blockbanded_work_doubles(int maxblocks, int64_t *per_operator);
+/* 0 (default): four reflectors per pass over the trailing panel; 1: one reflector per pass (validation: same results to rounding) */
+int ila_qr_blockbanded_set_mode(int mode);
 int ila_qr_blockbanded_solve_f64_dev(int64_t batch, const double *d_alpha, const double *d_beta, const double *d_lam,
                                      const double *d_T1, const double *d_T2, int64_t tld, int nb, const double *d_b, double tol,
                                      int colgrowth, int maxblocks, double *d_work, double *d_qtb, double *d_x, int64_t xld,

@@ -689,6 +689,13 @@ int ila_biconj_bands_f64(int upper, int64_t batch, int64_t n, const double *U, c
 
 // ================================ K11: adaptive block-banded QR solve ====================================
 
+int ila_qr_blockbanded_set_mode(int mode)
+{
+    if (mode != 0 && mode != 1) return set_error(ILA_ERR_ARG, "qr_blockbanded mode must be 0 (blocked reflectors) or 1 (one reflector per pass)");
+    qr_blockbanded_set_mode(mode);
+    return 0;
+}
+
 int ila_qr_blockbanded_work_doubles(int maxblocks, int64_t *per_operator)
 {
     if (maxblocks < 3 || maxblocks > 64 || !per_operator) return set_error(ILA_ERR_ARG, "qr_blockbanded_work_doubles: bad arguments");

@@ -136,6 +136,7 @@ struct BlockQrArgs {
 };
 int qr_blockbanded_smem_bytes(int maxblocks, int *hmax_out, int *wmax_out);
 int launch_qr_blockbanded(BlockQrArgs a, cudaStream_t s);
+void qr_blockbanded_set_mode(int mode);
 
 // from ql_finite_section.cu
 template <typename T>

@@ -66,8 +66,174 @@ __device__ __forceinline__ void reflector_scalars(double alpha, double ss, doubl
     }
 }
 
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- blocked variant: four reflectors per pass over the trailing panel ---------------------------------------------
+// Panel layout in registers of ONE warp: row i (relative to the panel's first pivot row) lives in lane i & 31, chunk i >> 5
+// (m <= 127 rows = 4 chunks), the (at most) four pivot columns side by side.  V[i][0..3] (explicit 1 on the diagonal, 0
+// above it) goes to shared memory as 32-byte rows, with the taus and the Gram entries g_kl = v_k . v_l that let a trailing
+// column apply all four reflectors from ONE set of dot products:
+//     w0 = tau0 d0,  w1 = tau1 (d1 - w0 g10),  w2 = tau2 (d2 - w0 g20 - w1 g21),  w3 = tau3 (d3 - w0 g30 - w1 g31 - w2 g32),
+//     col -= w0 v0 + w1 v1 + w2 v2 + w3 v3                      (d_k = v_k . col on the column BEFORE the panel).
+__device__ __forceinline__ void panel_factor(Panel &pn, double *Vbuf, double *psb, int cp, int kb, int m, int lane)
+{
+    const int ld = pn.ld;
+    double a[4][4];
+    int rowoff[4];
+    bool valid[4];
+    int cslot[4];
+    {
+        int sl = pn.cs(cp);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { cslot[k] = sl; if (++sl == pn.wmax) sl = 0; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int i = lane + 32 * q;
+        valid[q] = i < m;
+        rowoff[q] = pn.rs(cp + i) * ld;
+#pragma unroll
+        for (int k = 0; k < 4; k++) a[q][k] = (valid[q] && k < kb) ? pn.P[rowoff[q] + cslot[k]] : 0.0;
+    }
+    double tau[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        tau[k] = 0.0;
+        if (k < kb) {
+            double ss = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = lane + 32 * q;
+                if (i > k && valid[q]) ss = fma(a[q][k], a[q][k], ss);
+            }
+            ss = warp_sum(ss);
+            const double alpha = __shfl_sync(0xffffffffu, a[0][k], k);
+            double inv, beta;
+            reflector_scalars(alpha, ss, tau[k], inv, beta);
+            // rows above the diagonal of this column are final R entries; the diagonal becomes beta
+            if (lane < k) pn.P[rowoff[0] + cslot[k]] = a[0][k];
+            if (lane == k) pn.P[rowoff[0] + cslot[k]] = beta;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = lane + 32 * q;
+                a[q][k] = (i > k && valid[q]) ? a[q][k] * inv : ((i == k && tau[k] != 0.0) ? 1.0 : 0.0);
+            }
+            double d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int l = k + 1; l < 4; l++) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) d[l] = fma(a[q][k], a[q][l], d[l]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int l = k + 1; l < 4; l++) d[l] += __shfl_xor_sync(0xffffffffu, d[l], o);
+            }
+#pragma unroll
+            for (int l = k + 1; l < 4; l++) {
+                const double w = tau[k] * d[l];
+#pragma unroll
+                for (int q = 0; q < 4; q++) a[q][l] = fma(-w, a[q][k], a[q][l]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) a[q][k] = 0.0;
+        }
+    }
+    double g[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};      // g10, g20, g21, g30, g31, g32
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        g[0] = fma(a[q][1], a[q][0], g[0]);
+        g[1] = fma(a[q][2], a[q][0], g[1]); g[2] = fma(a[q][2], a[q][1], g[2]);
+        g[3] = fma(a[q][3], a[q][0], g[3]); g[4] = fma(a[q][3], a[q][1], g[4]); g[5] = fma(a[q][3], a[q][2], g[5]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int e = 0; e < 6; e++) g[e] += __shfl_xor_sync(0xffffffffu, g[e], o);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int i = lane + 32 * q;
+        if (valid[q]) {
+            double2 *dst = reinterpret_cast<double2 *>(Vbuf + i * 4);
+            dst[0] = make_double2(a[q][0], a[q][1]);
+            dst[1] = make_double2(a[q][2], a[q][3]);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) psb[k] = tau[k];
+#pragma unroll
+        for (int e = 0; e < 6; e++) psb[4 + e] = g[e];
+    }
+}
+
+// the current panel's four reflectors applied by ONE warp to the (at most four) columns of the next panel
+__device__ __forceinline__ void panel_apply(Panel &pn, const double *Vbuf, const double *psb, int cp, int m, int cn, int kbn, int lane)
+{
+    const int ld = pn.ld;
+    double a[4][4], v[4][4];
+    int rowoff[4];
+    bool valid[4];
+    int cslot[4];
+    {
+        int sl = pn.cs(cn);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { cslot[k] = sl; if (++sl == pn.wmax) sl = 0; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int i = lane + 32 * q;
+        valid[q] = i < m;
+        rowoff[q] = pn.rs(cp + i) * ld;
+#pragma unroll
+        for (int k = 0; k < 4; k++) a[q][k] = (valid[q] && k < kbn) ? pn.P[rowoff[q] + cslot[k]] : 0.0;
+        if (valid[q]) {
+            const double2 *src = reinterpret_cast<const double2 *>(Vbuf + i * 4);
+            const double2 x0 = src[0], x1 = src[1];
+            v[q][0] = x0.x; v[q][1] = x0.y; v[q][2] = x1.x; v[q][3] = x1.y;
+        } else {
+            v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double tau = psb[k];
+        double d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) d[l] = fma(v[q][k], a[q][l], d[l]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) d[l] += __shfl_xor_sync(0xffffffffu, d[l], o);
+        }
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            const double w = tau * d[l];
+#pragma unroll
+            for (int q = 0; q < 4; q++) a[q][l] = fma(-w, v[q][k], a[q][l]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (valid[q] && k < kbn) pn.P[rowoff[q] + cslot[k]] = a[q][k];
+    }
+}
+
 } // namespace
 
+template <bool BLOCKED>
 __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs A)
 {
     extern __shared__ double smem[];
@@ -175,6 +341,88 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
             load_block_rows(J + 1, J);
             __syncthreads();
             K11_ACC(tp_a);
+            if constexpr (BLOCKED) {
+            // (b) blocked: panels of four pivot columns.  Warp 0 is the panel warp: while the other 13 warps apply panel p to
+            // the columns behind the NEXT panel, it applies panel p to the next panel's columns and factorizes them (registers
+            // + shuffles), so the trailing update — the shared-memory-bound part — never waits for a panel factorization
+            // except at the first panel of a block column.
+            double *Vp = smem + (size_t)hmax * ld;            // [2][hmax][4]
+            double *ps = Vp + 2 * (size_t)hmax * 4;           // [2][16]
+            const int cend = c0 + ncols, rend = c0 + nrows;
+            if (warp == 0) panel_factor(pn, Vp, ps, c0, min(4, J), nrows, lane);
+            __syncthreads();
+            K11_ACC(tp_n);
+            int buf = 0;
+            for (int j0 = 0; j0 < J; j0 += 4) {
+                const int cp = c0 + j0, kb = min(4, J - j0), m = rend - cp;
+                const int kbn = min(4, J - j0 - kb);
+                const double *Vb = Vp + (size_t)buf * hmax * 4;
+                const double *psb = ps + buf * 16;
+                if (warp == 0) {
+                    if (kbn > 0) {
+                        panel_apply(pn, Vb, psb, cp, m, cp + kb, kbn, lane);
+                        __syncwarp();
+                        panel_factor(pn, Vp + (size_t)(buf ^ 1) * hmax * 4, ps + (buf ^ 1) * 16, cp + kb, kbn, m - kb, lane);
+                    }
+                } else {
+                    const int tq = (warp - 1) * 16 + (lane & 15);
+                    const int first = cp + kb + kbn, ntrail = cend - first;
+                    const bool act = tq <= ntrail;
+                    int scol = pn.cs(first) + tq;
+                    if (scol >= wmax) scol -= wmax;
+                    double *__restrict__ col = pn.P + (tq < ntrail ? scol : wmax);
+                    const int cnt = act ? (m - half + 1) >> 1 : 0;       // rows i = half, half+2, ... < m
+                    const int hm = pn.hmask;
+                    const double2 *__restrict__ V2 = reinterpret_cast<const double2 *>(Vb);
+                    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+                    {
+                        int r = pn.rs(cp + half), vi = half, k = 0;
+                        for (; k + 2 <= cnt; k += 2) {
+                            const int oa = r * ld, ob = ((r + 2) & hm) * ld;
+                            r = (r + 4) & hm;
+                            const double qa = col[oa], qb = col[ob];
+                            const double2 a0 = V2[vi * 2], a1 = V2[vi * 2 + 1], b0 = V2[vi * 2 + 4], b1 = V2[vi * 2 + 5];
+                            vi += 4;
+                            d0 = fma(a0.x, qa, d0); d1 = fma(a0.y, qa, d1); d2 = fma(a1.x, qa, d2); d3 = fma(a1.y, qa, d3);
+                            d0 = fma(b0.x, qb, d0); d1 = fma(b0.y, qb, d1); d2 = fma(b1.x, qb, d2); d3 = fma(b1.y, qb, d3);
+                        }
+                        if (k < cnt) {
+                            const double qa = col[r * ld];
+                            const double2 a0 = V2[vi * 2], a1 = V2[vi * 2 + 1];
+                            d0 = fma(a0.x, qa, d0); d1 = fma(a0.y, qa, d1); d2 = fma(a1.x, qa, d2); d3 = fma(a1.y, qa, d3);
+                        }
+                    }
+                    d0 += __shfl_xor_sync(0xffffffffu, d0, 16); d1 += __shfl_xor_sync(0xffffffffu, d1, 16);
+                    d2 += __shfl_xor_sync(0xffffffffu, d2, 16); d3 += __shfl_xor_sync(0xffffffffu, d3, 16);
+                    const double w0 = psb[0] * d0;
+                    const double w1 = psb[1] * fma(-w0, psb[4], d1);
+                    const double w2 = psb[2] * fma(-w1, psb[6], fma(-w0, psb[5], d2));
+                    const double w3 = psb[3] * fma(-w2, psb[9], fma(-w1, psb[8], fma(-w0, psb[7], d3)));
+                    {
+                        int r = pn.rs(cp + half), vi = half, k = 0;
+                        for (; k + 2 <= cnt; k += 2) {
+                            const int oa = r * ld, ob = ((r + 2) & hm) * ld;
+                            r = (r + 4) & hm;
+                            double qa = col[oa], qb = col[ob];
+                            const double2 a0 = V2[vi * 2], a1 = V2[vi * 2 + 1], b0 = V2[vi * 2 + 4], b1 = V2[vi * 2 + 5];
+                            vi += 4;
+                            qa = fma(-w0, a0.x, qa); qa = fma(-w1, a0.y, qa); qa = fma(-w2, a1.x, qa); qa = fma(-w3, a1.y, qa);
+                            qb = fma(-w0, b0.x, qb); qb = fma(-w1, b0.y, qb); qb = fma(-w2, b1.x, qb); qb = fma(-w3, b1.y, qb);
+                            col[oa] = qa; col[ob] = qb;
+                        }
+                        if (k < cnt) {
+                            const int oa = r * ld;
+                            double qa = col[oa];
+                            const double2 a0 = V2[vi * 2], a1 = V2[vi * 2 + 1];
+                            qa = fma(-w0, a0.x, qa); qa = fma(-w1, a0.y, qa); qa = fma(-w2, a1.x, qa); qa = fma(-w3, a1.y, qa);
+                            col[oa] = qa;
+                        }
+                    }
+                }
+                __syncthreads();
+                buf ^= 1;
+            }
+            } else {
             // (b) Householder QR of block column J.  The scalars of column j+1 are formed by the pair that updates it (the sum
             // of squares rides on its update pass), so only the first column of a block column needs a reduction of its own
             // and there is ONE barrier per column.
@@ -268,6 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                 }
                 if (++csc == wmax) csc = 0;
                 __syncthreads();
+            }
             }
             // (c) rows of block J are final: R[J, J..J+2] and (Q'b)[J] leave the panel (one warp per row, coalesced)
             K11_ACC(tp_j);
@@ -369,6 +618,9 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     }
 }
 
+static int g_blockqr_mode = 0;     // 0 = blocked reflectors (default), 1 = one reflector per pass (validation)
+void qr_blockbanded_set_mode(int mode) { g_blockqr_mode = mode; }
+
 int qr_blockbanded_smem_bytes(int maxblocks, int *hmax_out, int *wmax_out)
 {
     int hmax = 8;
@@ -376,7 +628,7 @@ int qr_blockbanded_smem_bytes(int maxblocks, int *hmax_out, int *wmax_out)
     const int wmax = 3 * maxblocks;
     if (hmax_out) *hmax_out = hmax;
     if (wmax_out) *wmax_out = wmax;
-    size_t need = (size_t)hmax * (wmax + 1) * sizeof(double);
+    size_t need = ((size_t)hmax * (wmax + 1) + 2 * (size_t)hmax * 4 + 32) * sizeof(double);
     const size_t backsub = (size_t)(64 * 65 + 64 + maxblocks * (maxblocks + 1) / 2 + 8) * sizeof(double);
     if (need < backsub) need = backsub;
     return (int)need;
@@ -391,10 +643,12 @@ int launch_qr_blockbanded(BlockQrArgs a, cudaStream_t s)
     ILA_CUDA_CHECK(cudaGetDevice(&dev));
     static int opted[16] = {};
     if (bytes > 48 * 1024 && (dev >= 16 || opted[dev] < bytes)) {        // the > 48 KB opt-in is per device
-        ILA_CUDA_CHECK(cudaFuncSetAttribute(qr_blockbanded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        ILA_CUDA_CHECK(cudaFuncSetAttribute(qr_blockbanded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        ILA_CUDA_CHECK(cudaFuncSetAttribute(qr_blockbanded_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
         if (dev < 16) opted[dev] = bytes;
     }
-    qr_blockbanded_kernel<<<(unsigned)a.batch, kThreads, bytes, s>>>(a);
+    if (g_blockqr_mode == 1) qr_blockbanded_kernel<false><<<(unsigned)a.batch, kThreads, bytes, s>>>(a);
+    else qr_blockbanded_kernel<true><<<(unsigned)a.batch, kThreads, bytes, s>>>(a);
     count_launch();
     ILA_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -34,7 +34,20 @@ struct TcRow {
     double dl, d, du, uxdl, uxd, uxdu;
 };
 
-// closed-form row k (1-based) from accessors R0,R1,R2 (rows of U) and the X bands
+// a / b with the refined reciprocal of b shared between the quotients of one row (same bits as ediv: div_refined takes the
+// reciprocal as an argument; outside the exponent boxes the IEEE intrinsic)
+struct Den {
+    double b, r;
+    bool ok;
+    __device__ __forceinline__ explicit Den(double b_) : b(b_), r(rcp_refined(b_)), ok(inbox_den(b_)) {}
+    __device__ __forceinline__ double div(double a) const
+    {
+        if (ok && (inbox(a) || a == 0.0)) return div_refined(a, b, r);
+        return __ddiv_rn(a, b);
+    }
+};
+
+// closed-form row k (1-based) from accessors R0,R1,R2 (rows of U) and the X bands; 7 quotients over 3 denominators
 template <class FR0, class FR1, class FR2, class FX0, class FX1, class FX2>
 __device__ __forceinline__ TcRow triconj_row(int64_t k, FR0 R0, FR1 R1, FR2 R2, FX0 Xdl, FX1 Xd, FX2 Xdu)
 {
@@ -43,22 +56,24 @@ __device__ __forceinline__ TcRow triconj_row(int64_t k, FR0 R0, FR1 R1, FR2 R2, 
     const double a = zadd(zmul(Ukk, xd_k), zmul(Uk1, xdl_k));
     const double b = zadd(zadd(zmul(Ukk, Xdu(k)), zmul(Uk1, Xd(k + 1))), zmul(Uk2, Xdl(k + 1)));
     const double cn = zmul(Unn, xdl_k);
+    const Den dkk(Ukk), dnn(Unn);
     TcRow r;
     r.uxdl = cn; r.uxd = a; r.uxdu = b;
-    r.dl = ediv(cn, Ukk);
-    const double tail = zsub(b, ediv(zmul(a, Uk1), Ukk));
+    r.dl = dkk.div(cn);
+    const double tail = zsub(b, dkk.div(zmul(a, Uk1)));
     double pre;
     if (k == 1) {
-        r.d = ediv(a, Ukk);
+        r.d = dkk.div(a);
         pre = tail;
     } else {
         const double Rp = R0(k - 1), Rpn = R1(k - 1), Rpnn = R2(k - 1);
+        const Den dp(Rp);
         const double c = zmul(Ukk, Xdl(k - 1));
-        const double t = ediv(c, Rp);
-        r.d = ediv(zsub(a, ediv(zmul(c, Rpn), Rp)), Ukk);
-        pre = zadd(zmul(t, zsub(ediv(zmul(Rpn, Uk1), Ukk), Rpnn)), tail);
+        const double t = dp.div(c);
+        r.d = dkk.div(zsub(a, dp.div(zmul(c, Rpn))));
+        pre = zadd(zmul(t, zsub(dkk.div(zmul(Rpn, Uk1)), Rpnn)), tail);
     }
-    r.du = ediv(pre, Unn);
+    r.du = dnn.div(pre);
     return r;
 }
 

@@ -54,5 +54,16 @@ check("revchol_tridiag", f)
 g10 = [[1.0, 0, 0, 1, 0], [0.0, 1, 0, 1, 1], [1.0, 0, 0, 1, 0]]
 f = lambda g: (lambda o: (o["Lband"], o["V"], o["tau"], o["N"], o["status"]))(ila_b200.ql_finite_section(1, 1, g10, shift=np.linspace(-6, -3, 77), ngpus=g))
 check("ql_finite_section", f)
+rng = np.random.default_rng(2)
+Ut = rng.normal(size=(37, 3, 801)) * 0.3; Ut[:, 0] = 1 + rng.random((37, 801)); Xt = rng.normal(size=(37, 3, 801))
+check("tridiagonal_conjugation", lambda g: (ila_b200.tridiagonal_conjugation(Ut, Xt, 800, ngpus=g),))
+check("bidiagonal_conjugation", lambda g: ila_b200.bidiagonal_conjugation(Ut, Xt, 800, "U", ngpus=g))
+kk = np.arange(1, 421, dtype=np.float64); ee = kk / np.sqrt(4 * kk * kk - 1)
+Xl = np.stack([ee, np.zeros(420), ee]); hd = np.stack([-ee[:410], np.zeros(410)])
+f = lambda g: (lambda o: (o["Y"], o["status"]))(ila_b200.chol_tridiagonal_conjugation(1, np.zeros((1, 2)), np.zeros((1, 2)), Xl, 400, shift=-np.linspace(1.05, 3, 45), head=hd, ngpus=g))
+check("chol_tridiagonal_conjugation", f)
+Tb = np.stack([np.full(50, 0.5), np.zeros(50), np.full(50, 0.5)])
+f = lambda g: (lambda o: (o["x"], o["ncols"], o["nblocks"], o["status"]))(ila_b200.qr_blockbanded_solve(Tb, Tb, 1.0, 1.0, np.linspace(4, 9, 21), tol=1e-12, maxblocks=40, ngpus=g))
+check("qr_blockbanded_solve", f)
 print("ALL OK" if ok else "FAILURES")
 sys.exit(0 if ok else 1)

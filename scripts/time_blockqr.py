@@ -11,6 +11,8 @@ L = lib()
 dev = torch.device("cuda:0")
 s = torch.cuda.current_stream()
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 592
+if len(sys.argv) > 2:
+    check(L.ila_qr_blockbanded_set_mode(int(sys.argv[2])))
 maxblocks = 64
 m = 80
 T = torch.tensor(np.stack([np.full(m, 0.5), np.zeros(m), np.full(m, 0.5)]), device=dev)

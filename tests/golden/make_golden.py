@@ -59,3 +59,26 @@ np.savez_compressed(os.path.join(HERE, "ql_solve.npz"), tri_col=col3, tri_lam=np
                     tri_status=s3, bull_col=colb, bull_lam=lamb, bull_b=np.array([1.0, 0.5j, -0.25]), bull_x=xb,
                     bull_status=sb)
 print("wrote fixtures")
+
+# triconj.npz : Tridiagonal(U*X/U) for the P -> C^(3/2) and P^(1,0) -> P^(2,0) pairs of test_bidiagonalconjugation.jl:111-120
+#               (n = 200) and the Cholesky case (:159-164, n = 100)
+# blockqr.npz : adaptive block-banded QR solves of test_infqr.jl:270-312 (x prefixes, Q'b prefixes, counts)
+sys.path.insert(0, os.path.dirname(HERE))
+from triconj_cases import cholesky_case, reference_pairs   # noqa: E402
+from oracle import block_qr as bqr                          # noqa: E402
+pairs = reference_pairs(203)
+Y1 = ob.tridiagonal_conjugation(pairs[1][1], pairs[1][2], 200)[0]
+Y2 = ob.tridiagonal_conjugation(pairs[2][1], pairs[2][2], 200)[0]
+u_, p_, q_, head_, X_, M_ = cholesky_case(110)
+cg_ = (100 + 4) // 2
+oc = ob.chol_banded_solve(u_, p_, q_, head=head_, b=[1.0], tol=np.inf, colgrowth=cg_, ncap=2 * cg_ + 3 * u_ + 2, want_factors=True)
+Uc = np.stack([oc["factors"][0][d:102 + d, u_ - d] for d in range(3)])
+Y3 = ob.tridiagonal_conjugation(Uc, X_, 100)[0]
+np.savez_compressed(os.path.join(HERE, "triconj.npz"), Y_P_C32=Y1, Y_P10_P20=Y2, Y_chol=Y3)
+T_ = bqr.toeplitz_bands(0.0, 0.5, 80)
+cases = [(1.0, 0.0, 2.0), (0.0, 1.0, 2.0), (1.0, 1.0, 4.0), (2.0, 1.0, 8.0)]
+outs = [bqr.block_qr_solve(T_, T_, *c) for c in cases]
+np.savez_compressed(os.path.join(HERE, "blockqr.npz"), cases=np.array(cases), ncols=np.array([o["ncols"] for o in outs]),
+                    nblocks=np.array([o["nblocks"] for o in outs]), x=np.stack([o["x"][:300] for o in outs]),
+                    qtb=np.stack([o["qtb"][:300] for o in outs]))
+print("wrote triconj / blockqr fixtures")

@@ -9,6 +9,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
+@pytest.fixture(params=[0, 1], ids=["blocked", "one-reflector"], autouse=True)
+def _mode(request, ila):
+    """Every test runs with four reflectors per pass (default) and with one reflector per pass (validation mode)."""
+    assert ila.lib().ila_qr_blockbanded_set_mode(request.param) == 0
+    yield
+    ila.lib().ila_qr_blockbanded_set_mode(0)
+
+
 def _T(m=80):
     from oracle import block_qr as bq
     return bq.toeplitz_bands(0.0, 0.5, m)

@@ -44,3 +44,20 @@ def test_toeplitz_fixtures():
     assert np.array_equal(st, s["bull_status"])
     ok = st == 0
     assert np.allclose(x[ok], s["bull_x"][ok], rtol=1e-12, atol=1e-13) and np.all(np.isnan(x[~ok]))
+
+
+def test_triconj_and_blockqr_fixtures():
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from triconj_cases import cholesky_case, reference_pairs
+    from oracle import block_qr as bqr
+    g = np.load(os.path.join(G, "triconj.npz"))
+    pairs = reference_pairs(203)
+    assert np.array_equal(ob.tridiagonal_conjugation(pairs[1][1], pairs[1][2], 200)[0], g["Y_P_C32"])
+    assert np.array_equal(ob.tridiagonal_conjugation(pairs[2][1], pairs[2][2], 200)[0], g["Y_P10_P20"])
+    b = np.load(os.path.join(G, "blockqr.npz"))
+    T = bqr.toeplitz_bands(0.0, 0.5, 80)
+    for i, c in enumerate(b["cases"]):
+        o = bqr.block_qr_solve(T, T, *c)
+        assert o["ncols"] == b["ncols"][i] and o["nblocks"] == b["nblocks"][i]
+        assert np.abs(o["x"][:300] - b["x"][i]).max() <= 1e-13 and np.abs(o["qtb"][:300] - b["qtb"][i]).max() <= 1e-13
