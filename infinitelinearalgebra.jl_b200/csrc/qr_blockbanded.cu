@@ -73,6 +73,55 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// all-reduce of N values (N = 4 or 16) over the 32 lanes with HALVING payloads: at the stage with lane offset o a lane keeps
+// the half of its values selected by its bit o and sends the other half, so N/2 + N/4 + ... + 1 shuffles bring every value
+// to one lane group (plus log2(32/N) single-value stages); N more shuffles broadcast the sums back.  16 values: 32 shuffles
+// instead of 80.
+template <int N>
+__device__ __forceinline__ void packed_allreduce(double (&v)[N], int lane)
+{
+    static_assert(N == 4 || N == 16, "packed_allreduce: N must be 4 or 16");
+    int o = 16;
+    if constexpr (N == 16) {
+        {
+            const bool up = lane & 16;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const double keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+        }
+        {
+            const bool up = lane & 8;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+        }
+        o = 4;
+    }
+    {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const double keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+        o >>= 1;
+    }
+    {
+        const bool up = lane & o;
+        const double keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        o >>= 1;
+    }
+    for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    const double sum = v[0];
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = __shfl_sync(0xffffffffu, sum, j * (32 / N));
+}
+
 // ---- blocked variant: four reflectors per pass over the trailing panel ---------------------------------------------
 // Panel layout in registers of ONE warp: row i (relative to the panel's first pivot row) lives in lane i & 31, chunk i >> 5
 // (m <= 127 rows = 4 chunks), the (at most) four pivot columns side by side.  V[i][0..3] (explicit 1 on the diagonal, 0
@@ -80,6 +129,32 @@ __device__ __forceinline__ double warp_sum(double v)
 // column apply all four reflectors from ONE set of dot products:
 //     w0 = tau0 d0,  w1 = tau1 (d1 - w0 g10),  w2 = tau2 (d2 - w0 g20 - w1 g21),  w3 = tau3 (d3 - w0 g30 - w1 g31 - w2 g32),
 //     col -= w0 v0 + w1 v1 + w2 v2 + w3 v3                      (d_k = v_k . col on the column BEFORE the panel).
+// reflector scalars without divisions on the dependent chain: y ~ 1/sqrt(alpha^2 + ss) by MUFU + two Newton steps,
+// norm = s2*y with one correction, tau = 1 + |alpha|/norm, 1/(alpha - beta) = sign(alpha)/(|alpha| + norm)
+__device__ __forceinline__ void reflector_scalars_fast(double alpha, double ss, double &tau, double &inv, double &beta)
+{
+    tau = 0.0; inv = 0.0; beta = alpha;
+    if (ss != 0.0) {
+        const double s2 = fma(alpha, alpha, ss);
+        if (inbox_sq(s2)) {
+            double y;
+            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s2));
+            const double h = 0.5 * s2;
+            y = fma(y, fma(-h * y, y, 0.5), y);
+            y = fma(y, fma(-h * y, y, 0.5), y);
+            double nrm = s2 * y;
+            nrm = fma(fma(-nrm, nrm, s2), 0.5 * y, nrm);
+            const double aa = fabs(alpha), den = aa + nrm;
+            tau = fma(aa, y, 1.0);
+            tau = fma(fma(-(tau - 1.0), nrm, aa), y, tau);         // one correction of |alpha|/norm
+            beta = -copysign(nrm, alpha);
+            inv = copysign(rcp_refined(den), alpha);
+        } else {
+            reflector_scalars(alpha, ss, tau, inv, beta);
+        }
+    }
+}
+
 __device__ __forceinline__ void panel_factor(Panel &pn, double *Vbuf, double *psb, int cp, int kb, int m, int lane)
 {
     const int ld = pn.ld;
@@ -100,43 +175,50 @@ __device__ __forceinline__ void panel_factor(Panel &pn, double *Vbuf, double *ps
 #pragma unroll
         for (int k = 0; k < 4; k++) a[q][k] = (valid[q] && k < kb) ? pn.P[rowoff[q] + cslot[k]] : 0.0;
     }
-    double tau[4];
+    double tau[4] = {0.0, 0.0, 0.0, 0.0};
+    double g[4][4];                                   // g[k][l], l < k: v_k . v_l
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int l = 0; l < 4; l++) g[k][l] = 0.0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        tau[k] = 0.0;
         if (k < kb) {
-            double ss = 0.0;
+            // ONE reduction round per pivot column: its sum of squares below the diagonal and its (unscaled) dot products with
+            // the columns to its right (the reflector is applied to them) and with the finished reflectors to its left (Gram)
+            double red[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int i = lane + 32 * q;
-                if (i > k && valid[q]) ss = fma(a[q][k], a[q][k], ss);
-            }
-            ss = warp_sum(ss);
-            const double alpha = __shfl_sync(0xffffffffu, a[0][k], k);
-            double inv, beta;
-            reflector_scalars(alpha, ss, tau[k], inv, beta);
-            // rows above the diagonal of this column are final R entries; the diagonal becomes beta
-            if (lane < k) pn.P[rowoff[0] + cslot[k]] = a[0][k];
-            if (lane == k) pn.P[rowoff[0] + cslot[k]] = beta;
+                if (i > k && valid[q]) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int i = lane + 32 * q;
-                a[q][k] = (i > k && valid[q]) ? a[q][k] * inv : ((i == k && tau[k] != 0.0) ? 1.0 : 0.0);
+                    for (int l = 0; l < 4; l++) red[l] = fma(a[q][k], a[q][l], red[l]);
+                }
             }
-            double d[4] = {0.0, 0.0, 0.0, 0.0};
+            double row_k[4];                          // row k of the panel (lane k, chunk 0)
 #pragma unroll
-            for (int l = k + 1; l < 4; l++) {
-#pragma unroll
-                for (int q = 0; q < 4; q++) d[l] = fma(a[q][k], a[q][l], d[l]);
-            }
+            for (int l = 0; l < 4; l++) row_k[l] = __shfl_sync(0xffffffffu, a[0][l], k);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                for (int l = k + 1; l < 4; l++) d[l] += __shfl_xor_sync(0xffffffffu, d[l], o);
+                for (int l = 0; l < 4; l++) red[l] += __shfl_xor_sync(0xffffffffu, red[l], o);
+            }
+            double inv, beta;
+            reflector_scalars_fast(row_k[k], red[k], tau[k], inv, beta);
+            // rows above the diagonal of this column are final R entries; the diagonal becomes beta
+            if (lane < k) pn.P[rowoff[0] + cslot[k]] = a[0][k];
+            if (lane == k) pn.P[rowoff[0] + cslot[k]] = beta;
+            const bool on = tau[k] != 0.0;
+#pragma unroll
+            for (int l = 0; l < k; l++) g[k][l] = on ? fma(inv, red[l], row_k[l]) : 0.0;      // v_k . v_l = v_l[k] + inv * sum
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = lane + 32 * q;
+                a[q][k] = (i > k && valid[q]) ? a[q][k] * inv : ((i == k && on) ? 1.0 : 0.0);
             }
 #pragma unroll
             for (int l = k + 1; l < 4; l++) {
-                const double w = tau[k] * d[l];
+                const double w = tau[k] * fma(inv, red[l], row_k[l]);
 #pragma unroll
                 for (int q = 0; q < 4; q++) a[q][l] = fma(-w, a[q][k], a[q][l]);
             }
@@ -144,18 +226,6 @@ __device__ __forceinline__ void panel_factor(Panel &pn, double *Vbuf, double *ps
 #pragma unroll
             for (int q = 0; q < 4; q++) a[q][k] = 0.0;
         }
-    }
-    double g[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};      // g10, g20, g21, g30, g31, g32
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        g[0] = fma(a[q][1], a[q][0], g[0]);
-        g[1] = fma(a[q][2], a[q][0], g[1]); g[2] = fma(a[q][2], a[q][1], g[2]);
-        g[3] = fma(a[q][3], a[q][0], g[3]); g[4] = fma(a[q][3], a[q][1], g[4]); g[5] = fma(a[q][3], a[q][2], g[5]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int e = 0; e < 6; e++) g[e] += __shfl_xor_sync(0xffffffffu, g[e], o);
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -169,12 +239,12 @@ __device__ __forceinline__ void panel_factor(Panel &pn, double *Vbuf, double *ps
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 4; k++) psb[k] = tau[k];
-#pragma unroll
-        for (int e = 0; e < 6; e++) psb[4 + e] = g[e];
+        psb[4] = g[1][0]; psb[5] = g[2][0]; psb[6] = g[2][1]; psb[7] = g[3][0]; psb[8] = g[3][1]; psb[9] = g[3][2];
     }
 }
 
-// the current panel's four reflectors applied by ONE warp to the (at most four) columns of the next panel
+// the current panel's four reflectors applied by ONE warp to the (at most four) columns of the next panel: all sixteen dot
+// products in one reduction round, then the same Gram recurrence as the trailing columns
 __device__ __forceinline__ void panel_apply(Panel &pn, const double *Vbuf, const double *psb, int cp, int m, int cn, int kbn, int lane)
 {
     const int ld = pn.ld;
@@ -202,25 +272,30 @@ __device__ __forceinline__ void panel_apply(Panel &pn, const double *Vbuf, const
             v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
         }
     }
+    double df[16];                                    // df[4k + l] = v_k . a_l
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const double tau = psb[k];
-        double d[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int l = 0; l < 4; l++) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) d[l] = fma(v[q][k], a[q][l], d[l]);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int l = 0; l < 4; l++) d[l] += __shfl_xor_sync(0xffffffffu, d[l], o);
-        }
+    for (int k = 0; k < 4; k++)
 #pragma unroll
         for (int l = 0; l < 4; l++) {
-            const double w = tau * d[l];
+            double t = 0.0;
 #pragma unroll
-            for (int q = 0; q < 4; q++) a[q][l] = fma(-w, v[q][k], a[q][l]);
+            for (int q = 0; q < 4; q++) t = fma(v[q][k], a[q][l], t);
+            df[4 * k + l] = t;
+        }
+    packed_allreduce<16>(df, lane);
+    const double t0 = psb[0], t1 = psb[1], t2 = psb[2], t3 = psb[3];
+    const double g10 = psb[4], g20 = psb[5], g21 = psb[6], g30 = psb[7], g31 = psb[8], g32 = psb[9];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        const double w0 = t0 * df[l];
+        const double w1 = t1 * fma(-w0, g10, df[4 + l]);
+        const double w2 = t2 * fma(-w1, g21, fma(-w0, g20, df[8 + l]));
+        const double w3 = t3 * fma(-w2, g32, fma(-w1, g31, fma(-w0, g30, df[12 + l])));
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double x = a[q][l];
+            x = fma(-w0, v[q][0], x); x = fma(-w1, v[q][1], x); x = fma(-w2, v[q][2], x); x = fma(-w3, v[q][3], x);
+            a[q][l] = x;
         }
     }
 #pragma unroll
@@ -244,8 +319,16 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     const int hmax = A.hmax, wmax = A.wmax, ld = wmax + 1;
     Panel pn{smem, hmax - 1, wmax, ld};
     const double al = A.alpha[inst], be = A.beta[inst], lam = A.lam[inst];
-    const double *T1 = A.T1, *T2 = A.T2;
-    const int64_t tld = A.tld;
+    // the 1-D operators' bands staged in shared memory (behind the panel, the V buffers and the panel scalars): the row
+    // generator reads them once per fresh row
+    constexpr int tld = 72;
+    double *T1 = smem + (size_t)hmax * ld + 2 * (size_t)hmax * 4 + 32, *T2 = T1 + 3 * tld;
+    for (int i = tid; i < 3 * tld; i += kThreads) {
+        const int band = i / tld, k = i % tld;
+        T1[i] = k <= A.maxblocks ? A.T1[band * A.tld + k] : 0.0;
+        T2[i] = k <= A.maxblocks ? A.T2[band * A.tld + k] : 0.0;
+    }
+    __syncthreads();
     const double *bi = A.b + inst * A.nb;
     const int nb = A.nb, cg = A.colgrowth, maxblocks = A.maxblocks;
     double *Rw = A.work + inst * A.work_stride;
@@ -280,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     };
 
 #ifdef ILA_K11_PROFILE
-    long long tp_a = 0, tp_n = 0, tp_j = 0, tp_c = 0, tp_bs = 0, tp_t0;
+    long long tp_a = 0, tp_n = 0, tp_j = 0, tp_c = 0, tp_bs = 0, tp_t0, tp_w0 = 0, tp_w1 = 0;
 #define K11_T0() tp_t0 = clock64()
 #define K11_ACC(v) do { const long long t_ = clock64(); v += t_ - tp_t0; tp_t0 = t_; } while (0)
 #else
@@ -358,6 +441,9 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                 const int kbn = min(4, J - j0 - kb);
                 const double *Vb = Vp + (size_t)buf * hmax * 4;
                 const double *psb = ps + buf * 16;
+#ifdef ILA_K11_PROFILE
+                const long long tw0 = clock64();
+#endif
                 if (warp == 0) {
                     if (kbn > 0) {
                         panel_apply(pn, Vb, psb, cp, m, cp + kb, kbn, lane);
@@ -419,6 +505,10 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                         }
                     }
                 }
+#ifdef ILA_K11_PROFILE
+                if (lane == 0 && warp == 0) tp_w0 += clock64() - tw0;
+                if (lane == 0 && warp == 1) tp_w1 += clock64() - tw0;
+#endif
                 __syncthreads();
                 buf ^= 1;
             }
@@ -586,9 +676,12 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                 if (warp == 0) {
                     // rows lane and lane+32 of the block in registers; x_k broadcast from its owner
                     double c_lo = lane < Kc ? cs_[lane] : 0.0, c_hi = lane + 32 < Kc ? cs_[lane + 32] : 0.0;
+                    // reciprocals of the diagonal off the dependent chain (x_k = c_k * (1/R_kk): one rounding more than the
+                    // reference's division, inside the 1e-12 bar)
+                    const double rd_lo = lane < Kc ? 1.0 / Ts[lane * ldt + lane] : 0.0;
+                    const double rd_hi = lane + 32 < Kc ? 1.0 / Ts[(lane + 32) * ldt + lane + 32] : 0.0;
                     for (int k = Kc - 1; k >= 0; k--) {
-                        const double num = __shfl_sync(0xffffffffu, k >= 32 ? c_hi : c_lo, k & 31);
-                        const double xk = num / Ts[k * ldt + k];
+                        const double xk = __shfl_sync(0xffffffffu, k >= 32 ? c_hi * rd_hi : c_lo * rd_lo, k & 31);
                         if (lane < k) c_lo = fma(-Ts[lane * ldt + k], xk, c_lo);
                         if (lane + 32 < k) c_hi = fma(-Ts[(lane + 32) * ldt + k], xk, c_hi);
                         if (lane == 0) xs[s + k] = xk;
@@ -609,7 +702,9 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     if (tid == 0) {
         double *xo = A.x + inst * A.xld + A.xld - 5;
         xo[0] = (double)tp_a; xo[1] = (double)tp_n; xo[2] = (double)tp_j; xo[3] = (double)tp_c; xo[4] = (double)tp_bs;
+        xo[-1] = (double)tp_w0;
     }
+    if (tid == 32) A.x[inst * A.xld + A.xld - 7] = (double)tp_w1;
 #endif
     if (tid == 0) {
         A.ncols[inst] = n2;
@@ -628,7 +723,7 @@ int qr_blockbanded_smem_bytes(int maxblocks, int *hmax_out, int *wmax_out)
     const int wmax = 3 * maxblocks;
     if (hmax_out) *hmax_out = hmax;
     if (wmax_out) *wmax_out = wmax;
-    size_t need = ((size_t)hmax * (wmax + 1) + 2 * (size_t)hmax * 4 + 32) * sizeof(double);
+    size_t need = ((size_t)hmax * (wmax + 1) + 2 * (size_t)hmax * 4 + 32 + 6 * 72) * sizeof(double);
     const size_t backsub = (size_t)(64 * 65 + 64 + maxblocks * (maxblocks + 1) / 2 + 8) * sizeof(double);
     if (need < backsub) need = backsub;
     return (int)need;

@@ -46,3 +46,4 @@ if os.environ.get("K11_PROFILE"):
     xc = x.cpu().numpy()
     i = int(np.argmax(nb_))
     print("phase cycles (operator with most blocks): load %.0f  first-norm %.0f  columns %.0f  write-out %.0f  back-substitution %.0f" % tuple(xc[i, -5:]))
+    print("panel loop work before the barrier: warp 0 (panel) %.0f cycles, warp 1 (trailing) %.0f cycles" % (xc[i, -6], xc[i, -7]))

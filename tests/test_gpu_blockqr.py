@@ -94,3 +94,17 @@ def test_batch_larger_than_the_sm_count(ila):
     for i in range(300):
         r = ((A0 - lam[i] * np.eye(n)) @ g["x"][i, :n])[:10] - e1
         assert np.abs(r).max() <= 1e-13, i
+
+
+def test_long_rhs_prefix_and_asymmetric_bands(ila):
+    # b spans four blocks (SB = 4: the adaptive test may only fire past it), T1 / T2 not symmetric, negative weights
+    from oracle import block_qr as bq
+    m = 80
+    k = np.arange(1, m + 1, dtype=np.float64)
+    T1 = np.stack([0.3 + 0.1 / k, 0.05 * np.cos(k), 0.6 - 0.1 / k])
+    T2 = np.stack([np.full(m, 0.45), -0.2 / k, np.full(m, 0.55)])
+    b = np.array([1.0, 0.0, -0.5, 0.25, 0.0, 0.0, 2.0])
+    al = np.array([1.0, -1.0, 0.7]); be = np.array([1.0, 0.5, -1.3]); lam = np.array([3.5, -3.0, 4.2])
+    g = ila.qr_blockbanded_solve(T1, T2, al, be, lam, b=b, tol=1e-25)
+    for i in range(3):
+        _check(g, i, bq.block_qr_solve(T1, T2, al[i], be[i], lam[i], b=b, tol=1e-25))
