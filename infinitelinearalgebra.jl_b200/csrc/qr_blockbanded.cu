@@ -198,11 +198,7 @@ __device__ __forceinline__ void panel_factor(Panel &pn, double *Vbuf, double *ps
             double row_k[4];                          // row k of the panel (lane k, chunk 0)
 #pragma unroll
             for (int l = 0; l < 4; l++) row_k[l] = __shfl_sync(0xffffffffu, a[0][l], k);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int l = 0; l < 4; l++) red[l] += __shfl_xor_sync(0xffffffffu, red[l], o);
-            }
+            packed_allreduce<4>(red, lane);
             double inv, beta;
             reflector_scalars_fast(row_k[k], red[k], tau[k], inv, beta);
             // rows above the diagonal of this column are final R entries; the diagonal becomes beta
