@@ -80,26 +80,25 @@ __device__ __forceinline__ double warp_sum(double v)
 template <int N>
 __device__ __forceinline__ void packed_allreduce(double (&v)[N], int lane)
 {
-    static_assert(N == 4 || N == 16, "packed_allreduce: N must be 4 or 16");
+    static_assert(N == 4 || N == 8 || N == 16, "packed_allreduce: N must be 4, 8 or 16");
     int o = 16;
-    if constexpr (N == 16) {
-        {
-            const bool up = lane & 16;
+    if constexpr (N >= 16) {
+        const bool up = lane & o;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const double keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
+        for (int i = 0; i < 8; i++) {
+            const double keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
-        {
-            const bool up = lane & 8;
+        o >>= 1;
+    }
+    if constexpr (N >= 8) {
+        const bool up = lane & o;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const double keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
+        for (int i = 0; i < 4; i++) {
+            const double keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
         }
-        o = 4;
+        o >>= 1;
     }
     {
         const bool up = lane & o;
@@ -239,19 +238,21 @@ __device__ __forceinline__ void panel_factor(Panel &pn, double *Vbuf, double *ps
     }
 }
 
-// the current panel's four reflectors applied by ONE warp to the (at most four) columns of the next panel: all sixteen dot
-// products in one reduction round, then the same Gram recurrence as the trailing columns
-__device__ __forceinline__ void panel_apply(Panel &pn, const double *Vbuf, const double *psb, int cp, int m, int cn, int kbn, int lane)
+// the current panel's four reflectors applied to two of the (at most four) columns of the next panel by one warp (warp 0
+// takes columns 0-1, the helper warp columns 2-3): all eight dot products in one packed reduction round, then the same Gram
+// recurrence as the trailing columns
+__device__ __forceinline__ void panel_apply2(Panel &pn, const double *Vbuf, const double *psb, int cp, int m, int cn, int ncol, int lane)
 {
     const int ld = pn.ld;
-    double a[4][4], v[4][4];
+    double a[4][2], v[4][4];
     int rowoff[4];
     bool valid[4];
-    int cslot[4];
+    int cslot[2];
     {
         int sl = pn.cs(cn);
-#pragma unroll
-        for (int k = 0; k < 4; k++) { cslot[k] = sl; if (++sl == pn.wmax) sl = 0; }
+        cslot[0] = sl;
+        if (++sl == pn.wmax) sl = 0;
+        cslot[1] = sl;
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -259,7 +260,7 @@ __device__ __forceinline__ void panel_apply(Panel &pn, const double *Vbuf, const
         valid[q] = i < m;
         rowoff[q] = pn.rs(cp + i) * ld;
 #pragma unroll
-        for (int k = 0; k < 4; k++) a[q][k] = (valid[q] && k < kbn) ? pn.P[rowoff[q] + cslot[k]] : 0.0;
+        for (int k = 0; k < 2; k++) a[q][k] = (valid[q] && k < ncol) ? pn.P[rowoff[q] + cslot[k]] : 0.0;
         if (valid[q]) {
             const double2 *src = reinterpret_cast<const double2 *>(Vbuf + i * 4);
             const double2 x0 = src[0], x1 = src[1];
@@ -268,25 +269,25 @@ __device__ __forceinline__ void panel_apply(Panel &pn, const double *Vbuf, const
             v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0;
         }
     }
-    double df[16];                                    // df[4k + l] = v_k . a_l
+    double df[8];                                     // df[2k + l] = v_k . a_l
 #pragma unroll
     for (int k = 0; k < 4; k++)
 #pragma unroll
-        for (int l = 0; l < 4; l++) {
+        for (int l = 0; l < 2; l++) {
             double t = 0.0;
 #pragma unroll
             for (int q = 0; q < 4; q++) t = fma(v[q][k], a[q][l], t);
-            df[4 * k + l] = t;
+            df[2 * k + l] = t;
         }
-    packed_allreduce<16>(df, lane);
+    packed_allreduce<8>(df, lane);
     const double t0 = psb[0], t1 = psb[1], t2 = psb[2], t3 = psb[3];
     const double g10 = psb[4], g20 = psb[5], g21 = psb[6], g30 = psb[7], g31 = psb[8], g32 = psb[9];
 #pragma unroll
-    for (int l = 0; l < 4; l++) {
+    for (int l = 0; l < 2; l++) {
         const double w0 = t0 * df[l];
-        const double w1 = t1 * fma(-w0, g10, df[4 + l]);
-        const double w2 = t2 * fma(-w1, g21, fma(-w0, g20, df[8 + l]));
-        const double w3 = t3 * fma(-w2, g32, fma(-w1, g31, fma(-w0, g30, df[12 + l])));
+        const double w1 = t1 * fma(-w0, g10, df[2 + l]);
+        const double w2 = t2 * fma(-w1, g21, fma(-w0, g20, df[4 + l]));
+        const double w3 = t3 * fma(-w2, g32, fma(-w1, g31, fma(-w0, g30, df[6 + l])));
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             double x = a[q][l];
@@ -297,8 +298,8 @@ __device__ __forceinline__ void panel_apply(Panel &pn, const double *Vbuf, const
 #pragma unroll
     for (int q = 0; q < 4; q++) {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (valid[q] && k < kbn) pn.P[rowoff[q] + cslot[k]] = a[q][k];
+        for (int k = 0; k < 2; k++)
+            if (valid[q] && k < ncol) pn.P[rowoff[q] + cslot[k]] = a[q][k];
     }
 }
 
@@ -440,14 +441,18 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
 #ifdef ILA_K11_PROFILE
                 const long long tw0 = clock64();
 #endif
-                if (warp == 0) {
+                if (warp == 0 || warp == kWarps - 1) {
+                    // panel warps: warp 0 and the helper each apply the current panel to two columns of the next one, meet at a
+                    // two-warp named barrier, then warp 0 factorizes the four columns
                     if (kbn > 0) {
-                        panel_apply(pn, Vb, psb, cp, m, cp + kb, kbn, lane);
-                        __syncwarp();
-                        panel_factor(pn, Vp + (size_t)(buf ^ 1) * hmax * 4, ps + (buf ^ 1) * 16, cp + kb, kbn, m - kb, lane);
+                        const int coff = warp == 0 ? 0 : 2;
+                        if (kbn > coff) panel_apply2(pn, Vb, psb, cp, m, cp + kb + coff, min(2, kbn - coff), lane);
+                        asm volatile("bar.sync 1, 64;" ::: "memory");
+                        if (warp == 0)
+                            panel_factor(pn, Vp + (size_t)(buf ^ 1) * hmax * 4, ps + (buf ^ 1) * 16, cp + kb, kbn, m - kb, lane);
                     }
                 } else {
-                    const int tq = (warp - 1) * 16 + (lane & 15);
+                    const int tq = (warp - 1) * 16 + (lane & 15);      // 12 trailing warps x 16 pairs = 192 >= 3*63 + 4 - 8
                     const int first = cp + kb + kbn, ntrail = cend - first;
                     const bool act = tq <= ntrail;
                     int scol = pn.cs(first) + tq;
