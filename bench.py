@@ -176,6 +176,7 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
