@@ -320,6 +320,20 @@ int ila_qr_blockbanded_solve_f64_dev(int64_t batch, const double *d_alpha, const
                                      int colgrowth, int maxblocks, double *d_work, double *d_qtb, double *d_x, int64_t xld,
                                      int64_t *d_ncols, int32_t *d_nblocks, int32_t *d_status, void *stream);
 
+/* ---- K12: adaptive QR solve of ∞ ALMOST-BANDED operators  A = Vcat(B, D)   ------------------------------------
+ * r dense rows B (boundary conditions) on top of a banded operator D with bandwidths (lD, uD): the ultraspherical-spectral-
+ * method shape of test/test_infqr.jl:193-267.  Replaces AdaptiveQRData(::AbstractAlmostBandedLayout) (src/infqr.jl:15-21),
+ * partialqr! -> _almostbanded_qr! (:50-66), the Q'b driver (:236-274) and ldiv!(R, B) (:350-355); the rank-r fill above the
+ * band is carried as r coefficients per row (see csrc/qr_almostbanded.cu).
+ *   dg   batch x (lD+uD+1) x 3, diagonals of D in data-row order (+uD first): value(t) = g0 + g1 t + g2 t^2, t = 0-based ROW of D
+ *   bg   batch x r x 4: B_m(j) = s^j (a + b j + c j^2), s = +1 / -1, j = 0-based column      (Ones: 1,1,0,0; (-1)^k: -1,1,0,0)
+ *   shift batch or NULL, subtracted from D's main diagonal;  b: batch x nb;  tol, colgrowth: floatmin and 1000 upstream
+ *   x    batch x ncap, zero padded; ncols[i] = the reference's datasize (nconv - 1 + colgrowth + lD + r); status 3 = ncap reached.
+ * Supported: 1 <= r <= 2, lD + r <= 4, lD + uD + 1 <= 12. */
+int ila_qr_almostbanded_solve_f64(int lD, int uD, int r, int64_t batch, const double *dg, const double *bg, const double *shift,
+                                  int nb, const double *b, double tol, int colgrowth, int64_t ncap, double *x, int64_t *ncols,
+                                  int64_t *nconv, int32_t *status, int ngpus);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,8 @@ SIGNATURES = {
     "ila_qr_blockbanded_set_mode": (C.c_int, [C.c_int]),
     "ila_qr_blockbanded_solve_f64_dev": (C.c_int, [C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_double, C.c_int,
                                                    C.c_int, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
+    "ila_qr_almostbanded_solve_f64": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_int,
+                                                C.c_int64, _vp, _vp, _vp, _vp, C.c_int]),
     "ila_release": (C.c_int, []),
     "ila_ql_finite_section_f64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_double, C.c_int64,
                                             _vp, _vp, _vp, _vp, _vp, C.c_int]),

@@ -472,6 +472,33 @@ def qr_blockbanded_solve(T1, T2, alpha, beta, lam, b=(1.0,), tol=1e-30, colgrowt
     return out
 
 
+def qr_almostbanded_solve(lD, uD, dg, bg, b, shift=None, tol=FLOATMIN, colgrowth=1000, ncap=6000, batch=None, ngpus=1):
+    """Adaptive QR solve of ∞ almost-banded operators Vcat(B, D - shift I), batched (reference src/infqr.jl:15-21, 50-66, 236-274,
+    350-355; test/test_infqr.jl:193-267).  dg: (batch x) (lD+uD+1) x 3 polynomial generators of D's diagonals (+uD first, value(t) =
+    g0 + g1 t + g2 t^2 in the row index of D); bg: (batch x) r x 4 boundary rows s^j (a + b j + c j^2).
+    Returns dict(x (batch x ncap, zero padded), ncols, nconv, status)."""
+    nd = lD + uD + 1
+    dg = np.asarray(dg, dtype=np.float64).reshape(-1, nd, 3)
+    bg = np.asarray(bg, dtype=np.float64)
+    bg = bg.reshape((-1,) + bg.shape[-2:]) if bg.ndim >= 2 else bg.reshape(1, 1, 4)
+    r = bg.shape[1]
+    b = np.asarray(b, dtype=np.float64)
+    if batch is None:
+        batch = max(dg.shape[0], bg.shape[0], 1 if shift is None else np.asarray(shift).size, b.shape[0] if b.ndim == 2 else 1)
+    dg = np.ascontiguousarray(np.broadcast_to(dg, (batch, nd, 3)))
+    bg = np.ascontiguousarray(np.broadcast_to(bg, (batch, r, 4)))
+    if b.ndim == 1:
+        b = np.broadcast_to(b, (batch, b.shape[0]))
+    b = np.ascontiguousarray(b)
+    shift = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=np.float64), (batch,)))
+    ncap = int(ncap)
+    x = np.empty((batch, ncap))
+    ncols = np.zeros(batch, dtype=np.int64); nconv = np.zeros(batch, dtype=np.int64); status = np.zeros(batch, dtype=np.int32)
+    check(lib().ila_qr_almostbanded_solve_f64(lD, uD, r, batch, ptr(dg), ptr(bg), ptr(shift), b.shape[1], ptr(b), float(tol),
+                                              int(colgrowth), ncap, ptr(x), ptr(ncols), ptr(nconv), ptr(status), ngpus))
+    return dict(x=x, ncols=ncols, nconv=nconv, status=status)
+
+
 def pentadiagonal_operator(sigma, eps=1e-4):
     """BASELINE config C4: S_σ = pentadiag(diag 6+σ+ε·k, ±1: -4, ±2: 1), upper bands in data-row order (+2, +1, 0)."""
     sigma = np.atleast_1d(np.asarray(sigma, dtype=np.float64))

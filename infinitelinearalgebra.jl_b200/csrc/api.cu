@@ -788,6 +788,63 @@ int ila_qr_blockbanded_solve_f64(int64_t batch, const double *alpha, const doubl
     return 0;
 }
 
+// ================================ K12: adaptive almost-banded QR solve ===================================
+
+int ila_qr_almostbanded_solve_f64(int lD, int uD, int r, int64_t batch, const double *dg, const double *bg, const double *shift,
+                                  int nb, const double *b, double tol, int colgrowth, int64_t ncap, double *x, int64_t *ncols,
+                                  int64_t *nconv, int32_t *status, int ngpus)
+{
+    if (batch < 0 || !dg || !bg || nb < 1 || !b || colgrowth < 1 || ncap < 1 || (batch > 0 && (!x || !ncols || !nconv || !status)))
+        return set_error(ILA_ERR_ARG, "qr_almostbanded_solve: bad arguments");
+    if (r < 1 || r > 2 || lD < 0 || uD < 0 || lD + r > 4 || lD + uD + 1 > 12 || nb > ncap)
+        return set_error(ILA_ERR_UNSUPPORTED, "qr_almostbanded_solve: need 1 <= r <= 2, lD + r <= 4, lD + uD + 1 <= 12, nb <= ncap");
+    int G = 0;
+    int rc = resolve_ngpus(ngpus, &G);
+    if (rc) return rc;
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (G > batch) G = (int)batch;
+    const int nd = lD + uD + 1;
+    const int64_t per = (batch + G - 1) / G, wstride = ncap * (int64_t)(nd + r + 1);
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= batch ? per : batch - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        cudaStream_t s = g_dev[pd].stream;
+        double *d_dg, *d_bg, *d_sh = nullptr, *d_b, *d_work, *d_x;
+        int64_t *d_ncols, *d_nconv;
+        int32_t *d_st;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt * nd * 3, &d_dg))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt * r * 4, &d_bg))) return rc;
+        if (shift && (rc = dev_buf_t(pd, 2, (size_t)cnt, &d_sh))) return rc;
+        if ((rc = dev_buf_t(pd, 3, (size_t)cnt * nb, &d_b))) return rc;
+        if ((rc = dev_buf_t(pd, 16, (size_t)cnt * wstride, &d_work))) return rc;
+        if ((rc = dev_buf_t(pd, 5, (size_t)cnt * ncap, &d_x))) return rc;
+        if ((rc = dev_buf_t(pd, 6, (size_t)cnt, &d_ncols))) return rc;
+        if ((rc = dev_buf_t(pd, 7, (size_t)cnt, &d_nconv))) return rc;
+        if ((rc = dev_buf_t(pd, 8, (size_t)cnt, &d_st))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_dg, dg + lo * nd * 3, sizeof(double) * cnt * nd * 3, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_bg, bg + lo * r * 4, sizeof(double) * cnt * r * 4, cudaMemcpyHostToDevice, s));
+        if (shift) ILA_CUDA_CHECK(cudaMemcpyAsync(d_sh, shift + lo, sizeof(double) * cnt, cudaMemcpyHostToDevice, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_b, b + lo * nb, sizeof(double) * cnt * nb, cudaMemcpyHostToDevice, s));
+        AlmostBandedArgs a{cnt, lD, uD, r, d_dg, d_bg, d_sh, d_b, nb, colgrowth, tol, ncap, d_work, wstride, d_x, d_ncols, d_nconv, d_st};
+        if ((rc = launch_qr_almostbanded(a, s))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(x + lo * ncap, d_x, sizeof(double) * cnt * ncap, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(ncols + lo, d_ncols, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(nconv + lo, d_nconv, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
 // ================================ K9: adaptive finite-section QL =========================================
 
 } // extern "C" (templates below have C++ linkage)

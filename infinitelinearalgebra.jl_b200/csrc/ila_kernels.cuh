@@ -138,6 +138,25 @@ int qr_blockbanded_smem_bytes(int maxblocks, int *hmax_out, int *wmax_out);
 int launch_qr_blockbanded(BlockQrArgs a, cudaStream_t s);
 void qr_blockbanded_set_mode(int mode);
 
+// from qr_almostbanded.cu
+struct AlmostBandedArgs {
+    int64_t batch;
+    int lD, uD, r;
+    const double *dg;          // batch x (lD+uD+1) x 3: diagonals of D, +uD first, value(t) = g0 + g1 t + g2 t^2 (t = row of D)
+    const double *bg;          // batch x r x 4: boundary rows B_m(j) = s^j (a + b j + c j^2)
+    const double *shift;       // batch or NULL (subtracted from D's main diagonal)
+    const double *b;           // batch x nb
+    int nb, colgrowth;
+    double tol;
+    int64_t ncap;
+    double *work;              // batch x work_stride records
+    int64_t work_stride;
+    double *x;                 // batch x ncap
+    int64_t *ncols, *nconv;
+    int32_t *status;
+};
+int launch_qr_almostbanded(const AlmostBandedArgs &a, cudaStream_t s);
+
 // from ql_finite_section.cu
 template <typename T>
 struct FsqlArgsT {
