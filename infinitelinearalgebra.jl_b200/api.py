@@ -683,3 +683,41 @@ class _EyeType:
 
 
 Eye = _EyeType()
+
+
+# ---- almost-banded operators: Vcat(boundary rows, BandedMatrix) ------------------------------------------------
+
+class Poly:
+    """Entry t (t = 0, 1, ...) = g0 + g1*t + g2*t^2 — `1:∞` = Poly(1, 1), `(1:∞).*(2:∞)` = Poly(2, 3, 1), `4:2:∞` = Poly(4, 2)."""
+
+    def __init__(self, g0=0.0, g1=0.0, g2=0.0):
+        self.g = (g0, g1, g2)
+
+
+class BoundaryRow:
+    """Dense ∞ row s^j (a + b j + c j^2): `Ones(1,∞)` = BoundaryRow(), `((-1).^(0:∞))'` = BoundaryRow(s=-1)."""
+
+    def __init__(self, s=1.0, a=1.0, b=0.0, c=0.0):
+        self.g = (s, a, b, c)
+
+
+class AlmostBanded:
+    """Vcat(rows..., D): dense boundary rows on top of an ∞ banded operator given by `{d: Poly | number}` with the entry of
+    diagonal d counted along the ROWS of D (test/test_infqr.jl:193-267).  `A - c*I` is not defined upstream for this layout; a
+    shifted family is spelled through `shift`, subtracted from D's main diagonal."""
+
+    def __init__(self, rows, diags: dict, shift=0.0):
+        self.rows, self.diags, self.shift = rows, diags, shift
+
+    def solve(self, b, tolerance=_b.FLOATMIN, ncap=6000):
+        """`A \\ b` = qr(A) \\ b (src/infqr.jl:15-21, 50-66, 236-274, 350-355)."""
+        lD, uD = max(0, -min(self.diags)), max(0, max(self.diags))
+        dg = []
+        for d in range(uD, -lD - 1, -1):
+            v = self.diags.get(d, 0.0)
+            dg.append(list(v.g) if isinstance(v, Poly) else [float(v), 0.0, 0.0])
+        bb = np.atleast_1d(np.asarray(b.head if isinstance(b, Vcat) else b, dtype=float))
+        out = _b.qr_almostbanded_solve(lD, uD, dg, [list(r.g) for r in self.rows], bb, shift=[self.shift] if self.shift else None,
+                                       tol=tolerance, ncap=ncap)
+        _raise_status(out["status"][0], "qr(A) \\ b (almost-banded)")
+        return out["x"][0][: int(out["ncols"][0])]

@@ -58,3 +58,16 @@ def test_blockbanded_mirror(ila):
     assert abs(gen2d(u, 50) - 1 / (x + y - 4)) <= 1e-14
     u = (2 * KronTrav(D, Eye) + KronTrav(Eye, D) - 8 * I).solve([1.0])
     assert abs(gen2d(u, 40) - 1 / (2 * x + y - 8)) <= 1e-14
+
+
+def test_almostbanded_mirror(ila):
+    # test_infqr.jl:194-221, 223-248
+    from scipy.special import gammaln
+    from ila_b200.api import AlmostBanded, BoundaryRow, Poly
+    ref = np.exp(-gammaln(np.arange(1000) + 1.0))
+    A = AlmostBanded([BoundaryRow()], {0: -1.0, 1: Poly(1, 1)})                     # Vcat(Ones(1,∞), BandedMatrix(0 => -Ones, 1 => 1:∞))
+    assert np.abs(A.solve([np.e])[:1000] - ref).max() <= 1e-15
+    A = AlmostBanded([BoundaryRow(), BoundaryRow(s=-1)], {0: -1.0, 2: Poly(2, 3, 1)})  # two-bands, B = BandedMatrix(0 => -Ones, 2 => k(k+1))
+    assert np.abs(A.solve([np.e, 1 / np.e])[:1000] - ref).max() <= 1e-15
+    x = 0.1
+    assert abs(A.solve([1.0])[:1000] @ x ** np.arange(1000) - (np.exp(1 - x) * (-1 + np.exp(2 + 2 * x))) / (-1 + np.exp(4))) <= 1e-15
