@@ -480,6 +480,15 @@ def run_ours(args, rank, local_rank, world):
         cols11 = float(sum(K * (K + 1) // 2 for K in blk11))
         flops11 = float(sum(sum(4.0 * (2 * J + 1 - j) * (3 * J + 3 - j) for j in range(J)) for K in blk11 for J in range(1, K + 1)))
         del w11
+        # K12: almost-banded adaptive QR, u' = λu with u(1) = e^λ for 1024 values of λ (host entry, wall clock)
+        lam12 = np.linspace(-2.0, 3.0, 1024)
+        res12 = {}
+        def run12():
+            res12["o"] = ila_b200.qr_almostbanded_solve(0, 1, [[1, 1, 0], [0, 0, 0]], [[1, 1, 0, 0]], np.exp(lam12)[:, None], shift=lam12, ncap=3200)
+        ms12 = wall(run12)
+        if int((res12["o"]["status"] != 0).sum()) != 0:
+            raise SystemExit("bench.py: K12 instances failed")
+        cols12 = float((res12["o"]["nconv"] + 1).sum())
         line["other_configs"] = [
             {"metric": "adaptive_cholesky_columns_per_s", "value": cols4 * world / (ms4 * 1e-3), "unit": "columns/s",
              "ms_per_step": ms4, "config": {"workload": "C4 pentadiagonal adaptive Cholesky, 2048 shifts (per GPU)",
@@ -516,6 +525,11 @@ def run_ours(args, rank, local_rank, world):
              "ms_per_step": ms9, "config": {"workload": "complex-eltype adaptive QR, (J - λI) \\ e1, 512 shifts λ = x + 0.2i (per GPU)",
                                             "columns": cols9, "timing": "host C-ABI call, wall clock, copies included"},
              "gpu_launches_per_step": 3},
+            {"metric": "almostbanded_qr_columns_per_s", "value": cols12 * world / (ms12 * 1e-3), "unit": "columns/s",
+             "ms_per_step": ms12, "config": {"workload": "K12 almost-banded adaptive QR, Vcat(Ones, BandedMatrix(0 => -λ, 1 => 1:∞)) \\ [e^λ; 0...], "
+                                                         "1024 values of λ in [-2, 3] (per GPU)", "columns_factorized": cols12,
+                                             "timing": "host C-ABI call, wall clock, copies included (26 MB of zero-padded x back)"},
+             "gpu_launches_per_step": 1},
             {"metric": "tridiagonal_conjugation_rows_per_s", "value": rows10 * world / (ms_k10 * 1e-3), "unit": "rows/s",
              "ms_per_step": ms_k10, "config": {"workload": "K10 Y = Tridiagonal(U*X/U), 2048 operators x 16384 rows, three bands of U and "
                                                           "X per operator (per GPU)"},

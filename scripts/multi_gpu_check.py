@@ -65,5 +65,7 @@ check("chol_tridiagonal_conjugation", f)
 Tb = np.stack([np.full(50, 0.5), np.zeros(50), np.full(50, 0.5)])
 f = lambda g: (lambda o: (o["x"], o["ncols"], o["nblocks"], o["status"]))(ila_b200.qr_blockbanded_solve(Tb, Tb, 1.0, 1.0, np.linspace(4, 9, 21), tol=1e-12, maxblocks=40, ngpus=g))
 check("qr_blockbanded_solve", f)
+f = lambda g: (lambda o: (o["x"], o["ncols"], o["nconv"], o["status"]))(ila_b200.qr_almostbanded_solve(0, 1, [[1, 1, 0], [0, 0, 0]], [[1, 1, 0, 0]], np.exp(np.linspace(-2, 3, 33))[:, None], shift=np.linspace(-2, 3, 33), ncap=3200, ngpus=g))
+check("qr_almostbanded_solve", f)
 print("ALL OK" if ok else "FAILURES")
 sys.exit(0 if ok else 1)
