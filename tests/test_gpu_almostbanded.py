@@ -62,3 +62,15 @@ def test_shift_family_tolerance_capacity(ila):
     _check(g, 0, ab.almostbanded_qr_solve(0, 1, dg, [ONES], [np.e], shift=1.0, **kw))
     g = ila.qr_almostbanded_solve(0, 1, [[1, 1, 0], [-1, 0, 0]], [ONES], [np.e], ncap=900)
     assert g["status"][0] == 3 and g["ncols"][0] == 0
+
+
+def test_generic_shape_and_quadratic_boundary_row(ila):
+    # (lD, uD, r) = (1, 2, 1) is not one of the register-resident shapes: the runtime-shape kernel; boundary row (-1)^j (1 + j/2)
+    from oracle import almostbanded_qr as ab
+    dg = [[0.3, 0, 0], [1, 1, 0], [-2, 0, 0], [0.4, 0, 0]]
+    g = ila.qr_almostbanded_solve(1, 2, dg, [ONES], [1.0], ncap=3300)
+    _check(g, 0, ab.almostbanded_qr_solve(1, 2, dg, [ONES], [1.0], ncap=3300))
+    bg = [[-1, 1, 0.5, 0]]
+    g = ila.qr_almostbanded_solve(1, 2, dg, bg, [[1.0, -0.3], [0.5, 2.0]], shift=[0.7, -0.2], ncap=3300)
+    _check(g, 0, ab.almostbanded_qr_solve(1, 2, dg, bg, [1.0, -0.3], shift=0.7, ncap=3300))
+    _check(g, 1, ab.almostbanded_qr_solve(1, 2, dg, bg, [0.5, 2.0], shift=-0.2, ncap=3300))
