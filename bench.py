@@ -544,8 +544,9 @@ def run_ours(args, rank, local_rank, world):
                                                "operators_per_s": b11 * world / (ms_k11 * 1e-3)},
              "roofline": {"bound": "fp64", "achieved": flops11 / (ms_k11 * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                           "frac": flops11 / (ms_k11 * 1e-3) / 1e12 / fp64_peak, "traffic": None,
-                          "note": "Householder flops 4(2J+1-j)(3J+3-j) per column; the rank-1 updates stream the panel through "
-                                  "shared memory (24 B per 2 flops), so the kernel is shared-memory-bandwidth bound, not FP64 bound"},
+                          "note": "Householder flops 4(2J+1-j)(3J+3-j) per column; four reflectors per pass over the trailing panel; "
+                                  "bound by the serial chain of the panel warp (shuffle-reduction rounds + reflector scalars), not by "
+                                  "the FP64 pipe (ncu: FP64 pipe 11 %, issue slots 28 %)"},
              "gpu_launches_per_step": 1},
         ]
 
