@@ -60,36 +60,68 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md recipe).  NVML in
+    process (pynvml) — a few hundred µs per sample and no driver-wide lock held by a spawned nvidia-smi, which matters when
+    8 ranks sample at once; falls back to the `nvidia-smi --query-gpu` line of the recipe when pynvml is unavailable."""
 
-    def __init__(self, index: int):
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index: int, uuid: str | None = None):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, [reason flags])
         self.stop_flag = threading.Event()
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.handle = None
 
-    def run(self):
+    def _sample_nvml(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [bool(r & nv.nvmlClocksThrottleReasonHwSlowdown), bool(r & nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 bool(r & nv.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & nv.nvmlClocksThrottleReasonSwPowerCap)]
+        self.rows.append((sm, self.max_mhz, flags))
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [s.strip() for s in out.strip().split(",")]
+        if len(parts) >= 6:
+            self.rows.append((float(parts[0]), float(parts[1]), [p.lower().startswith("active") for p in parts[2:6]]))
+
+    def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                if self.handle is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.05 if self.handle is not None else 0.25)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.handle is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -172,6 +204,8 @@ def run_ours(args, rank, local_rank, world):
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
+    if os.environ.get("ILA_BENCH_DEVMAP"):       # diagnostic: comma-separated physical device per local rank
+        local_rank = int(os.environ["ILA_BENCH_DEVMAP"].split(",")[local_rank])
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.check(ila_b200.lib().ila_set_device(local_rank))
@@ -222,6 +256,7 @@ def run_ours(args, rank, local_rank, world):
             e1.synchronize()
             tot += e0.elapsed_time(e1)
         barrier()
+        timed.last_local = tot
         return max_over_ranks(tot)          # ms for all K steps, max over ranks
 
     lib = ila_b200.lib()
@@ -244,12 +279,22 @@ def run_ours(args, rank, local_rank, world):
         if k3_fn(*k3_args) != 0:
             raise SystemExit("bench.py: ila_ql_toeplitz_l11_c64_dev failed")
 
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     sampler.start()
     l0 = lib.ila_kernel_launches()
     ms_total = timed(step_dev, args.steps, args.warmup)
     launches = lib.ila_kernel_launches() - l0 - args.warmup
     ms_step = ms_total / args.steps
+    rank_ms = [timed.last_local / args.steps]
+    if dist is not None:
+        t = torch.tensor([timed.last_local / args.steps], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(x.item()) for x in allt]
     value = n * world / (ms_step * 1e-3)
 
     # ---------------- e2e: host API, pinned host buffers, H2D + kernel + D2H inside the timed region --------
@@ -320,7 +365,7 @@ def run_ours(args, rank, local_rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
         "config": {"workload": "C3 Bull-head ql(A-λI).L[1,1], 1024x1024 λ grid (bands -3,-2,+1), per-GPU slab",
-                   "points_per_gpu": n, "l2": "flushed between timed steps (768 MiB fill, untimed)", "parallelism":
+                   "points_per_gpu": n, "ms_per_step_by_rank": rank_ms, "l2": "flushed between timed steps (768 MiB fill, untimed)", "parallelism":
                    f"shift-grid sharding x{world}, no collective on the data path"},
         "e2e": {"value": e2e_value, "unit": "lambda-points/s", "h2d_bytes_per_step": 16 * n,
                 "d2h_bytes_per_step": 20 * n, "ms_per_step": e2e_ms, "host_matches_device": same,

@@ -20,6 +20,9 @@ namespace ila {
 
 constexpr int kMaxDeg = 8;   // l + 1 <= 8
 constexpr int kAberthMaxIt = 48;
+// FP32 scout: a cold start converges in 6-8 sweeps (14 at most on the C3 grid); in rare regions of the λ plane the FP32 iteration
+// from the circle start never settles although the FP64 one does in 8 sweeps — give up early and let the FP64 path take over
+constexpr int kScoutMaxIt = 16;
 static int g_tz_spt = 0;   // 0 = automatic; set by ila_ql_set_shifts_per_thread (1 = every shift starts cold)
 void tz_set_spt(int v) { g_tz_spt = v; }
 
@@ -446,9 +449,16 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
 #pragma unroll
         for (int j = 0; j < N; j++) dwf[j] = wf[j] - wold[j];
     }
+#ifdef ILA_K3_DEBUG
+    int dbg_f32 = 0, dbg_f64 = 0, dbg_flags = have_roots ? 1 : 0;
+#define K3_DBG(x) x
+#else
+#define K3_DBG(x)
+#endif
     if (scout != 0) {
-        for (int it = 0; it < kAberthMaxIt; it++) {
+        for (int it = 0; it < kScoutMaxIt; it++) {
             scout = aberth_sweep_f32<N>(cff, wf);
+            K3_DBG(dbg_f32++;)
             if (scout == 0) break;
         }
     }
@@ -520,8 +530,11 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
 #pragma unroll
             for (int j = 0; j < N; j++) w[j] = c + rad * P.unit[j];
         }
-        for (int it = 0; it < kAberthMaxIt; it++)
+        K3_DBG(dbg_flags |= 2 | (scout == 2 ? 4 : 0);)
+        for (int it = 0; it < kAberthMaxIt; it++) {
+            K3_DBG(dbg_f64++;)
             if (aberth_sweep<N>(cf, w) == 0) break;
+        }
         jsel = select_root<N>(w, P.branch_rank, gap);
         ws = w[0];
 #pragma unroll
@@ -577,6 +590,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
             status[idx] = st;
             const double l11 = (c_abs == 0.0) ? copysign(ay, y.re) : -ay;
             reinterpret_cast<double2 *>(L11)[idx] = (st == ILA_OK) ? make_double2(l11, 0.0) : make_double2(qn, qn);
+            K3_DBG(reinterpret_cast<double2 *>(L11)[idx].y = dbg_f32 + 100.0 * dbg_f64 + 10000.0 * dbg_flags + 1e-3 * gapf;)
         }
         continue;
     }
