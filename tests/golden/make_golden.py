@@ -82,3 +82,14 @@ np.savez_compressed(os.path.join(HERE, "blockqr.npz"), cases=np.array(cases), nc
                     nblocks=np.array([o["nblocks"] for o in outs]), x=np.stack([o["x"][:300] for o in outs]),
                     qtb=np.stack([o["qtb"][:300] for o in outs]))
 print("wrote triconj / blockqr fixtures")
+
+# almostbanded.npz : adaptive QR solves of the almost-banded operators of test_infqr.jl:194-266 (x prefixes, counts)
+from oracle import almostbanded_qr as abq                   # noqa: E402
+ONES_, ALT_ = [1, 1, 0, 0], [-1, 1, 0, 0]
+o1 = abq.almostbanded_qr_solve(0, 1, [[1, 1, 0], [-1, 0, 0]], [ONES_], [np.e], ncap=3200)
+o2 = abq.almostbanded_qr_solve(0, 2, [[2, 3, 1], [0, 0, 0], [-1, 0, 0]], [ONES_, ALT_], [np.e, 1 / np.e], ncap=3200)
+dg5 = [[1, 0, 0], [0, 0, 0], [1, 0, 0], [4, 2, 0], [1, 0, 0], [0, 0, 0], [1, 0, 0]]
+o3 = abq.almostbanded_qr_solve(1, 5, dg5, [ONES_, ALT_], [1.0, 2.0], ncap=4200)
+np.savez_compressed(os.path.join(HERE, "almostbanded.npz"), x1=o1["x"][:400], x2=o2["x"][:400], x3=o3["x"][:400],
+                    ncols=np.array([o1["ncols"], o2["ncols"], o3["ncols"]]), nconv=np.array([o1["nconv"], o2["nconv"], o3["nconv"]]))
+print("wrote almostbanded fixture")

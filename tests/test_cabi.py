@@ -57,3 +57,20 @@ def test_work_layout_host_helper(ila):
                                                    ctypes.byref(xb)))
     assert list(gbase) == [0, 16, 24]                               # group capacities rounded up to 8 rows
     assert xb.value == 24 * 32 * 8 and wb.value == 24 * 32 * 8 * 6  # 6 doubles per record with reflectors (l=u=1)
+
+
+def test_new_entries_refuse_to_run_without_a_gpu(ila):
+    """K10 / K11 / K12 host entries: ILA_ERR_NOGPU (-3) on a box without a CUDA device — never a CPU fallback."""
+    if ila.lib().ila_device_count() != 0:
+        pytest.skip("a CUDA device is visible")
+    U = np.ones((1, 3, 12)); X = np.ones((3, 12))
+    T = np.stack([np.full(80, 0.5), np.zeros(80), np.full(80, 0.5)])
+    calls = [lambda: ila.tridiagonal_conjugation(U, X, 10),
+             lambda: ila.bidiagonal_conjugation(U, U, 10),
+             lambda: ila.chol_tridiagonal_conjugation(1, [[0.0, 2.0]], [[0.0, 0.0]], X, 10),
+             lambda: ila.qr_blockbanded_solve(T, T, 1.0, 1.0, [4.0]),
+             lambda: ila.qr_almostbanded_solve(0, 1, [[1, 1, 0], [-1, 0, 0]], [[1, 1, 0, 0]], [np.e])]
+    for f in calls:
+        with pytest.raises(ila.IlaError) as e:
+            f()
+        assert e.value.code == -3

@@ -61,3 +61,10 @@ def test_triconj_and_blockqr_fixtures():
         o = bqr.block_qr_solve(T, T, *c)
         assert o["ncols"] == b["ncols"][i] and o["nblocks"] == b["nblocks"][i]
         assert np.abs(o["x"][:300] - b["x"][i]).max() <= 1e-13 and np.abs(o["qtb"][:300] - b["qtb"][i]).max() <= 1e-13
+
+
+def test_almostbanded_fixture():
+    from oracle import almostbanded_qr as abq
+    g = np.load(os.path.join(G, "almostbanded.npz"))
+    o1 = abq.almostbanded_qr_solve(0, 1, [[1, 1, 0], [-1, 0, 0]], [[1, 1, 0, 0]], [np.e], ncap=3200)
+    assert o1["ncols"] == g["ncols"][0] and o1["nconv"] == g["nconv"][0] and np.abs(o1["x"][:400] - g["x1"]).max() <= 1e-15
