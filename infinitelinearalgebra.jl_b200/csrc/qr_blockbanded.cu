@@ -18,14 +18,23 @@
 // the right-hand side as one more column, (2J+1) x (3J+4) doubles — lives in shared memory (up to 197 KB: the reason for
 // one CTA per SM) with CIRCULAR row and column indexing, so that moving from block column J to J+1 neither copies nor
 // shifts anything: the J+1 fresh rows of block J+2 are generated from (T1, T2, alpha, beta, lam) straight into the slots
-// the finished rows leave.  Per Householder column: warp 0 forms the norm with shuffles and publishes (tau, 1/(alpha-beta));
-// then one thread per trailing column does the dot product and the update (consecutive threads touch consecutive
-// shared-memory words; the reflector entry is a broadcast).  Q'b is the extra column, so the adaptive test (max|Q'b| over
-// the blocks J..J+l at the COLGROWTH cadence) is a shared-memory reduction — no host round trip.  Finished R rows stream
-// to the operator's slab of global memory (coalesced, L2-resident: ≤ 2.1 MB) and the back-substitution reads them back
-// block row by block row: warp-per-row dot products for the part right of the diagonal block, and ONE warp with the
-// diagonal block in shared memory and the right-hand side in registers for the triangular part (shuffle broadcast of each
-// new solution entry, no block-wide barrier inside a block row).
+// the finished rows leave.
+//   Default path (BLOCKED): panels of four pivot columns.  Warp 0 holds a panel in registers (row i in lane i mod 32) and
+// factorizes it with one packed shuffle all-reduce per pivot column (norm, dot products with the columns to the right and
+// Gram entries with the reflectors to the left together), division-free reflector scalars; V (32-byte rows), the four taus
+// and the six Gram entries go to shared memory, double buffered.  Twelve warps apply a whole panel to the trailing columns
+// (16 column pairs per warp, the two lanes of a pair on alternate rows): one pass for the four dot products, the Gram
+// recurrence for the coefficients of the four sequential reflections, one pass for col -= sum w_k v_k — the trailing panel
+// is read twice and written once per FOUR reflectors.  Meanwhile warp 0 and a helper warp apply the panel to the next
+// panel's columns (two each, meeting at a two-warp named barrier) and warp 0 factorizes them: one block barrier per panel.
+//   Validation path (ila_qr_blockbanded_set_mode(1)): one reflector per pass, 16 column pairs per warp, the pair that
+// updates the next pivot column forms its scalars on the way (one barrier per column).
+// Q'b is the extra column, so the adaptive test (max|Q'b| over the blocks J..J+l at the COLGROWTH cadence) is a
+// shared-memory reduction — no host round trip.  Finished R rows stream to the operator's slab of global memory
+// (coalesced, L2-resident: <= 2.1 MB) and the back-substitution reads them back block row by block row: warp-per-row dot
+// products for the part right of the diagonal block, and ONE warp with the diagonal block in shared memory and the
+// right-hand side in registers for the triangular part (reciprocals of the diagonal formed in parallel, shuffle broadcast
+// of each new solution entry, no block-wide barrier inside a block row).
 #include "ila_common.cuh"
 #include "ila_kernels.cuh"
 #include "ila_exact.cuh"

@@ -17,7 +17,8 @@
 //     Y[k,k+1] = ((c / U[k-1,k-1]) ((U[k-1,k] U[k,k+1]) / U[k,k] - U[k-1,k+1]) + (b - (a U[k,k+1]) / U[k,k])) / U[k+1,k+1]
 // with every product, sum and quotient a separate IEEE operation in the reference's order, so the result equals the
 // sequential oracle (oracle/ila_oracle_triconj.c) bit for bit — and every row is independent: one thread per (operator,
-// row), no recurrence, an HBM-streaming kernel (48-72 B per row against 5 divisions).
+// row), no recurrence, an HBM-streaming kernel (48-72 B per row against 7 quotients over 3 denominators, the refined
+// reciprocal of a denominator shared between its quotients).
 //
 // Two sources for U: (0) explicit band arrays, operator-major (U[i][d][k], coalesced along k); (1) the group-interleaved
 // factor records K1 / K5 leave in device memory (record k of lane ℓ of group g: chunk c at double2 index
