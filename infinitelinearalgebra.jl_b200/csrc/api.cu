@@ -819,7 +819,7 @@ int ila_qr_almostbanded_solve_f64(int lD, int uD, int r, int64_t batch, const do
         if ((rc = dev_buf_t(pd, 1, (size_t)cnt * r * 4, &d_bg))) return rc;
         if (shift && (rc = dev_buf_t(pd, 2, (size_t)cnt, &d_sh))) return rc;
         if ((rc = dev_buf_t(pd, 3, (size_t)cnt * nb, &d_b))) return rc;
-        if ((rc = dev_buf_t(pd, 16, (size_t)cnt * wstride, &d_work))) return rc;
+        if ((rc = dev_buf_t(pd, 16, (size_t)((cnt + 31) / 32) * 32 * wstride, &d_work))) return rc;     // whole warps (interleaved records)
         if ((rc = dev_buf_t(pd, 5, (size_t)cnt * ncap, &d_x))) return rc;
         if ((rc = dev_buf_t(pd, 6, (size_t)cnt, &d_ncols))) return rc;
         if ((rc = dev_buf_t(pd, 7, (size_t)cnt, &d_nconv))) return rc;

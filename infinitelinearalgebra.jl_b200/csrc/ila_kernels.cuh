@@ -149,8 +149,8 @@ struct AlmostBandedArgs {
     int nb, colgrowth;
     double tol;
     int64_t ncap;
-    double *work;              // batch x work_stride records
-    int64_t work_stride;
+    double *work;              // ceil(batch/32) x 32 x work_stride: records, interleaved per warp
+    int64_t work_stride;       // ncap * (lD+uD+1 + r + 1)
     double *x;                 // batch x ncap
     int64_t *ncols, *nconv;
     int32_t *status;

@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(32) qr_almostbanded_kernel(AlmostBandedArgs A)
     const int nb = A.nb, cg = A.colgrowth;
     const int64_t ncap = A.ncap;
     const int REC = W + r + 1;
-    double *rec = A.work + inst * A.work_stride;
+    // records of the 32 operators of a warp interleaved: element e of record k of lane ℓ at ((k*REC + e)*32 + ℓ), so that the
+    // forward sweep stores and the back-substitution loads 256 contiguous bytes per element (same idea as K1's layout)
+    double *rec = A.work + (int64_t)blockIdx.x * 32 * A.work_stride + threadIdx.x;
     double *xo = A.x + inst * ncap;
 
     // A[R, j] of the banded part (R >= r): row t = R - r of D, diagonal d = j - t
@@ -140,13 +142,13 @@ __global__ void __launch_bounds__(32) qr_almostbanded_kernel(AlmostBandedArgs A)
         }
         // ---- row k is final
         {
-            double *dst = rec + k * REC;
+            double *dst = rec + k * REC * 32;
             dst[0] = beta;
 #pragma unroll
-            for (int c = 1; c < W; c++) dst[c] = E[0][c];
+            for (int c = 1; c < W; c++) dst[c * 32] = E[0][c];
 #pragma unroll
-            for (int m = 0; m < r; m++) dst[W + m] = C[0][m];
-            dst[W + r] = bq[0];
+            for (int m = 0; m < r; m++) dst[(W + m) * 32] = C[0][m];
+            dst[(W + r) * 32] = bq[0];
         }
         // ---- slide the window: rows up, columns left; the entering column is pure fill, the entering row pure band
 #pragma unroll
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(32) qr_almostbanded_kernel(AlmostBandedArgs A)
         for (int c = 0; c < W; c++) xw[c] = 0.0;
         bool any = false;
         for (int64_t k = kfinal - 1; k >= 0; k--) {
-            const double *src = rec + k * REC;
+            const double *src = rec + k * REC * 32;
             // column k + W leaves the window of row k+1 into the tail of row k
             const int64_t jout = k + W;
             if (jout < kfinal) {
@@ -182,12 +184,12 @@ __global__ void __launch_bounds__(32) qr_almostbanded_kernel(AlmostBandedArgs A)
 #pragma unroll
                 for (int m = 0; m < r; m++) S[m] += ab_boundary(bg + m * 4, jout) * xj;
             }
-            double acc = src[W + r];
+            double acc = src[(W + r) * 32];
             any |= fabs(acc) > A.tol;
 #pragma unroll
-            for (int c = 1; c < W; c++) acc -= src[c] * xw[c - 1];
+            for (int c = 1; c < W; c++) acc -= src[c * 32] * xw[c - 1];
 #pragma unroll
-            for (int m = 0; m < r; m++) acc -= src[W + m] * S[m];
+            for (int m = 0; m < r; m++) acc -= src[(W + m) * 32] * S[m];
             const double xk = acc / src[0];
 #pragma unroll
             for (int c = W - 1; c >= 1; c--) xw[c] = xw[c - 1];
