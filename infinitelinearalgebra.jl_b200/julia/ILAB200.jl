@@ -207,4 +207,27 @@ function blockbanded_solve(T1::Matrix{Float64}, T2::Matrix{Float64}, Î±::Real, Î
     x, ncols, status
 end
 
+"""
+    almostbanded_solve(lD, uD, dg, bg, b, shifts; tol=floatmin(Float64), colgrowth=1000, ncap=6000, ngpus=1) -> (x, ncols, status)
+
+`Vcat(B, D - Î» I) \ [b; zeros(âˆž)]` for every Î» in `shifts` (src/infqr.jl:15-21, 50-66, 236-274, 350-355): `dg` is the
+`(lD+uD+1) x 3` matrix of polynomial generators of D's diagonals (+uD first, `g0 + g1 t + g2 t^2` in the row index of D), `bg`
+the `r x 4` matrix of boundary rows `s^j (a + b j + c j^2)`.  Column `i` of `x` is the zero-padded solution for `shifts[i]`.
+"""
+function almostbanded_solve(lD::Integer, uD::Integer, dg::Matrix{Float64}, bg::Matrix{Float64}, b::Vector{Float64},
+                            shifts::AbstractVector{<:Real}; tol::Real=floatmin(Float64), colgrowth::Integer=1000,
+                            ncap::Integer=6000, ngpus::Integer=1)
+    batch = length(shifts); r = size(bg, 1)
+    dgt = repeat(vec(permutedims(dg)), batch); bgt = repeat(vec(permutedims(bg)), batch)     # operator-major, row-major blocks
+    x = Matrix{Float64}(undef, ncap, batch); ncols = Vector{Int64}(undef, batch); nconv = Vector{Int64}(undef, batch)
+    status = Vector{Int32}(undef, batch)
+    rc = ccall((:ila_qr_almostbanded_solve_f64, lib), Cint,
+               (Cint, Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Float64, Cint, Int64,
+                Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Cint),
+               lD, uD, r, batch, dgt, bgt, Vector{Float64}(shifts), length(b), repeat(b, batch), tol, colgrowth, ncap, x, ncols,
+               nconv, status, ngpus)
+    check(rc)
+    x, ncols, status
+end
+
 end # module
