@@ -31,8 +31,8 @@ NX = NY = 1024
 BYTES_PER_POINT = 36            # 16 (λ) + 16 (L11) + 4 (status): SURVEY §8d
 FLOPS_PER_POINT_LAPACK = 6.9e3  # LAPACK-style count of the reference's per-λ work, for context
 FP64_FLOPS_PER_POINT = 241.0    # FP64 flops this kernel EXECUTES per shift (ncu op counts, profiles/r01_k3_ql_toeplitz_ncu_full.txt)
-K3_DRAM_TRAFFIC = 20.5e6        # dram read+write bytes of one 1024x1024 launch (same capture)
-K3_INSTR_PER_POINT = 905.0      # thread-level instructions issued per shift (smsp__inst_executed.sum * 32 / 2^20, same capture)
+K3_DRAM_TRAFFIC = 23.3e6        # dram read+write bytes of one 1024x1024 launch (same capture: 20.1 MB read + 3.3 MB written back in-kernel)
+K3_INSTR_PER_POINT = 907.0      # thread-level instructions issued per shift (smsp__inst_executed.sum * 32 / 2^20, same capture)
 BYTES_PER_COLUMN = 72           # Bessel (l=u=1): SURVEY §8d
 FLOPS_PER_COLUMN = 42
 
