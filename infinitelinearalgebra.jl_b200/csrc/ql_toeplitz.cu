@@ -104,12 +104,14 @@ struct TzParams {
     cplx cf0[N + 1];   // (-1)^k a_{m-k}/β, k = 0..N, before the shift (only k = 1 moves with λ)
     cplxf cf0f[N + 1];
     cplx unit[N];      // initial directions exp(i(θ0 + 2πj/N))
+    float cmax2f;      // max_{k >= 2} |cf0_k|^2 (the shift-independent coefficients)
     double beta2;      // |β|^2
     int branch_rank;
 };
 
+// lim2: square of 8x a Cauchy-type bound on the root moduli (1 + max|cf_k|); an iterate beyond it is pulled back
 template <int N>
-__device__ __forceinline__ int aberth_sweep_f32(const cplxf (&cf)[N + 1], cplxf (&w)[N])
+__device__ __forceinline__ int aberth_sweep_f32(const cplxf (&cf)[N + 1], cplxf (&w)[N], float lim2)
 {
     bool notconv = false, big = false;
 #pragma unroll
@@ -135,8 +137,18 @@ __device__ __forceinline__ int aberth_sweep_f32(const cplxf (&cf)[N + 1], cplxf 
         cplxf corr = mkf(0.f);
         if (b2 > 1e-30f && b2 < 1e30f) corr = rcpf_approx(b2) * (top * conjf_(bot));
         else big = true;
+        const cplxf wold = w[j];
         w[j] = w[j] - corr;
-        const float w2 = abs2f(w[j]), c2 = abs2f(corr);
+        float w2 = abs2f(w[j]);
+        const float c2 = abs2f(corr);
+        if (!(w2 < lim2)) {
+            // excursion: a step that lands far outside the Cauchy bound of the roots (next to a pole of the Aberth map the
+            // FP32 correction overflows and the iterate would stay Inf/NaN for good).  Keep the direction, cut the length.
+            const float s = (c2 > 0.f && c2 < 1e37f) ? sqrtf(0.0625f * lim2 / c2) : 0.f;
+            w[j] = (s > 0.f) ? wold - s * corr : mkf(0.7f * wold.re - 0.7f * wold.im, 0.7f * wold.re + 0.7f * wold.im);
+            w2 = abs2f(w[j]);
+            big = true;
+        }
         notconv = notconv || (c2 > 2.5e-5f * w2);   // |corr| > 5e-3 |w|: the cubic step then lands at ~1e-6 or better
         big = big || (c2 > 1e-4f * w2) || !(w2 < 1e30f);
     }
@@ -417,6 +429,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     }
     cf[1] = cf[1] + lam * P.ginv;
     cff[1] = mkf((float)cf[1].re, (float)cf[1].im);
+    const float lim2 = 64.f * (1.f + P.cmax2f + abs2f(cff[1]));     // (8 (1 + max|cf_k|))^2, up to a factor: excursion guard of the scout
     cplx g[N + 1];   // g_k = (-1)^k cf_k = a_{m-k}/β
 #pragma unroll
     for (int k = 0; k <= N; k++) g[k] = (k & 1) ? -cf[k] : cf[k];
@@ -457,7 +470,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
 #endif
     if (scout != 0) {
         for (int it = 0; it < kScoutMaxIt; it++) {
-            scout = aberth_sweep_f32<N>(cff, wf);
+            scout = aberth_sweep_f32<N>(cff, wf, lim2);
             K3_DBG(dbg_f32++;)
             if (scout == 0) break;
         }
@@ -466,7 +479,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     int jsel = select_root_f32<N>(wf, P.branch_rank, gapf);
     if (scout == 0 && gapf < 1e-3f) {
         // near-tie in the ranking: one more (cubic) sweep takes the scout to FP32 precision before deciding
-        scout = aberth_sweep_f32<N>(cff, wf);
+        scout = aberth_sweep_f32<N>(cff, wf, lim2);
         if (scout != 2) scout = 0;
         jsel = select_root_f32<N>(wf, P.branch_rank, gapf);
     }
@@ -741,6 +754,11 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
         if (k & 1) v = cplx{-v.re, -v.im};
         P.cf0[k] = v;
         P.cf0f[k] = cplxf{(float)v.re, (float)v.im};
+    }
+    {
+        double mx = 0.0;
+        for (int k = 2; k <= N; k++) mx = fmax(mx, P.cf0[k].re * P.cf0[k].re + P.cf0[k].im * P.cf0[k].im);
+        P.cmax2f = (float)fmin(mx, 1e30);
     }
     const double theta0 = 0.7;   // asymmetric start: a conjugate-symmetric start cannot split real root pairs
     for (int j = 0; j < N; j++) {
