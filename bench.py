@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native adaptive-factorization hot path.
 
-Metric (BASELINE.json): Bull-head QL λ-points/s  — `ql(A - λI).L[1,1]` over the 1024 x 1024 complex λ grid of
-config C3 (per GPU; weak scaling: with N ranks the global grid is 1024 x 1024·N, rank r owns a 1024-row slab), and
-adaptive-QR columns/s on the 4096 batched Bessel solves of config C2 (reported under "secondary").
+Metric (BASELINE.json): Bull-head QL λ-points/s  — `ql(A - λI).L[1,1]` over ONE 1024 x 1024 complex λ grid (config C3)
+sharded by rows over the N GPUs (STRONG scaling: the global grid is fixed; rank r owns rows r, r+N, ...), and
+adaptive-QR columns/s on the 4096 batched Bessel solves of config C2 (reported under "secondary").  The same line also
+carries the 8192 x 8192 grid ("large", strong) and the one-1024²-slab-per-GPU run of round 1 ("weak").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-secondary]
 
@@ -28,20 +29,41 @@ sys.path.insert(0, ROOT)
 
 BULLHEAD_COLUMN = np.array([2j, 0.0, 0.0, 1.0, 0.7])      # BandedMatrix(-3=>7/10, -2=>1, 1=>2im) data column
 NX = NY = 1024
-BYTES_PER_POINT = 36            # 16 (λ) + 16 (L11) + 4 (status): SURVEY §8d
+BYTES_PER_POINT = 36            # 16 (λ) + 16 (L11) + 4 (status): SURVEY §8d — the algorithmic figure the roofline uses
+BYTES_PER_POINT_COMPACT = 25    # what the compact ABI form moves: 16 (λ) + 8 (real L11) + 1 (status)
 FLOPS_PER_POINT_LAPACK = 6.9e3  # LAPACK-style count of the reference's per-λ work, for context
-FP64_FLOPS_PER_POINT = 241.0    # FP64 flops this kernel EXECUTES per shift (ncu op counts, profiles/r01_k3_ql_toeplitz_ncu_full.txt)
-K3_DRAM_TRAFFIC = 23.3e6        # dram read+write bytes of one 1024x1024 launch (same capture: 20.1 MB read + 3.3 MB written back in-kernel)
-K3_INSTR_PER_POINT = 907.0      # thread-level instructions issued per shift (smsp__inst_executed.sum * 32 / 2^20, same capture)
+NL = 8192                       # the large strong-scaling grid (NL x NL)
+
+
+def k3_ncu_constants():
+    """ncu-derived per-launch constants of the K3 kernel on the 1024² grid, read from the file the capture script writes
+    (profiles/k3_ncu_constants.json: commit hash of the capture, dram bytes, instructions and FP64 flops per shift)."""
+    path = os.path.join(ROOT, "profiles", "k3_ncu_constants.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {"commit": None, "dram_bytes_per_launch": None, "instr_per_point": None, "fp64_flops_per_point": None,
+                "source": "profiles/k3_ncu_constants.json missing"}
+
+
 BYTES_PER_COLUMN = 72           # Bessel (l=u=1): SURVEY §8d
 FLOPS_PER_COLUMN = 42
 
 
 def grid_slab(rank: int, world: int) -> np.ndarray:
-    """Rows rank, rank+world, ... of the global 1024 x (1024*world) λ grid over the C3 window (interleaved, so that
-    every rank covers the whole window and the per-GPU work is the same)."""
+    """WEAK form: rows rank, rank+world, ... of a global 1024 x (1024*world) λ grid over the C3 window (interleaved, so
+    that every rank covers the whole window and the per-GPU work is the same)."""
     import ila_b200
     return ila_b200.sharding.grid_rows(NX, NY * world, rank, world)
+
+
+def grid_shard(rank: int, world: int, nx: int = NX, ny: int = NY) -> np.ndarray:
+    """STRONG form: rows rank, rank+world, ... of the ONE global nx x ny grid (BASELINE config C3: 1024 x 1024)."""
+    import ila_b200
+    return ila_b200.sharding.grid_rows(nx, ny, rank, world)
+
+
+WORKLOAD = "C3 Bull-head ql(A-λI).L[1,1], ONE 1024x1024 complex λ grid (bands -3,-2,+1) sharded by rows over the GPUs"
 
 
 def c2_z():
@@ -151,7 +173,7 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     rows = 128                                       # bounded sample: 128 of the 1024 rows of the rank-0 slab
-    lam = grid_slab(0, max(world, 1))[:rows * NX]
+    lam = grid_shard(0, 1)[:rows * NX]
     times = []
     for _ in range(args.steps):
         dt, _ = cpu_bullhead(lam, threads)
@@ -160,9 +182,9 @@ def run_reference(args, rank, world):
     val = lam.size / (ms * 1e-3)
     line = {
         "metric": "bullhead_ql_lambda_points_per_s", "value": val, "unit": "lambda-points/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "C3 Bull-head ql(A-λI).L[1,1], 1024x1024 λ grid (bands -3,-2,+1), per-GPU slab",
+        "config": {"workload": WORKLOAD,
                    "sample": f"{rows} of 1024 grid rows per step"},
         "cpu_baseline": {"value": val, "unit": "lambda-points/s", "cores": threads, "kind": "port",
                          "sample": f"{rows}x{NX} λ-points per step, numpy/LAPACK zgeev oracle, {threads} threads"},
@@ -262,22 +284,35 @@ def run_ours(args, rank, local_rank, world):
     lib = ila_b200.lib()
     stream = torch.cuda.current_stream(dev).cuda_stream
 
-    # ---------------- C3: Bull-head λ grid, device resident ----------------
-    lam_h = grid_slab(rank, world)
-    n = lam_h.size
-    d_lam = torch.from_numpy(lam_h).to(dev)
-    d_L = torch.empty(n, dtype=torch.complex128, device=dev)
-    d_st = torch.empty(n, dtype=torch.int32, device=dev)
-
-    # the timed call: the device-resident C-ABI entry with pre-marshalled arguments, so that the host needs a few µs per step and
-    # the launch is queued while the (untimed) L2 flush still runs — no host-induced gap inside the event bracket
+    # ---------------- C3: ONE 1024 x 1024 Bull-head λ grid, rows sharded over the ranks (strong scaling) ----------------
     col_c = np.ascontiguousarray(BULLHEAD_COLUMN, dtype=np.complex128)
-    k3_args = (3, 1, _lib.ptr(col_c), _lib.ptr(d_lam), n, 1, _lib.ptr(d_L), None, _lib.ptr(d_st), ctypes.c_void_p(stream))
-    k3_fn = lib.ila_ql_toeplitz_l11_c64_dev
+    fn_dev = lib.ila_ql_toeplitz_l11re_c64_dev          # compact form: Float64 L11 (NaN payload = status) + uint8 status
+    sv = ctypes.c_void_p(stream)
 
-    def step_dev():
-        if k3_fn(*k3_args) != 0:
-            raise SystemExit("bench.py: ila_ql_toeplitz_l11_c64_dev failed")
+    def k3_device_run(lam_host, steps, warmup):
+        """Device-resident timing of this rank's share: returns (ms_per_step max over ranks, per-rank ms list, launches/step)."""
+        n_loc = lam_host.size
+        d_lam = torch.from_numpy(lam_host).to(dev)
+        d_L = torch.empty(n_loc, dtype=torch.float64, device=dev)
+        d_st = torch.empty(n_loc, dtype=torch.uint8, device=dev)
+        # pre-marshalled arguments: the host needs a few µs per step and the launch is queued while the (untimed) L2 flush still
+        # runs — no host-induced gap inside the event bracket
+        a = (3, 1, _lib.ptr(col_c), _lib.ptr(d_lam), n_loc, 1, _lib.ptr(d_L), _lib.ptr(d_st), sv)
+
+        def step():
+            if fn_dev(*a) != 0:
+                raise SystemExit("bench.py: ila_ql_toeplitz_l11re_c64_dev failed")
+        l0 = lib.ila_kernel_launches()
+        ms_tot = timed(step, steps, warmup)
+        per_step_launches = (lib.ila_kernel_launches() - l0) / float(steps + warmup)
+        mine = timed.last_local / steps
+        ranks = [mine]
+        if dist is not None:
+            t = torch.tensor([mine], dtype=torch.float64, device=dev)
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            ranks = [float(x.item()) for x in allt]
+        return ms_tot / steps, ranks, per_step_launches, (d_lam, d_L, d_st)
 
     try:
         gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
@@ -285,117 +320,236 @@ def run_ours(args, rank, local_rank, world):
         gpu_uuid = None
     sampler = ClockSampler(local_rank, gpu_uuid)
     sampler.start()
-    l0 = lib.ila_kernel_launches()
-    ms_total = timed(step_dev, args.steps, args.warmup)
-    launches = lib.ila_kernel_launches() - l0 - args.warmup
-    ms_step = ms_total / args.steps
-    rank_ms = [timed.last_local / args.steps]
-    if dist is not None:
-        t = torch.tensor([timed.last_local / args.steps], dtype=torch.float64, device=dev)
-        allt = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(allt, t)
-        rank_ms = [float(x.item()) for x in allt]
-    value = n * world / (ms_step * 1e-3)
+    lam_h = grid_shard(rank, world)                  # this rank's rows of THE 1024 x 1024 grid
+    n = lam_h.size
+    n_global = NX * NY
+    ms_step, rank_ms, launches_per_step, (d_lam, d_L, d_st) = k3_device_run(lam_h, args.steps, args.warmup)
+    launches = int(round(launches_per_step * args.steps))
+    value = n_global / (ms_step * 1e-3)
 
-    # ---------------- e2e: host API, pinned host buffers, H2D + kernel + D2H inside the timed region --------
-    h_lam = torch.from_numpy(lam_h).pin_memory()
-    h_L = torch.empty(n, dtype=torch.complex128).pin_memory()
-    h_st = torch.empty(n, dtype=torch.int32).pin_memory()
-    col = np.ascontiguousarray(BULLHEAD_COLUMN, dtype=np.complex128)
+    # ---------------- e2e: the host C-ABI call (compact form), HOST buffers, H2D + kernel + D2H inside the timed region --------
+    def host_bufs(n_loc, lam_src, pinned):
+        mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+        return (mk(torch.from_numpy(np.ascontiguousarray(lam_src))), mk(torch.empty(n_loc, dtype=torch.float64)),
+                mk(torch.empty(n_loc, dtype=torch.uint8)))
+
+    def wall_ms(fn, steps, warmup, all_ranks=True):
+        for _ in range(warmup):
+            fn()
+        if all_ranks:
+            barrier()
+        tot = 0.0
+        for _ in range(steps):
+            flush_l2()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()                                  # synchronous: returns after the D2H copies completed
+            tot += time.perf_counter() - t0
+        if all_ranks:
+            barrier()
+            return max_over_ranks(tot * 1e3) / steps
+        return tot * 1e3 / steps
+
+    def wall_ms_interleaved(fns, steps, warmup):
+        """The host of a GPU box is shared (copy rates drift by tens of percent between seconds): every variant is timed in the
+        same round-robin loop, so the drift hits all of them alike.  Returns {name: (mean ms, median ms)}, max over ranks."""
+        for f in fns.values():
+            for _ in range(warmup):
+                f()
+        barrier()
+        ts = {k: [] for k in fns}
+        for _ in range(steps):
+            for k, f in fns.items():
+                flush_l2()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                f()
+                ts[k].append((time.perf_counter() - t0) * 1e3)
+        barrier()
+        return {k: (max_over_ranks(float(np.mean(v))), max_over_ranks(float(np.median(v)))) for k, v in ts.items()}
+
+    col = col_c
+    h_lam, h_L, h_st = host_bufs(n, lam_h, True)
+    p_lam, p_L, p_st = host_bufs(n, lam_h, False)          # ordinary pageable arrays (what a Julia ccall passes)
+    h_Lc = torch.empty(n, dtype=torch.complex128).pin_memory()
+    h_st32 = torch.empty(n, dtype=torch.int32).pin_memory()
+    d_in = torch.empty(16 * n, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(9 * n, dtype=torch.uint8, device=dev)
+    hb_in = torch.empty(16 * n, dtype=torch.uint8).pin_memory()
+    hb_out = torch.empty(9 * n, dtype=torch.uint8).pin_memory()
+    s2 = torch.cuda.Stream(dev)
 
     def step_e2e():
-        _lib.check(lib.ila_ql_toeplitz_l11_c64(3, 1, _lib.ptr(col), _lib.ptr(h_lam), n, 1, _lib.ptr(h_L), None,
-                                               _lib.ptr(h_st), 1))
+        _lib.check(lib.ila_ql_toeplitz_l11re_c64(3, 1, _lib.ptr(col), _lib.ptr(h_lam), n, 1, _lib.ptr(h_L), _lib.ptr(h_st), 1))
 
-    for _ in range(args.warmup):
-        step_e2e()
-    barrier()
-    t_e2e = 0.0
-    for _ in range(args.steps):
-        flush_l2()
+    def step_e2e_pageable():        # the library's pinned staging ring + worker threads
+        _lib.check(lib.ila_ql_toeplitz_l11re_c64(3, 1, _lib.ptr(col), _lib.ptr(p_lam), n, 1, _lib.ptr(p_L), _lib.ptr(p_st), 1))
+
+    def step_e2e_pageable_driver():  # the same call forced onto plain cudaMemcpyAsync from the pageable arrays (round 1's path)
+        lib.ila_set_host_copy_mode(1)
+        try:
+            _lib.check(lib.ila_ql_toeplitz_l11re_c64(3, 1, _lib.ptr(col), _lib.ptr(p_lam), n, 1, _lib.ptr(p_L), _lib.ptr(p_st), 1))
+        finally:
+            lib.ila_set_host_copy_mode(0)
+
+    def step_e2e_c():                # round 1's form: ComplexF64 L11 + int32 status back (36 B/shift), pinned
+        _lib.check(lib.ila_ql_toeplitz_l11_c64(3, 1, _lib.ptr(col), _lib.ptr(h_lam), n, 1, _lib.ptr(h_Lc), None, _lib.ptr(h_st32), 1))
+
+    def step_copy():                 # copy floor: the same bytes by bare pinned cudaMemcpyAsync, both directions at once
+        d_in.copy_(hb_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hb_out.copy_(d_out, non_blocking=True)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step_e2e()                          # synchronous: returns after the D2H copies completed
-        t_e2e += time.perf_counter() - t0
-    barrier()
-    e2e_ms = max_over_ranks(t_e2e * 1e3) / args.steps
-    e2e_value = n * world / (e2e_ms * 1e-3)
+
+    def step_h2d():
+        d_in.copy_(hb_in, non_blocking=True)
+        torch.cuda.synchronize()
+
+    tv = wall_ms_interleaved({"pinned": step_e2e, "pageable": step_e2e_pageable, "pageable_driver": step_e2e_pageable_driver,
+                              "complex": step_e2e_c, "copy": step_copy, "h2d": step_h2d}, args.steps, args.warmup)
+    e2e_ms = tv["pinned"][0]
+    e2e_value = n_global / (e2e_ms * 1e-3)
+    e2e_pageable_ms, e2e_c_ms, copy_floor_ms, h2d_ms = tv["pageable"][0], tv["complex"][0], tv["copy"][0], tv["h2d"][0]
+    del d_in, d_out, hb_in, hb_out
     # ---------------- e2e, grid form (the reference example's call: ranges x, y in, abs(L11)/-1 matrix out) ----------
     xg = np.linspace(-10.0, 7.0, NX)
-    yg = np.linspace(-7.0, 8.0, NY * world)[rank::world].copy()
+    yg = np.linspace(-7.0, 8.0, NY)[rank::world].copy()
     h_x = torch.from_numpy(xg).pin_memory()
     h_y = torch.from_numpy(yg).pin_memory()
-    h_z = torch.empty(NY * NX, dtype=torch.float64).pin_memory()
+    h_z = torch.empty(yg.size * NX, dtype=torch.float64).pin_memory()
 
     def step_grid():
-        _lib.check(lib.ila_ql_toeplitz_absl11_grid_c64(3, 1, _lib.ptr(col), _lib.ptr(h_x), NX, _lib.ptr(h_y), NY, 1,
+        _lib.check(lib.ila_ql_toeplitz_absl11_grid_c64(3, 1, _lib.ptr(col), _lib.ptr(h_x), NX, _lib.ptr(h_y), yg.size, 1,
                                                        _lib.ptr(h_z), 1))
-
-    for _ in range(args.warmup):
-        step_grid()
-    barrier()
-    t_grid = 0.0
-    for _ in range(args.steps):
-        flush_l2()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step_grid()
-        t_grid += time.perf_counter() - t0
-    barrier()
-    grid_ms = max_over_ranks(t_grid * 1e3) / args.steps
-    zref = torch.where(h_st == 0, torch.view_as_real(h_L)[:, 0].abs(), torch.full((n,), -1.0, dtype=torch.float64))
+    grid_ms = wall_ms(step_grid, args.steps, args.warmup)
+    st_h = h_st.to(torch.int32)
+    zref = torch.where(st_h == 0, h_L.abs(), torch.full((n,), -1.0, dtype=torch.float64))
     if not bool(torch.allclose(h_z, zref, rtol=1e-12, atol=2e-12)):
         raise SystemExit("bench.py: grid form disagrees with the array form")
+    # cross-checks: host path (chunked launches) == device path == ComplexF64 form == pageable path (statuses, L11 to 1e-12)
+    def same_as_dev(L_host, st_host):
+        a = d_L.cpu().nan_to_num(0.0)
+        b = L_host.nan_to_num(0.0)
+        return bool(torch.equal(d_st.cpu().to(torch.int32), st_host.to(torch.int32))) and bool(torch.allclose(a, b, rtol=1e-12, atol=2e-12))
+    same = same_as_dev(h_L, h_st) and same_as_dev(p_L, p_st) and same_as_dev(torch.view_as_real(h_Lc)[:, 0].contiguous(), h_st32)
+    if not same:
+        raise SystemExit("bench.py: host, pageable, complex-form and device paths disagree")
+
+    # ---------------- the library's own in-process sharding: ONE call, ngpus = N, from rank 0 (other ranks wait) ----------
+    one_proc = None
+    ndev_visible = lib.ila_device_count()
+    if world > 1 and ndev_visible >= world:
+        barrier()
+        if rank == 0:
+            full = grid_shard(0, 1)
+            f_lam, f_L, f_st = host_bufs(full.size, full, True)
+
+            def step_full():
+                _lib.check(lib.ila_ql_toeplitz_l11re_c64(3, 1, _lib.ptr(col), _lib.ptr(f_lam), full.size, 1, _lib.ptr(f_L), _lib.ptr(f_st), world))
+            ms_full = wall_ms(step_full, max(3, args.steps // 2), args.warmup, all_ranks=False)
+            _lib.check(lib.ila_set_device(local_rank))
+            torch.cuda.set_device(local_rank)
+            one_proc = {"value": full.size / (ms_full * 1e-3), "unit": "lambda-points/s", "ms_per_step": ms_full,
+                        "api": f"ONE process, ila_ql_toeplitz_l11re_c64(..., ngpus={world}) on the whole 1024x1024 grid, pinned host buffers"}
+            del f_lam, f_L, f_st
+        barrier()
+
+    # ---------------- large strong-scaling case: ONE 8192 x 8192 grid over the same window ----------------
+    large = None
+    if not args.no_secondary:
+        lamL = grid_shard(rank, world, NL, NL)
+        kL = max(2, min(args.steps, 5))
+        msL, rank_msL, _, bufsL = k3_device_run(lamL, kL, 3)
+        large = {"metric": "bullhead_ql_lambda_points_per_s", "value": NL * NL / (msL * 1e-3), "unit": "lambda-points/s",
+                 "scaling": "strong", "ms_per_step": msL, "ms_per_step_by_rank": rank_msL,
+                 "config": {"workload": f"ONE {NL}x{NL} λ grid over the same window, rows sharded over the GPUs", "points_per_gpu": int(lamL.size)},
+                 "roofline": {"bound": "hbm", "achieved": BYTES_PER_POINT * lamL.size / (max(rank_msL) * 1e-3) / 1e9, "unit": "GB/s",
+                              "bytes_per_unit": BYTES_PER_POINT}}
+        del bufsL, lamL
+    # ---------------- weak form of round 1: one 1024 x 1024 slab per GPU ----------------
+    weak = None
+    if world > 1 and not args.no_secondary:
+        lamW = grid_slab(rank, world)
+        msW, rank_msW, _, bufsW = k3_device_run(lamW, max(3, args.steps // 2), 3)
+        weak = {"metric": "bullhead_ql_lambda_points_per_s", "value": lamW.size * world / (msW * 1e-3), "unit": "lambda-points/s",
+                "scaling": "weak", "ms_per_step": msW, "ms_per_step_by_rank": rank_msW,
+                "config": {"workload": "one 1024x1024 slab of a 1024 x (1024 N) grid per GPU (round 1's line)"}}
+        del bufsW, lamW
     sampler.stop_flag.set()
     sampler.join(timeout=2)
-    # cross-check: the host path (chunked launches) and the device path agree (same statuses, L11 to 1e-12)
-    dL = torch.view_as_real(d_L.cpu()).nan_to_num(0.0)
-    hL = torch.view_as_real(h_L).nan_to_num(0.0)
-    same = bool(torch.equal(d_st.cpu(), h_st)) and bool(torch.allclose(dL, hL, rtol=1e-12, atol=2e-12))
-    if not same:
-        raise SystemExit("bench.py: host and device paths disagree")
+
     hbm_peak, peak_kind = measured_peaks()
-    achieved_gbs = BYTES_PER_POINT * n / (ms_step * 1e-3) / 1e9
+    kc = k3_ncu_constants()
+    my_ms = max(rank_ms)
+    achieved_gbs = BYTES_PER_POINT * n / (my_ms * 1e-3) / 1e9
     fp64_peak = ila_b200.fp64_peak_tflops()
     clk = sampler.summary()
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     sm_clock_ghz = (clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0) / 1e3
+    ipp = kc.get("instr_per_point")
+    fpp = kc.get("fp64_flops_per_point")
     line = {
         "metric": "bullhead_ql_lambda_points_per_s", "value": value, "unit": "lambda-points/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": {"workload": "C3 Bull-head ql(A-λI).L[1,1], 1024x1024 λ grid (bands -3,-2,+1), per-GPU slab",
-                   "points_per_gpu": n, "ms_per_step_by_rank": rank_ms, "l2": "flushed between timed steps (768 MiB fill, untimed)", "parallelism":
-                   f"shift-grid sharding x{world}, no collective on the data path"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "points_global": n_global, "points_per_gpu": n, "ms_per_step_by_rank": rank_ms,
+                   "kernel_us_by_rank": [1e3 * t for t in rank_ms],
+                   "l2": "flushed between timed steps (768 MiB fill, untimed)",
+                   "parallelism": f"rows r, r+{world}, ... of the one grid on rank r; no collective on the data path",
+                   "abi_form": "ila_ql_toeplitz_l11re_c64_dev: Float64 L11 (NaN payload = status) + uint8 status"},
         "e2e": {"value": e2e_value, "unit": "lambda-points/s", "h2d_bytes_per_step": 16 * n,
-                "d2h_bytes_per_step": 20 * n, "ms_per_step": e2e_ms, "host_matches_device": same,
-                "api": "ila_ql_toeplitz_l11_c64 (λ array in, complex L11 + status out)", "host_affinity": numa},
-        "e2e_grid": {"value": n * world / (grid_ms * 1e-3), "unit": "lambda-points/s", "ms_per_step": grid_ms,
-                     "h2d_bytes_per_step": 8 * (NX + NY), "d2h_bytes_per_step": 8 * n,
+                "d2h_bytes_per_step": 9 * n, "ms_per_step": e2e_ms, "host_matches_device": same,
+                "api": "ila_ql_toeplitz_l11re_c64 (λ array in; Float64 L11 + uint8 status out), pinned host buffers, per rank its rows",
+                "host_affinity": numa,
+                "pageable_ms_per_step": e2e_pageable_ms, "pageable_value": n_global / (e2e_pageable_ms * 1e-3),
+                "pageable_driver_copy_ms_per_step": tv["pageable_driver"][0],
+                "median_ms": {k: v[1] for k, v in tv.items()},
+                "complex_form_ms_per_step": e2e_c_ms, "complex_form_bytes_per_point": 36,
+                "copy_floor_ms": copy_floor_ms, "h2d_only_ms": h2d_ms,
+                "h2d_gbs_measured": 16 * n / (h2d_ms * 1e-3) / 1e9,
+                "note": "all variants timed round-robin in one loop (shared host: copy rates drift); values are means over the steps, "
+                        "median_ms beside them.  copy_floor_ms = the same 16 n B in and 9 n B out moved by bare pinned cudaMemcpyAsync "
+                        "on two streams: the PCIe/host ceiling of the call on this box.  pageable = ordinary host arrays through the "
+                        "library's pinned staging ring (worker threads); pageable_driver = plain cudaMemcpyAsync on them"},
+        "e2e_grid": {"value": n_global / (grid_ms * 1e-3), "unit": "lambda-points/s", "ms_per_step": grid_ms,
+                     "h2d_bytes_per_step": 8 * (NX + yg.size), "d2h_bytes_per_step": 8 * n,
                      "api": "ila_ql_toeplitz_absl11_grid_c64 = the example's ℓ11.(Ref(A), x' .+ y.*im): ranges in, "
                             "abs(L11)/-1.0 matrix out (examples/toeplitz.jl:14-33)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": K3_DRAM_TRAFFIC if n == NX * NY else None,
+                     "frac": achieved_gbs / hbm_peak,
+                     "traffic": kc.get("dram_bytes_per_launch") if (world == 1 and n == NX * NY) else None,
                      "peak_kind": peak_kind,
                      "kernel": "ql_toeplitz_l11_kernel<4,false,false>", "bytes_per_unit": BYTES_PER_POINT,
-                     "note": "issue-slot / FP-latency bound, not HBM bound: see roofline_issue and roofline_fp64"},
-        "roofline_issue": {"bound": "warp-instruction issue (4 schedulers/SM, 1 instr/cycle each)",
-                           "achieved": K3_INSTR_PER_POINT / 32 * n / (ms_step * 1e-3) / 1e9,
-                           "peak": sm_count * 4 * sm_clock_ghz, "unit": "G warp-instr/s",
-                           "frac": K3_INSTR_PER_POINT / 32 * n / (ms_step * 1e-3) / 1e9 / (sm_count * 4 * sm_clock_ghz),
-                           "instr_per_unit": K3_INSTR_PER_POINT,
-                           "note": "per shift: ~148 FP64 + ~400 FP32 arithmetic instructions, rest selects/moves/compares"},
-        "roofline_fp64": {"bound": "fp64", "achieved": FP64_FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12,
-                          "peak": fp64_peak, "unit": "TFLOP/s",
-                          "frac": FP64_FLOPS_PER_POINT * n / (ms_step * 1e-3) / 1e12 / fp64_peak,
-                          "flops_per_unit": FP64_FLOPS_PER_POINT, "peak_kind": "measured DFMA probe (this run)",
-                          "note": "executed FP64 flops (ncu); the kernel also runs ~400 FP32 instr/shift on the FP32 pipe "
-                                  "and is issue-slot bound (ncu: issue active 65 %); the reference's LAPACK path is "
-                                  f"~{FLOPS_PER_POINT_LAPACK:.0f} flop/shift"},
-        "clocks": sampler.summary(),
+                     "bytes_per_unit_moved": BYTES_PER_POINT_COMPACT, "units_per_launch": n,
+                     "ncu_constants": kc,
+                     "note": "issue-slot / FP-latency bound, not HBM bound: see roofline_issue and roofline_fp64; per-rank launch "
+                             "of this rank's rows, slowest rank"},
+        "clocks": clk,
     }
-
+    if ipp:
+        line["roofline_issue"] = {"bound": "warp-instruction issue (4 schedulers/SM, 1 instr/cycle each)",
+                                  "achieved": ipp / 32 * n / (my_ms * 1e-3) / 1e9,
+                                  "peak": sm_count * 4 * sm_clock_ghz, "unit": "G warp-instr/s",
+                                  "frac": ipp / 32 * n / (my_ms * 1e-3) / 1e9 / (sm_count * 4 * sm_clock_ghz),
+                                  "instr_per_unit": ipp,
+                                  "note": "instr_per_unit from the ncu capture of the FULL 1024² launch (profiles/k3_ncu_constants.json); "
+                                          "sub-wave slabs (N > 1) run more cold starts per shift, so this understates their issue load"}
+    if fpp:
+        line["roofline_fp64"] = {"bound": "fp64", "achieved": fpp * n / (my_ms * 1e-3) / 1e12,
+                                 "peak": fp64_peak, "unit": "TFLOP/s",
+                                 "frac": fpp * n / (my_ms * 1e-3) / 1e12 / fp64_peak,
+                                 "flops_per_unit": fpp, "peak_kind": "measured DFMA probe (this run)",
+                                 "note": "executed FP64 flops (ncu); the root search runs on the FP32 pipe; the reference's LAPACK "
+                                         f"path is ~{FLOPS_PER_POINT_LAPACK:.0f} flop/shift"}
+    if one_proc is not None:
+        line["e2e_one_process"] = one_proc
+    if large is not None:
+        large["roofline"]["peak"] = hbm_peak
+        large["roofline"]["frac"] = large["roofline"]["achieved"] / hbm_peak
+        line["large"] = large
+    if weak is not None:
+        line["weak"] = weak
     # ---------------- secondary: C2 batched Bessel adaptive-QR solves ----------------
     if not args.no_secondary:
         from scipy.special import jv
@@ -415,15 +569,26 @@ def run_ours(args, rank, local_rank, world):
         cols_ref = float(plan.d_ncols.sum().item())
         gbs2 = BYTES_PER_COLUMN * cols / (ms2 * 1e-3) / 1e9
         line["secondary"] = {
-            "metric": "adaptive_qr_columns_per_s", "value": cols * world / (ms2 * 1e-3), "unit": "columns/s",
-            "ms_per_step": ms2, "config": {"workload": "C2 4096 Bessel solves, z in [1e3,1e5] (per GPU)",
+            "metric": "adaptive_qr_columns_per_s", "value": cols * world / (ms2 * 1e-3), "unit": "columns/s", "scaling": "weak",
+            "ms_per_step": ms2, "config": {"workload": "C2 4096 Bessel solves, z in [1e3,1e5] (the whole batch on every GPU)",
                                            "columns_swept": cols, "columns_reference_datasize": cols_ref},
             "roofline": {"bound": "hbm", "achieved": gbs2, "peak": hbm_peak, "unit": "GB/s", "frac": gbs2 / hbm_peak,
                          "traffic": None, "peak_kind": peak_kind, "bytes_per_unit": BYTES_PER_COLUMN,
                          "note": "latency bound: 4096 serial recurrences = 128 warps on 148 SMs"},
             "gpu_launches_per_step": launches2,
         }
-
+        if world > 1:
+            # strong form: the ONE batch of 4096 z sharded round-robin (z sorted, i mod N: lengths balance)
+            zi = ila_b200.sharding.interleaved(len(zs), rank, world)
+            plan_s = ila_b200.QrBandedPlan(1, 1, p[zi], q[zi], r[zi], b=jv(1, zs[zi])[:, None], ncap_per=caps[zi], device=dev)
+            ms2s = timed(plan_s.run, k2, 1) / k2
+            cols_s = sum_over_ranks(float(plan_s.d_nswept.sum().item()))
+            line["secondary"]["strong"] = {
+                "value": cols_s / (ms2s * 1e-3), "unit": "columns/s", "scaling": "strong", "ms_per_step": ms2s,
+                "config": {"workload": "the ONE C2 batch sharded round-robin over the GPUs",
+                           "note": "the time is the dependent chain of the longest instance (z = 1e5), which one GPU holds "
+                                   "whatever N is: a single batch of 4096 serial recurrences does not strong-scale"}}
+            del plan_s
     # ---------------- other §8 configs (device resident, same timing rules): C4 Cholesky, C5 block QL --------
     if not args.no_secondary:
         sigma = 0.01 + (10 - 0.01) * np.arange(2048) / 2047
@@ -599,7 +764,7 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         rows = 256
-        sample = lam_h[:rows * NX]
+        sample = grid_shard(0, 1)[:rows * NX]
         dt, res = cpu_bullhead(sample, threads)
         line["cpu_baseline"] = {"value": sample.size / dt, "unit": "lambda-points/s", "cores": threads, "kind": "port",
                                 "sample": f"{rows}x{NX} λ-points once, numpy/LAPACK zgeev oracle in {threads} worker "

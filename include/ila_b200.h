@@ -65,6 +65,33 @@ int ila_ql_toeplitz_l11_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambd
                             ila_c64 *L11, ila_c64 *tail_opt, int32_t *status, int ngpus);
 int ila_ql_toeplitz_l11_f64(int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank,
                             double *L11, double *tail_opt, int32_t *status, int ngpus);
+/* Compact form for complex symbols / shifts.  L[1,1] of a ComplexF64 factorization is REAL: ql_X!'s k = 1 reflector
+ * leaves X[1,m-1] = -nu (src/banded/infqltoeplitz.jl:33 -> ql!, the `(T<:Real)` bound of examples/jacobi.jl:63) and the
+ * sign fix (:34-37) only negates it — so the imaginary part the _c64 form returns is a literal 0.  This form returns
+ *   L11re       n doubles; where status != 0 a quiet NaN whose low mantissa bits hold the status code
+ *               (bits = 0x7ff8000000000000 | status)
+ *   status8_opt NULL, or n bytes with the same codes
+ * 16 B in, 8 (+1) B out per shift instead of 16 + 20: the end-to-end call is PCIe-bound. */
+int ila_ql_toeplitz_l11re_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank,
+                              double *L11re, uint8_t *status8_opt, int ngpus);
+int ila_ql_toeplitz_l11re_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d_lambda, int64_t n, int branch_rank,
+                                  double *d_L11re, uint8_t *d_status8_opt, void *stream);
+
+/* Host buffers.  The K3 host entry points accept ANY host pointer.  Pinned memory (ila_host_alloc, ila_host_register,
+ * cudaHostAlloc, a torch pinned tensor) is copied by DMA straight from/to the caller's arrays, chunked over several
+ * streams.  Ordinary pageable memory (a Julia Vector passed by ccall) goes through the library's own pinned staging
+ * ring with worker threads (mode 0 = automatic); ila_set_host_copy_mode(1) forces plain cudaMemcpyAsync on the caller's
+ * pointers, (2) forces the staging ring.  ila_host_register pins an existing allocation in place (unregister it before
+ * freeing it). */
+int ila_host_alloc(void **ptr, int64_t bytes);
+int ila_host_free(void *ptr);
+int ila_host_register(void *ptr, int64_t bytes);
+int ila_host_unregister(void *ptr);
+int ila_set_host_copy_mode(int mode);
+/* Chunk schedule of the pinned-buffer pipeline of the K3 host call: chunk = remaining / divisor, never below
+ * min_chunk_shifts, the last chunk takes the remainder (0, 0 = defaults: 64 Ki shifts, divisor 3). */
+int ila_set_host_chunking(int64_t min_chunk_shifts, int divisor);
+
 /* device-resident forms: `a` stays a HOST pointer (l+u+1 values, passed by value to the kernel) */
 int ila_ql_toeplitz_l11_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d_lambda, int64_t n, int branch_rank,
                                 ila_c64 *d_L11, ila_c64 *d_tail_opt, int32_t *d_status, void *stream);
@@ -96,6 +123,10 @@ int ila_ql_perttoeplitz_l11_f64(int l, int u, int p, const double *head, const d
  * shift's roots (any doubt falls back to a cold simultaneous solve, so results do not depend on it).
  * 0 = automatic (default), 1 = every shift cold. */
 int ila_ql_set_shifts_per_thread(int spt);
+/* Sweep limits of the K3 root finder (0 = defaults: 48 FP64 Aberth sweeps, 16 FP32 scout sweeps).  A shift whose
+ * iteration uses up its sweeps without reaching a root to rounding (backward error test) gets status
+ * ILA_NOT_CONVERGED and NaN — never a silent value.  Lowering the limits is a test hook that forces that outcome. */
+int ila_ql_set_max_sweeps(int fp64_sweeps, int scout_sweeps);
 
 /* ---- K1+K2: adaptive banded QR solve  x_i = A_i \ b_i ----------------------------------------
  * Replaces qr(A) -> adaptiveqr (src/infqr.jl:163-174) and `\` = ldiv!(F.R, F.Q'*b) (src/infqr.jl:370-374):

@@ -88,6 +88,15 @@ SIGNATURES = {
     "ila_ql_finite_section_c64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_double, C.c_int64,
                                             _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "ila_ql_set_shifts_per_thread": (C.c_int, [C.c_int]),
+    "ila_ql_set_max_sweeps": (C.c_int, [C.c_int, C.c_int]),
+    "ila_ql_toeplitz_l11re_c64": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int]),
+    "ila_ql_toeplitz_l11re_c64_dev": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp]),
+    "ila_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "ila_host_free": (C.c_int, [_vp]),
+    "ila_host_register": (C.c_int, [_vp, C.c_int64]),
+    "ila_host_unregister": (C.c_int, [_vp]),
+    "ila_set_host_copy_mode": (C.c_int, [C.c_int]),
+    "ila_set_host_chunking": (C.c_int, [C.c_int64, C.c_int]),
     "ila_qr_banded_solve_f64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp,
                                           C.c_double, C.c_int, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp,
                                           _vp, _vp, _vp, C.c_int]),

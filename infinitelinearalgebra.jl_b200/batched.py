@@ -49,6 +49,28 @@ def ql_toeplitz_l11(data_column, lambdas, branch_rank: int = 1, want_tail: bool 
     return res
 
 
+def ql_toeplitz_l11_real(data_column, lambdas, branch_rank: int = 1, ngpus: int = 1, want_status: bool = True, out=None,
+                         status_out=None):
+    """Compact complex-eltype form (`ila_ql_toeplitz_l11re_c64`): L[1,1] of ql(A - λI) is REAL for ComplexF64 input, so
+    8 B (+ 1 B status) per shift come back instead of 16 + 4.  Returns (L11 float64 — NaN where status != 0 with the
+    status in the NaN payload —, status uint8 or None)."""
+    col = np.ascontiguousarray(np.asarray(data_column), dtype=np.complex128)
+    lam = np.asarray(lambdas)
+    shape = lam.shape
+    lam = np.ascontiguousarray(lam, dtype=np.complex128).reshape(-1)
+    n = lam.size
+    L11 = out if out is not None else np.empty(n, dtype=np.float64)
+    status = status_out if status_out is not None else (np.empty(n, dtype=np.uint8) if want_status else None)
+    check(lib().ila_ql_toeplitz_l11re_c64(col.size - 2, 1, ptr(col), ptr(lam), n, branch_rank, ptr(L11), ptr(status), ngpus))
+    return L11.reshape(shape), (status.reshape(shape) if status is not None else None)
+
+
+def status_from_nan_payload(L11re):
+    """Status codes carried by the NaN payloads of `ql_toeplitz_l11_real`'s result (0 where the entry is a number)."""
+    bits = np.ascontiguousarray(L11re, dtype=np.float64).view(np.uint64)
+    return np.where(np.isnan(L11re), (bits & np.uint64(0xFF)).astype(np.int32), 0).astype(np.int32)
+
+
 def ql_toeplitz_solve(data_column, lambdas, b, nout: int, branch_rank: int = 1, ngpus: int = 1,
                       real_path: bool | None = None):
     """First `nout` entries of x = ql(A - λI) \\ b over all shifts `lambdas`, for the pure Toeplitz A of

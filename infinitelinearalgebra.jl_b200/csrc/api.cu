@@ -1,6 +1,11 @@
 // api.cu — the C ABI of libila_b200 (include/ila_b200.h): host-pointer entry points that own device memory,
 // streams and the multi-GPU sharding, plus the device-pointer (`_dev`) forms.  No torch types, no CPU fallback.
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "ila_common.cuh"
@@ -14,13 +19,20 @@ std::atomic<int64_t> g_launches{0};
 // ---- per-device grow-only buffer pool (host entry points only) ---------------------------------------
 constexpr int kMaxDev = 16;
 constexpr int kSlots = 24;
-constexpr int kPipe = 3;   // copy/compute pipeline depth of the host entry points
+constexpr int kPipe = 4;   // copy/compute pipeline depth of the host entry points (= staging workers per device)
+constexpr int kMaxChunkEv = 48;   // chunks of the pinned-buffer pipeline (the last one takes the remainder)
+constexpr int kStage = 2;  // pinned staging slots per pipeline stream (double buffering)
 struct DevState {
     bool init = false;
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[kPipe] = {};
     void *buf[kSlots] = {};
     size_t cap[kSlots] = {};
+    // pinned staging buffers of the pageable-caller path (grow-only, cudaHostAlloc) and their completion events
+    void *hin[kPipe][kStage] = {}, *hout[kPipe][kStage] = {};
+    size_t hin_cap[kPipe][kStage] = {}, hout_cap[kPipe][kStage] = {};
+    cudaEvent_t hev[kPipe][kStage] = {};
+    cudaEvent_t cev[kMaxChunkEv][2] = {};   // per chunk of the pinned pipeline: input arrived / kernel done
 };
 static DevState g_dev[kMaxDev];
 static std::mutex g_mutex;
@@ -31,6 +43,10 @@ static int dev_init(int d)
     if (!g_dev[d].init) {
         ILA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_dev[d].stream, cudaStreamNonBlocking));
         for (int i = 0; i < kPipe; i++) ILA_CUDA_CHECK(cudaStreamCreateWithFlags(&g_dev[d].pipe[i], cudaStreamNonBlocking));
+        for (int i = 0; i < kPipe; i++)
+            for (int k = 0; k < kStage; k++) ILA_CUDA_CHECK(cudaEventCreateWithFlags(&g_dev[d].hev[i][k], cudaEventDisableTiming));
+        for (int i = 0; i < kMaxChunkEv; i++)
+            for (int k = 0; k < 2; k++) ILA_CUDA_CHECK(cudaEventCreateWithFlags(&g_dev[d].cev[i][k], cudaEventDisableTiming));
         g_dev[d].init = true;
     }
     return 0;
@@ -49,6 +65,74 @@ static int dev_buf(int d, int slot, size_t bytes, void **out)
     *out = S.buf[slot];
     return 0;
 }
+static int host_stage_buf(void **buf, size_t *cap, size_t bytes)
+{
+    if (*cap >= bytes) return 0;
+    if (*buf) ILA_CUDA_CHECK(cudaFreeHost(*buf));
+    *buf = nullptr;
+    *cap = 0;
+    ILA_CUDA_CHECK(cudaHostAlloc(buf, bytes, cudaHostAllocPortable));
+    *cap = bytes;
+    return 0;
+}
+// true when the driver can DMA straight from/to this host pointer (cudaHostAlloc / cudaHostRegister / managed memory)
+static bool host_ptr_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+static std::atomic<int64_t> g_chunk_min{0};   // tuning hooks of the pinned pipeline (ila_set_host_chunking): smallest chunk,
+static std::atomic<int> g_chunk_div{0};       // and the divisor of the geometric schedule (chunk = remaining / div)
+static std::atomic<int> g_host_copy_mode{0};   // 0 auto, 1 always direct cudaMemcpyAsync, 2 always staged (ila_set_host_copy_mode)
+
+// Persistent host worker threads of the staged copy path (created on first use, never destroyed: they sleep on a
+// condition variable between calls; host entry points are serialised by g_mutex, so one call uses the pool at a time).
+class WorkerPool {
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::deque<std::function<void()>> q_;
+    std::vector<std::thread> th_;
+    int pending_ = 0;
+
+  public:
+    void ensure(int n)
+    {
+        while ((int)th_.size() < n)
+            th_.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> job;
+                    {
+                        std::unique_lock<std::mutex> lk(m_);
+                        cv_.wait(lk, [this] { return !q_.empty(); });
+                        job = std::move(q_.front());
+                        q_.pop_front();
+                    }
+                    job();
+                    {
+                        std::lock_guard<std::mutex> lk(m_);
+                        if (--pending_ == 0) done_.notify_all();
+                    }
+                }
+            });
+    }
+    void submit(std::function<void()> f)
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.push_back(std::move(f));
+            pending_++;
+        }
+        cv_.notify_one();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+};
+static WorkerPool *g_pool = nullptr;   // leaked on purpose (its threads must not be joined from a static destructor)
+
 template <class T>
 static int dev_buf_t(int d, int slot, size_t count, T **out)
 {
@@ -74,11 +158,37 @@ static int resolve_ngpus(int ngpus, int *out)
     if (cnt > kMaxDev) cnt = kMaxDev;
     if (ngpus <= 0 || ngpus > cnt) ngpus = cnt;
     *out = ngpus;
-    int cur = 0;
-    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = 0; }
-    g_base_dev = cur;
     return 0;
 }
+
+// Every host entry point holds g_mutex for its whole duration and declares one HostGuard right after taking it: the guard
+// records the caller's current device (the device single-GPU calls run on) UNDER the lock, and on every exit that did not
+// reach the normal end (`done`) it drains the streams of all devices the call may have used and restores the caller's
+// device — so an error return never leaves async copies into the caller's buffers in flight.
+struct HostGuard {
+    int G;
+    bool done = false;
+    explicit HostGuard(int G_) : G(G_)
+    {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = 0; }
+        if (cur < 0 || cur >= kMaxDev) cur = 0;
+        g_base_dev = cur;
+    }
+    ~HostGuard()
+    {
+        if (done) return;
+        for (int d = 0; d < G; d++) {
+            const int pd = phys(d, G);
+            if (pd < 0 || pd >= kMaxDev || !g_dev[pd].init) continue;
+            if (cudaSetDevice(pd) != cudaSuccess) { cudaGetLastError(); continue; }
+            cudaStreamSynchronize(g_dev[pd].stream);
+            for (int i = 0; i < kPipe; i++) cudaStreamSynchronize(g_dev[pd].pipe[i]);
+        }
+        cudaSetDevice(g_base_dev);
+        cudaGetLastError();
+    }
+};
 
 // ---- FP64 peak probe ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_probe_kernel(double *out, int iters)
@@ -167,8 +277,17 @@ int ila_release(void)
             S.cap[k] = 0;
         }
         if (S.stream) cudaStreamDestroy(S.stream);
-        for (int i = 0; i < kPipe; i++)
+        for (int i = 0; i < kPipe; i++) {
             if (S.pipe[i]) cudaStreamDestroy(S.pipe[i]);
+            for (int k = 0; k < kStage; k++) {
+                if (S.hin[i][k]) cudaFreeHost(S.hin[i][k]);
+                if (S.hout[i][k]) cudaFreeHost(S.hout[i][k]);
+                if (S.hev[i][k]) cudaEventDestroy(S.hev[i][k]);
+            }
+        }
+        for (int i = 0; i < kMaxChunkEv; i++)
+            for (int k = 0; k < 2; k++)
+                if (S.cev[i][k]) cudaEventDestroy(S.cev[i][k]);
         S = DevState{};
     }
     cudaSetDevice(cur);
@@ -231,45 +350,189 @@ int ila_fp64_latency_probe(double *out4)
 
 // ================================ K3: Toeplitz-tail QL =================================================
 
-static int ql_toeplitz_host(bool real_path, int l, int u, const double *a, const double *lambda, int64_t n,
-                            int branch_rank, double *L11, double *tail_opt, int32_t *status, int ngpus)
+// One device's share of a K3 host call through pinned staging buffers (the caller's arrays are ordinary pageable memory —
+// what a Julia `ccall` passes).  kPipe worker threads, each with its own stream and kStage pinned slots: memcpy λ-chunk
+// into a slot -> H2D -> kernel -> D2H into the slot -> (when the slot comes round again) memcpy the results out.  The
+// host copies of the workers run in parallel with each other and with the GPU work of the other slots.
+struct TzStageJob {
+    bool real_path;
+    int out_mode, l, u, branch_rank, pd;
+    const double *a, *lambda;
+    int64_t lo, cnt, chunk;
+    double *d_lam, *d_L;
+    void *d_st;
+    double *L11;
+    void *status;
+    bool stage_in, stage_out;   // which side goes through the pinned slots (a pinned caller buffer is used directly)
+};
+
+static int tz_stage_worker(const TzStageJob &J, int t)
 {
-    if (n < 0 || !a || (n > 0 && (!lambda || !L11 || !status))) return set_error(ILA_ERR_ARG, "ql_toeplitz: null pointer / negative n");
+    DevState &S = g_dev[J.pd];
+    ILA_CUDA_CHECK(cudaSetDevice(J.pd));
+    const int w = J.real_path ? 1 : 2, ow = (J.out_mode == 1) ? 1 : w, sb = (J.out_mode == 1) ? 1 : 4;
+    const size_t in_b = sizeof(double) * w, out_b = sizeof(double) * ow;
+    // slot layout: L11 chunk, then the status chunk at an 8-aligned offset
+    const size_t st_off = (size_t)J.chunk * out_b;
+    cudaStream_t s = S.pipe[t];
+    const int64_t nchunks = (J.cnt + J.chunk - 1) / J.chunk;
+    struct Pending { int64_t c0 = -1, cc = 0; } pend[kStage];
+    auto flush = [&](int k) -> int {
+        if (pend[k].c0 < 0) return 0;
+        ILA_CUDA_CHECK(cudaEventSynchronize(S.hev[t][k]));
+        const char *src = static_cast<const char *>(S.hout[t][k]);
+        memcpy(reinterpret_cast<char *>(J.L11) + (size_t)(J.lo + pend[k].c0) * out_b, src, (size_t)pend[k].cc * out_b);
+        if (J.status)
+            memcpy(static_cast<char *>(J.status) + (size_t)(J.lo + pend[k].c0) * sb, src + st_off, (size_t)pend[k].cc * sb);
+        pend[k].c0 = -1;
+        return 0;
+    };
+    int rc = 0, it = 0;
+    for (int64_t ci = t; ci < nchunks; ci += kPipe, it++) {
+        const int k = it % kStage;
+        const int64_t c0 = ci * J.chunk, cc = (c0 + J.chunk <= J.cnt) ? J.chunk : J.cnt - c0;
+        if ((rc = flush(k))) return rc;
+        const double *src_lam = J.lambda + (size_t)(J.lo + c0) * w;
+        if (J.stage_in) {
+            if (it >= kStage && !J.stage_out) ILA_CUDA_CHECK(cudaEventSynchronize(S.hev[t][k]));   // slot's last H2D done
+            memcpy(S.hin[t][k], src_lam, (size_t)cc * in_b);
+            src_lam = static_cast<const double *>(S.hin[t][k]);
+        }
+        ILA_CUDA_CHECK(cudaMemcpyAsync(J.d_lam + c0 * w, src_lam, (size_t)cc * in_b, cudaMemcpyHostToDevice, s));
+        if (J.out_mode == 1)
+            rc = launch_ql_toeplitz_l11re(J.l, J.u, J.a, J.branch_rank, J.d_lam + c0 * w, cc, J.d_L + c0,
+                                          J.status ? static_cast<uint8_t *>(J.d_st) + c0 : nullptr, s);
+        else
+            rc = launch_ql_toeplitz(J.real_path, J.l, J.u, J.a, J.branch_rank, J.d_lam + c0 * w, cc, J.d_L + c0 * w, nullptr,
+                                    static_cast<int32_t *>(J.d_st) + c0, s);
+        if (rc) return rc;
+        if (J.stage_out) {
+            char *dst = static_cast<char *>(S.hout[t][k]);
+            ILA_CUDA_CHECK(cudaMemcpyAsync(dst, J.d_L + c0 * ow, (size_t)cc * out_b, cudaMemcpyDeviceToHost, s));
+            if (J.status)
+                ILA_CUDA_CHECK(cudaMemcpyAsync(dst + st_off, static_cast<char *>(J.d_st) + (size_t)c0 * sb, (size_t)cc * sb, cudaMemcpyDeviceToHost, s));
+            pend[k].c0 = c0;
+            pend[k].cc = cc;
+        } else {
+            ILA_CUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<char *>(J.L11) + (size_t)(J.lo + c0) * out_b, J.d_L + c0 * ow, (size_t)cc * out_b, cudaMemcpyDeviceToHost, s));
+            if (J.status)
+                ILA_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(J.status) + (size_t)(J.lo + c0) * sb, static_cast<char *>(J.d_st) + (size_t)c0 * sb, (size_t)cc * sb, cudaMemcpyDeviceToHost, s));
+        }
+        ILA_CUDA_CHECK(cudaEventRecord(S.hev[t][k], s));
+    }
+    for (int j = 0; j < kStage; j++)
+        if ((rc = flush((it + j) % kStage))) return rc;
+    return 0;
+}
+
+// out_mode 0: L11 has the symbol's scalar type, status int32.  out_mode 1 (complex symbols only): L11 is Float64 (L[1,1] of a
+// complex-eltype factorization is real), status uint8 or NULL (the NaN payload carries it) — 24-25 B/shift instead of 36.
+static int ql_toeplitz_host(bool real_path, int out_mode, int l, int u, const double *a, const double *lambda, int64_t n,
+                            int branch_rank, double *L11, double *tail_opt, void *status, int ngpus)
+{
+    if (n < 0 || !a || (n > 0 && (!lambda || !L11 || (!status && out_mode != 1)))) return set_error(ILA_ERR_ARG, "ql_toeplitz: null pointer / negative n");
     int G = 0;
     int rc = resolve_ngpus(ngpus, &G);
     if (rc) return rc;
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     const int w = real_path ? 1 : 2;             // doubles per scalar
+    const int ow = (out_mode == 1) ? 1 : w;      // doubles per L11 entry
+    const int sb = (out_mode == 1) ? 1 : 4;      // bytes per status entry
     const int m = l + 2, tl = 2 * m + 2;
     if (G > n) G = (int)n;
     const int64_t per = (n + G - 1) / G;
+    // pageable caller buffers (a Julia Vector): the driver's own pageable path stages every copy through one bounce buffer and
+    // blocks the calling thread; kPipe workers with pinned slots keep PCIe busy in both directions instead
+    const int mode = g_host_copy_mode.load();
+    const bool pin_in = host_ptr_pinned(lambda), pin_out = host_ptr_pinned(L11) && (!status || host_ptr_pinned(status));
+    const bool staged = !tail_opt && (mode == 2 || (mode == 0 && !(pin_in && pin_out) && n >= 4096));
+    const bool stage_in = staged && (mode == 2 || !pin_in), stage_out = staged && (mode == 2 || !pin_out);
+    std::vector<TzStageJob> jobs;
     for (int d = 0; d < G; d++) {
         const int64_t lo = d * per, cnt = (lo + per <= n ? per : n - lo);
         if (cnt <= 0) continue;
         const int pd = phys(d, G);
         if ((rc = dev_init(pd))) return rc;
         double *d_lam, *d_L, *d_tail = nullptr;
-        int32_t *d_st;
+        char *d_st = nullptr;
         if ((rc = dev_buf_t(pd, 0, (size_t)cnt * w, &d_lam))) return rc;
-        if ((rc = dev_buf_t(pd, 1, (size_t)cnt * w, &d_L))) return rc;
-        if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt * ow, &d_L))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt * 4, &d_st))) return rc;
         if (tail_opt && (rc = dev_buf_t(pd, 3, (size_t)cnt * tl * w, &d_tail))) return rc;
-        // chunked three-stream pipeline: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c
-        // (full-duplex PCIe when the caller's buffers are pinned; pageable buffers still work, serialised)
-        const int64_t chunk = cnt > (1 << 18) ? (1 << 17) : cnt;
-        int ci = 0;
-        for (int64_t c0 = 0; c0 < cnt; c0 += chunk, ci++) {
-            const int64_t cc = (c0 + chunk <= cnt) ? chunk : cnt - c0;
-            cudaStream_t s = g_dev[pd].pipe[ci % kPipe];
-            ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam + c0 * w, lambda + (lo + c0) * w, sizeof(double) * cc * w, cudaMemcpyHostToDevice, s));
-            if ((rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam + c0 * w, cc, d_L + c0 * w,
-                                         d_tail ? d_tail + c0 * tl * w : nullptr, d_st + c0, s))) return rc;
-            ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + (lo + c0) * w, d_L + c0 * w, sizeof(double) * cc * w, cudaMemcpyDeviceToHost, s));
-            ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo + c0, d_st + c0, sizeof(int32_t) * cc, cudaMemcpyDeviceToHost, s));
-            if (tail_opt)
-                ILA_CUDA_CHECK(cudaMemcpyAsync(tail_opt + (lo + c0) * tl * w, d_tail + c0 * tl * w, sizeof(double) * cc * tl * w, cudaMemcpyDeviceToHost, s));
+        if (staged) {
+            // chunk: at least 8 per device so that every worker has work, at most 64 Ki shifts (1 MiB of λ) per slot
+            int64_t chunk = (cnt + 2 * kPipe - 1) / (2 * kPipe);
+            if (chunk > (1 << 16)) chunk = 1 << 16;
+            if (chunk < 1024) chunk = cnt < 1024 ? cnt : 1024;
+            for (int t = 0; t < kPipe; t++)
+                for (int k = 0; k < kStage; k++) {
+                    if ((rc = host_stage_buf(&g_dev[pd].hin[t][k], &g_dev[pd].hin_cap[t][k], (size_t)chunk * sizeof(double) * w))) return rc;
+                    if ((rc = host_stage_buf(&g_dev[pd].hout[t][k], &g_dev[pd].hout_cap[t][k], (size_t)chunk * (sizeof(double) * ow + 8)))) return rc;
+                }
+            jobs.push_back(TzStageJob{real_path, out_mode, l, u, branch_rank, pd, a, lambda, lo, cnt, chunk, d_lam, d_L, d_st, L11, status,
+                                      stage_in, stage_out});
+            continue;
         }
+        // pinned caller buffers.  The call is bound by the H2D copy of λ (16 B/shift over PCIe), so the pipeline is built around
+        // keeping that copy engine busy from the first microsecond to the last: ALL input chunks go back to back on one
+        // stream; the kernels (two alternating streams) and the D2H copies (their own stream) hang off events.  Chunk sizes
+        // shrink geometrically so that what is left after the last input byte has arrived — one small kernel and its
+        // small D2H — is short.
+        DevState &S = g_dev[pd];
+        cudaStream_t s_in = S.pipe[0], s_out = S.pipe[1];
+        const int64_t min_chunk = g_chunk_min.load() > 0 ? g_chunk_min.load() : (1 << 16);
+        const int shrink = g_chunk_div.load() > 1 ? g_chunk_div.load() : 3;
+        int ci = 0;
+        for (int64_t c0 = 0; c0 < cnt; ci++) {
+            int64_t cc = (cnt - c0) / shrink;
+            cc = (cc + 1023) & ~(int64_t)1023;           // whole grid rows of the usual power-of-two widths
+            if (cc < min_chunk) cc = min_chunk;
+            if (c0 + cc > cnt || cnt - (c0 + cc) < min_chunk / 2) cc = cnt - c0;
+            if (ci >= kMaxChunkEv) cc = cnt - c0;
+            cudaStream_t s_k = S.pipe[2 + (ci & 1)];
+            ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam + c0 * w, lambda + (lo + c0) * w, sizeof(double) * cc * w, cudaMemcpyHostToDevice, s_in));
+            ILA_CUDA_CHECK(cudaEventRecord(S.cev[ci][0], s_in));
+            ILA_CUDA_CHECK(cudaStreamWaitEvent(s_k, S.cev[ci][0], 0));
+            if (out_mode == 1)
+                rc = launch_ql_toeplitz_l11re(l, u, a, branch_rank, d_lam + c0 * w, cc, d_L + c0,
+                                              status ? reinterpret_cast<uint8_t *>(d_st) + c0 : nullptr, s_k);
+            else
+                rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam + c0 * w, cc, d_L + c0 * w,
+                                        d_tail ? d_tail + c0 * tl * w : nullptr, reinterpret_cast<int32_t *>(d_st) + c0, s_k);
+            if (rc) return rc;
+            ILA_CUDA_CHECK(cudaEventRecord(S.cev[ci][1], s_k));
+            ILA_CUDA_CHECK(cudaStreamWaitEvent(s_out, S.cev[ci][1], 0));
+            ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + (lo + c0) * ow, d_L + c0 * ow, sizeof(double) * cc * ow, cudaMemcpyDeviceToHost, s_out));
+            if (status)
+                ILA_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(status) + (lo + c0) * sb, d_st + c0 * sb, (size_t)cc * sb, cudaMemcpyDeviceToHost, s_out));
+            if (tail_opt)
+                ILA_CUDA_CHECK(cudaMemcpyAsync(tail_opt + (lo + c0) * tl * w, d_tail + c0 * tl * w, sizeof(double) * cc * tl * w, cudaMemcpyDeviceToHost, s_out));
+            c0 += cc;
+        }
+    }
+    if (!jobs.empty()) {
+        // workers: kPipe per device from the persistent pool; worker (job 0, stream 0) runs on the calling thread
+        if (!g_pool) g_pool = new WorkerPool();
+        g_pool->ensure((int)jobs.size() * kPipe - 1);
+        std::vector<int> rcs(jobs.size() * kPipe, 0);
+        std::vector<std::string> errs(jobs.size() * kPipe);
+        for (size_t j = 0; j < jobs.size(); j++)
+            for (int t = 0; t < kPipe; t++) {
+                if (j == 0 && t == 0) continue;
+                g_pool->submit([&, j, t] {
+                    rcs[j * kPipe + t] = tz_stage_worker(jobs[j], t);
+                    if (rcs[j * kPipe + t]) errs[j * kPipe + t] = g_last_error;   // thread-local text -> caller
+                });
+            }
+        rcs[0] = tz_stage_worker(jobs[0], 0);
+        g_pool->wait();
+        for (size_t k = 0; k < rcs.size(); k++)
+            if (rcs[k]) {
+                if (k) snprintf(g_last_error, sizeof(g_last_error), "%s", errs[k].c_str());
+                return rcs[k];
+            }
     }
     for (int d = 0; d < G; d++) {
         const int pd = phys(d, G);
@@ -277,6 +540,7 @@ static int ql_toeplitz_host(bool real_path, int l, int u, const double *a, const
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         for (int i = 0; i < kPipe; i++) ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].pipe[i]));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -284,14 +548,71 @@ static int ql_toeplitz_host(bool real_path, int l, int u, const double *a, const
 int ila_ql_toeplitz_l11_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank,
                             ila_c64 *L11, ila_c64 *tail_opt, int32_t *status, int ngpus)
 {
-    return ql_toeplitz_host(false, l, u, (const double *)a, (const double *)lambda, n, branch_rank, (double *)L11,
+    return ql_toeplitz_host(false, 0, l, u, (const double *)a, (const double *)lambda, n, branch_rank, (double *)L11,
                             (double *)tail_opt, status, ngpus);
 }
 
 int ila_ql_toeplitz_l11_f64(int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank,
                             double *L11, double *tail_opt, int32_t *status, int ngpus)
 {
-    return ql_toeplitz_host(true, l, u, a, lambda, n, branch_rank, L11, tail_opt, status, ngpus);
+    return ql_toeplitz_host(true, 0, l, u, a, lambda, n, branch_rank, L11, tail_opt, status, ngpus);
+}
+
+int ila_ql_toeplitz_l11re_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank,
+                              double *L11re, uint8_t *status8_opt, int ngpus)
+{
+    return ql_toeplitz_host(false, 1, l, u, (const double *)a, (const double *)lambda, n, branch_rank, L11re, nullptr,
+                            status8_opt, ngpus);
+}
+
+int ila_ql_toeplitz_l11re_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d_lambda, int64_t n, int branch_rank,
+                                  double *d_L11re, uint8_t *d_status8_opt, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    if (n < 0 || !a || (n > 0 && (!d_lambda || !d_L11re))) return set_error(ILA_ERR_ARG, "ql_toeplitz_l11re: null pointer / negative n");
+    return launch_ql_toeplitz_l11re(l, u, (const double *)a, branch_rank, (const double *)d_lambda, n, d_L11re, d_status8_opt,
+                                    (cudaStream_t)stream);
+}
+
+int ila_set_host_chunking(int64_t min_chunk_shifts, int divisor)
+{
+    if (min_chunk_shifts < 0 || divisor < 0) return set_error(ILA_ERR_ARG, "host chunking: arguments must be >= 0 (0 = default)");
+    g_chunk_min.store(min_chunk_shifts);
+    g_chunk_div.store(divisor);
+    return 0;
+}
+
+int ila_set_host_copy_mode(int mode)
+{
+    if (mode < 0 || mode > 2) return set_error(ILA_ERR_ARG, "host copy mode must be 0 (auto), 1 (direct) or 2 (staged)");
+    g_host_copy_mode.store(mode);
+    return 0;
+}
+
+/* pinned host memory for callers that want the direct (zero-staging) path */
+int ila_host_alloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) return set_error(ILA_ERR_ARG, "host_alloc: bad arguments");
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    ILA_CUDA_CHECK(cudaHostAlloc(ptr, bytes > 0 ? (size_t)bytes : 8, cudaHostAllocPortable));
+    return 0;
+}
+int ila_host_free(void *ptr)
+{
+    if (ptr) ILA_CUDA_CHECK(cudaFreeHost(ptr));
+    return 0;
+}
+int ila_host_register(void *ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return set_error(ILA_ERR_ARG, "host_register: bad arguments");
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    ILA_CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return 0;
+}
+int ila_host_unregister(void *ptr)
+{
+    if (ptr) ILA_CUDA_CHECK(cudaHostUnregister(ptr));
+    return 0;
 }
 
 int ila_ql_toeplitz_l11_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d_lambda, int64_t n, int branch_rank,
@@ -325,6 +646,7 @@ int ila_ql_toeplitz_absl11_grid_c64(int l, int u, const ila_c64 *a, const double
     if (rc) return rc;
     if ((int64_t)nx * ny == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > ny) G = (int)ny;
     const int64_t per = (ny + G - 1) / G;           // contiguous row slabs per device
     for (int d = 0; d < G; d++) {
@@ -356,6 +678,7 @@ int ila_ql_toeplitz_absl11_grid_c64(int l, int u, const ila_c64 *a, const double
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         for (int i = 0; i < kPipe; i++) ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].pipe[i]));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -391,6 +714,7 @@ static int ql_solve_host(bool real_path, int l, int u, const double *a, const do
     if ((rc = resolve_ngpus(ngpus, &G))) return rc;
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     const int w = real_path ? 1 : 2;
     if (G > n) G = (int)n;
     const int64_t per = (n + G - 1) / G;
@@ -419,6 +743,7 @@ static int ql_solve_host(bool real_path, int l, int u, const double *a, const do
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -459,6 +784,7 @@ static int ql_pert_host(bool real_path, int l, int u, int p, const double *head,
     if (rc) return rc;
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     const int w = real_path ? 1 : 2;
     const int m = l + 2, tl = 2 * m + 2;
     if (G > n) G = (int)n;
@@ -494,6 +820,7 @@ static int ql_pert_host(bool real_path, int l, int u, int p, const double *head,
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -539,6 +866,7 @@ int ila_revchol_tridiag_f64(int64_t batch, const double *ga, const double *gb, c
     if (rc) return rc;
     if (batch == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int64_t per = (batch + G - 1) / G;
     for (int d = 0; d < G; d++) {
@@ -579,6 +907,7 @@ int ila_revchol_tridiag_f64(int64_t batch, const double *ga, const double *gb, c
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -618,6 +947,7 @@ int ila_triconj_bands_f64(int nbands, int64_t batch, int64_t n, const double *U,
     if (rc) return rc;
     if (batch == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int64_t per = (batch + G - 1) / G;
     for (int d = 0; d < G; d++) {
@@ -644,6 +974,7 @@ int ila_triconj_bands_f64(int nbands, int64_t batch, int64_t n, const double *U,
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -657,6 +988,7 @@ int ila_biconj_bands_f64(int upper, int64_t batch, int64_t n, const double *U, c
     if (rc) return rc;
     if (batch == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int64_t per = (batch + G - 1) / G;
     for (int d = 0; d < G; d++) {
@@ -683,6 +1015,7 @@ int ila_biconj_bands_f64(int upper, int64_t batch, int64_t n, const double *U, c
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -736,6 +1069,7 @@ int ila_qr_blockbanded_solve_f64(int64_t batch, const double *alpha, const doubl
     if (rc) return rc;
     if (batch == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int64_t per = (batch + G - 1) / G;
     const int64_t wstride = (int64_t)(maxblocks - 1) * maxblocks * (maxblocks + 1);
@@ -784,6 +1118,7 @@ int ila_qr_blockbanded_solve_f64(int64_t batch, const double *alpha, const doubl
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -803,6 +1138,7 @@ int ila_qr_almostbanded_solve_f64(int lD, int uD, int r, int64_t batch, const do
     if (rc) return rc;
     if (batch == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int nd = lD + uD + 1;
     const int64_t per = (batch + G - 1) / G, wstride = ncap * (int64_t)(nd + r + 1);
@@ -841,6 +1177,7 @@ int ila_qr_almostbanded_solve_f64(int lD, int uD, int r, int64_t batch, const do
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -864,6 +1201,7 @@ static int fsql_host(int l, int u, int64_t batch, const T *g, const T *shift, in
     if (rc) return rc;
     if (batch == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int nd = l + u + 1;
     const int64_t per = (batch + G - 1) / G;
@@ -901,6 +1239,7 @@ static int fsql_host(int l, int u, int64_t batch, const T *g, const T *shift, in
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -972,6 +1311,7 @@ static int blocktri_host(int n, const T *c, const T *a, const T *b, int n_dl, co
     if ((rc = resolve_ngpus(ngpus, &G))) return rc;
     if (batch == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int64_t per = (batch + G - 1) / G;
     for (int d = 0; d < G; d++) {
@@ -998,6 +1338,7 @@ static int blocktri_host(int n, const T *c, const T *a, const T *b, int n_dl, co
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -1038,6 +1379,13 @@ int ila_ql_blocktri_l11_c64(int n, const ila_c64 *c, const ila_c64 *a, const ila
     return blocktri_host<cplx>(n, (const cplx *)c, (const cplx *)a, (const cplx *)b, n_dl, (const cplx *)dl_head, n_d,
                                (const cplx *)d_head, n_du, (const cplx *)du_head, (const cplx *)energy, batch, atol, maxit,
                                (cplx *)L11, iters, status, ngpus);
+}
+
+int ila_ql_set_max_sweeps(int fp64_sweeps, int scout_sweeps)
+{
+    if (fp64_sweeps < 0 || scout_sweeps < 0) return set_error(ILA_ERR_ARG, "sweep limits must be >= 0 (0 = default)");
+    tz_set_max_sweeps(fp64_sweeps, scout_sweeps);
+    return 0;
 }
 
 int ila_ql_set_shifts_per_thread(int spt)
@@ -1147,6 +1495,7 @@ static int banded_solve_host(int kind, int l, int u, int64_t batch, const double
     if (rc) return rc;
     if (batch == 0) { xoff[0] = 0; return 0; }
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int nd = l + u + 1, LD = 2 * l + u + 1;
     const bool refl = kind == 0 && (factors_opt || tau_opt);
@@ -1247,7 +1596,8 @@ static int banded_solve_host(int kind, int l, int u, int64_t batch, const double
     }
     xoff[batch] = acc;
     if (acc > xcap || !x) {
-        ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+        guard.done = true;
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
         return set_error(ILA_ERR_CAPACITY, "qr_banded_solve: x capacity too small; xoff[batch] holds the required number of doubles");
     }
     // phase 2
@@ -1292,6 +1642,7 @@ static int banded_solve_host(int kind, int l, int u, int64_t batch, const double
         ILA_CUDA_CHECK(cudaSetDevice(phys(d, G)));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[phys(d, G)].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -1320,6 +1671,7 @@ int ila_qr_banded_solve_c64(int l, int u, int64_t batch, const ila_c64 *p, const
     if (rc) return rc;
     if (batch == 0) { xoff[0] = 0; return 0; }
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int nd = l + u + 1, REC = qr_c64_record_chunks(l, u);
     const int64_t per = (batch + G - 1) / G;
@@ -1399,7 +1751,8 @@ int ila_qr_banded_solve_c64(int l, int u, int64_t batch, const ila_c64 *p, const
     }
     xoff[batch] = acc;
     if (acc > xcap || !x) {
-        ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+        guard.done = true;
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
         return set_error(ILA_ERR_CAPACITY, "qr_banded_solve_c64: x capacity too small; xoff[batch] holds the required number of scalars");
     }
     for (int d = 0; d < G; d++) {
@@ -1418,6 +1771,7 @@ int ila_qr_banded_solve_c64(int l, int u, int64_t batch, const ila_c64 *p, const
         ILA_CUDA_CHECK(cudaSetDevice(phys(d, G)));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[phys(d, G)].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }
@@ -1450,6 +1804,7 @@ int ila_chol_triconj_f64(int u, int64_t batch, const double *p, const double *q,
     if (rc) return rc;
     if (batch == 0) return 0;
     std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
     if (G > batch) G = (int)batch;
     const int nd = u + 1;
     const int64_t cg = (n + 4) / 2, ncap = 2 * cg + 3 * u + 2;
@@ -1507,6 +1862,7 @@ int ila_chol_triconj_f64(int u, int64_t batch, const double *p, const double *q,
         ILA_CUDA_CHECK(cudaSetDevice(pd));
         ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
     }
+    guard.done = true;
     ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
     return 0;
 }

@@ -13,7 +13,10 @@
 // "QL exists" <=> |w| >= 1), finds all roots simultaneously with a Gauss–Seidel Aberth–Ehrlich iteration
 // (cubic convergence, one complex division per root per sweep), selects the branch, and recovers the
 // eigenvector in closed form from the companion structure (V_1 = 1, V_{i+1} = g_i - w V_i).
-// Everything is FP64/ComplexF64 on the CUDA cores; 36 B of HBM traffic per shift, so the kernel is FP64-pipe bound.
+// The simultaneous iteration runs as an FP32 "scout" on the FP32 pipe (consecutive shifts of a thread track the roots
+// with one Durand–Kerner sweep); only the selected root is refined in FP64 (Newton + chord step) and the epilogue is
+// FP64.  16 B in and 8-20 B out per shift against ~900 instructions: the kernel is issue-slot bound, not HBM bound
+// (profiles/).  A root finder that exhausts its sweeps reports ILA_NOT_CONVERGED, never a silent value.
 #include "ila_common.cuh"
 
 namespace ila {
@@ -23,8 +26,14 @@ constexpr int kAberthMaxIt = 48;
 // FP32 scout: a cold start converges in 6-8 sweeps (14 at most on the C3 grid); in rare regions of the λ plane the FP32 iteration
 // from the circle start never settles although the FP64 one does in 8 sweeps — give up early and let the FP64 path take over
 constexpr int kScoutMaxIt = 16;
-static int g_tz_spt = 0;   // 0 = automatic; set by ila_ql_set_shifts_per_thread (1 = every shift starts cold)
-void tz_set_spt(int v) { g_tz_spt = v; }
+static std::atomic<int> g_tz_spt{0};   // 0 = automatic; set by ila_ql_set_shifts_per_thread (1 = every shift starts cold)
+static std::atomic<int> g_tz_max_it{0}, g_tz_scout_max_it{0};   // 0 = kAberthMaxIt / kScoutMaxIt (ila_ql_set_max_sweeps: test hook)
+void tz_set_spt(int v) { g_tz_spt.store(v); }
+void tz_set_max_sweeps(int fp64_sweeps, int scout_sweeps)
+{
+    g_tz_max_it.store(fp64_sweeps > 0 ? fp64_sweeps : 0);
+    g_tz_scout_max_it.store(scout_sweeps > 0 ? scout_sweeps : 0);
+}
 
 
 // branch-free reciprocal for the root-finder's corrections (MUFU seed + two Newton steps, ~1 ulp): an iteration that
@@ -107,6 +116,8 @@ struct TzParams {
     float cmax2f;      // max_{k >= 2} |cf0_k|^2 (the shift-independent coefficients)
     double beta2;      // |β|^2
     int branch_rank;
+    int max_it, scout_max_it;   // sweep limits of the FP64 / FP32 simultaneous iterations
+    int out_mode;      // complex-eltype L11-only output: 0 = ComplexF64 + int32 status, 1 = Float64 (NaN payload = status) + optional uint8 status
 };
 
 // lim2: square of 8x a Cauchy-type bound on the root moduli (1 + max|cf_k|); an iterate beyond it is pulled back
@@ -327,6 +338,7 @@ struct TzGrid {
     const double *gx, *gy;
     int nx;
     double *absout;
+    int out_mode;   // array form, complex eltype, L11 only: 1 = Float64 L11 (+ optional uint8 status), see TzParams
 };
 
 constexpr int kSolveMaxB = 16;
@@ -469,7 +481,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
 #define K3_DBG(x)
 #endif
     if (scout != 0) {
-        for (int it = 0; it < kScoutMaxIt; it++) {
+        for (int it = 0; it < P.scout_max_it; it++) {
             scout = aberth_sweep_f32<N>(cff, wf, lim2);
             K3_DBG(dbg_f32++;)
             if (scout == 0) break;
@@ -491,6 +503,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     double gap = (double)gapf;
     bool full = (scout != 0) || (gap < 1e-5);
     bool newton_done = false;
+    bool lost = false;           // the FP64 simultaneous iteration used up its sweeps without settling
     if (!full) {
         // ---- FP64 Newton on the selected root only (~1e-6 -> 1e-12 -> rounding level); accepted when the last
         //      correction applied is below 1e-10 |w| (the iterate is then exact to rounding)
@@ -547,10 +560,13 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
             for (int j = 0; j < N; j++) w[j] = c + (1.6 * rad) * (P.unit[j] * rot);
         }
         K3_DBG(dbg_flags |= 2 | (scout == 2 ? 4 : 0);)
-        for (int it = 0; it < kAberthMaxIt; it++) {
+        int rc64 = 2;
+        for (int it = 0; it < P.max_it; it++) {
             K3_DBG(dbg_f64++;)
-            if (aberth_sweep<N>(cf, w) == 0) break;
+            rc64 = aberth_sweep<N>(cf, w);
+            if (rc64 == 0) break;
         }
+        lost = (rc64 != 0);
         jsel = select_root<N>(w, P.branch_rank, gap);
         ws = w[0];
 #pragma unroll
@@ -578,6 +594,17 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
             if (abs2(corr) < 1e-6 * abs2(ws)) ws = ws - corr;
         }
     }
+    if (lost) {
+        // sweeps exhausted (infqltoeplitz.jl has no counterpart: LAPACK's QR iteration reports info > 0 and `eigen` throws):
+        // accept the root only if it is one to rounding — backward error |P(w)| <= 1e-13 sum_k |cf_k||w|^(N-k), the
+        // criterion that also holds at multiple roots, where the corrections stay large — else ILA_NOT_CONVERGED.
+        const cplx pv = horner1<N>(cf, ws);
+        const double aw = sqrt(abs2(ws));
+        double bnd = 1.0;
+#pragma unroll
+        for (int k = 1; k <= N; k++) bnd = fma(bnd, aw, sqrt(abs2(cf[k])));
+        if (!(abs2(pv) <= 1e-26 * bnd * bnd)) st = ILA_NOT_CONVERGED;
+    }
 
     // μ = β w ; n2 = |μ|^2 ; existence test n2 >= |β|^2 (infqltoeplitz.jl:13,23)
     const cplx beta = P.a[N];
@@ -601,7 +628,13 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
         const double ay = fast_sqrt(abs2(y));
         const double qn = __longlong_as_double(0x7ff8000000000000LL);
         if (G.absout) {
-            G.absout[idx] = (st == ILA_OK) ? ay : -1.0;
+            G.absout[idx] = (st == ILA_OK) ? ay : (st == ILA_NOT_CONVERGED ? qn : -1.0);
+        } else if (P.out_mode == 1) {
+            // L[1,1] of a complex-eltype factorization is real (-ν of the k = 1 reflector): 8 B out; the status rides in
+            // the NaN payload (low mantissa bits) and, when asked for, in a byte array
+            const double l11 = (c_abs == 0.0) ? copysign(ay, y.re) : -ay;
+            L11[idx] = (st == ILA_OK) ? l11 : __longlong_as_double(0x7ff8000000000000LL | (long long)st);
+            if (status) reinterpret_cast<uint8_t *>(status)[idx] = (uint8_t)st;
         } else {
             status[idx] = st;
             const double l11 = (c_abs == 0.0) ? copysign(ay, y.re) : -ay;
@@ -611,11 +644,19 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
         continue;
     }
 
-    // eigenvector of the companion matrix in closed form (V_1 = 1): V_{i+1} = g_i - w V_i
+    // eigenvector of the companion matrix in closed form (V_1 = 1).  The rows of (C/β) V = w V read V_{i+1} = g_i - w V_i
+    // (i < N) and V_N = g_N / w.  Run forward, that recurrence multiplies rounding errors by |w| per step (|w|^(N-1):
+    // 1e-6 relative for N = 8, |w| = 36) — so it is run BACKWARD from the last row, V_i = (g_i - V_{i+1}) / w, which damps
+    // them by 1/|w| per step and is stable exactly where a factorization exists (|w| >= 1).
     cplx V[N];
     V[0] = mk(1.0, 0.0);
+    {
+        const double w2 = abs2(ws);
+        const cplx winv = (w2 > 0.0) ? (1.0 / w2) * conj(ws) : mk(0.0, 0.0);
+        V[N - 1] = g[N] * winv;
 #pragma unroll
-    for (int i = 1; i < N; i++) V[i] = g[i] - ws * V[i - 1];
+        for (int i = N - 2; i >= 1; i--) V[i] = (g[i + 1] - V[i + 1]) * winv;
+    }
 
     // de = c_sgn c_abs V[end:-1:1]; with V_1 = 1 the reference's c_sgn is exactly -1 (complex branch,
     // infqltoeplitz.jl:24-26, since V_1 a_{m-1} - V_2 a_m = μ V_1).  Real branch: see below.
@@ -694,7 +735,7 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
         tau1 = tau2 = mk(qnan, qnan);
     }
     if (G.absout) {
-        G.absout[idx] = (st == ILA_OK) ? sqrt(abs2(X1[N - 1])) : -1.0;
+        G.absout[idx] = (st == ILA_OK) ? sqrt(abs2(X1[N - 1])) : (st == ILA_NOT_CONVERGED ? qnan : -1.0);
         continue;
     }
     status[idx] = st;
@@ -747,6 +788,9 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     P.ginv = cplx{beta.re / b2, -beta.im / b2};
     P.beta2 = b2;
     P.branch_rank = branch_rank;
+    P.max_it = g_tz_max_it.load() > 0 ? g_tz_max_it.load() : kAberthMaxIt;
+    P.scout_max_it = g_tz_scout_max_it.load() > 0 ? g_tz_scout_max_it.load() : kScoutMaxIt;
+    P.out_mode = G.out_mode;
     for (int k = 0; k <= N; k++) {
         // cf0_k = (-1)^k a_{m-k}/β with a_{m-k} = a_rev[N-k]; cf0_0 = 1
         cplx v = (k == 0) ? cplx{1.0, 0.0} : cplx{a_rev[N - k].re * P.ginv.re - a_rev[N - k].im * P.ginv.im,
@@ -769,23 +813,33 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     const int threads = 128;
     // shifts per thread: consecutive shifts share a warm start (longer runs amortise the cold start), but the grid
     // should still fill every SM to its resident-block limit: the smallest spt for which the grid is one full wave
-    static int wave_cache[2] = {0, 0};   // resident blocks of this instantiation over the whole GPU (tail / no tail)
+    // resident blocks of this instantiation over the whole GPU, per device (tail / no tail); racing writers store the same value
+    static std::atomic<int> wave_cache[16][2];
     const bool want_tail = d_tail != nullptr || SV.x != nullptr;
-    int wave_blocks = wave_cache[want_tail ? 1 : 0];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int dslot = (dev >= 0 && dev < 16) ? dev : 0;
+    int wave_blocks = (dev == dslot) ? wave_cache[dslot][want_tail ? 1 : 0].load() : 0;
     if (wave_blocks == 0) {
-        int dev = 0, sms = 148, per_sm = 4;
-        cudaGetDevice(&dev);
+        int sms = 148, per_sm = 4;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (want_tail)
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ql_toeplitz_l11_kernel<N, REAL_PATH, true>, threads, 0);
         else
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ql_toeplitz_l11_kernel<N, REAL_PATH, false>, threads, 0);
         wave_blocks = sms * (per_sm > 0 ? per_sm : 1);
-        wave_cache[want_tail ? 1 : 0] = wave_blocks;
+        if (dev == dslot) wave_cache[dslot][want_tail ? 1 : 0].store(wave_blocks);
     }
-    int spt = (int)((n + (int64_t)wave_blocks * threads - 1) / ((int64_t)wave_blocks * threads));
+    // Run length.  r = n / (threads of one full wave).  A warm shift costs about a quarter of a cold one, so below ~8 waves it
+    // pays to run HALF the resident threads with runs twice as long (measured on B200, 1024-wide grid rows, µs per launch:
+    // 64 Ki shifts 17.4 -> 15.4, 128 Ki 21.5 -> 19.5, 256 Ki 29.7 -> 25.6, 512 Ki 33.8, 1 Mi 52.2 at spt 8, 4 Mi 142 at 16;
+    // profiles/r02_k3_e2e_probe.json); from 8 waves up the run length that makes the grid one full wave is best.
+    const double r = (double)n / ((double)wave_blocks * threads);
+    int spt = (int)ceil(2.0 * r + 0.5);
+    const int full = (int)ceil(r);
+    if (spt > 8 && spt > full) spt = full > 8 ? full : 8;
     while (spt & (spt - 1)) spt &= spt - 1;   // power of two: runs then do not straddle the rows of power-of-two grids
-    if (g_tz_spt > 0) spt = g_tz_spt;
+    if (g_tz_spt.load() > 0) spt = g_tz_spt.load();
     if (spt < 1) spt = 1;
     if (spt > 16) spt = 16;
     const int64_t nthreads = (n + spt - 1) / spt;
@@ -825,7 +879,16 @@ int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int b
                        int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream)
 {
     return launch_ql_toeplitz_ex(real_path, l, u, a_host, branch_rank, d_lambda, n, d_L11, d_tail, d_status, stream,
-                                 TzGrid{nullptr, nullptr, 0, nullptr}, TzSolveArgs{});
+                                 TzGrid{nullptr, nullptr, 0, nullptr, 0}, TzSolveArgs{});
+}
+
+// complex eltype, L11 only, compact output: d_L11re = n doubles (NaN with the status in its payload where status != 0),
+// d_status8 = n bytes or nullptr
+int launch_ql_toeplitz_l11re(int l, int u, const double *a_host, int branch_rank, const double *d_lambda, int64_t n,
+                             double *d_L11re, uint8_t *d_status8, cudaStream_t stream)
+{
+    return launch_ql_toeplitz_ex(false, l, u, a_host, branch_rank, d_lambda, n, d_L11re, nullptr,
+                                 reinterpret_cast<int32_t *>(d_status8), stream, TzGrid{nullptr, nullptr, 0, nullptr, 1}, TzSolveArgs{});
 }
 
 // grid mode: |L11| (or -1) for λ = gx[j] + i*gy[k], idx = k*nx + j, k < ny
@@ -833,7 +896,7 @@ int launch_ql_toeplitz_grid(int l, int u, const double *a_host, int branch_rank,
                             const double *d_gy, int64_t ny, double *d_absout, cudaStream_t stream)
 {
     return launch_ql_toeplitz_ex(false, l, u, a_host, branch_rank, nullptr, (int64_t)nx * ny, nullptr, nullptr, nullptr,
-                                 stream, TzGrid{d_gx, d_gy, nx, d_absout}, TzSolveArgs{});
+                                 stream, TzGrid{d_gx, d_gy, nx, d_absout, 0}, TzSolveArgs{});
 }
 
 int launch_ql_toeplitz_ex(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
@@ -1150,7 +1213,7 @@ int launch_ql_toeplitz_solve_fused(bool real_path, int l, int u, const double *a
     SV.nout = nout;
     SV.x = d_x;
     return launch_ql_toeplitz_ex(real_path, l, u, a_host, branch_rank, d_lambda, n, d_L11, nullptr, d_status, stream,
-                                 TzGrid{nullptr, nullptr, 0, nullptr}, SV);
+                                 TzGrid{nullptr, nullptr, 0, nullptr, 0}, SV);
 }
 
 // b_host: nb scalars (real or interleaved complex, like the symbol); d_tail: the `tail` output of launch_ql_toeplitz

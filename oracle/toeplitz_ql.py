@@ -12,8 +12,13 @@ Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline legs may 
 Parity status: pinned by the reference's known answers for this path
 (test/test_reduceql.jl:41-45 constants, test/test_infql.jl:12-67 reconstruction identities,
 test/test_infql.jl:147-153 `(Q'b)[1]`) — see tests/test_oracle_toeplitz.py.
-The *sign* of the real-typed path follows LAPACK's eigenvector sign (infqltoeplitz.jl:14-15) and is
-therefore "parity unpinned" beyond the cases the reference tests hold.
+The *sign* of the real-typed path follows LAPACK's eigenvector sign (infqltoeplitz.jl:14-15): the reference returns
+either (Q, L) or (-Q, -L) depending on which sign `dgeev` hands back for V[:, j].  `sign_rule="lapack"` (default)
+restates that literally (numpy's LAPACK standing in for Julia's).  `sign_rule="householder"` picks, of the two, the
+factorization for which `ql_X!` needs no sign flip — which is the limit of the finite-section Householder QL, i.e. the
+L the reference's own tests assert (`L[1:10,1:10] ≈ ql(A[1:n,1:n]).L[1:10,1:10]`, test/test_infql.jl:14-17); the two
+rules agree in every case those tests hold, and tests/test_oracle_toeplitz.py checks the householder rule against
+dense finite sections on random real symbols.  The C ABI's `_f64` entries are specified with the householder rule.
 """
 from __future__ import annotations
 
@@ -142,8 +147,9 @@ def _reflector_apply(x, tau, A):
         A[i] = A[i] - x[i][None] * vA
 
 
-def ql_X(X):
-    """`ql_X!` (infqltoeplitz.jl:31-39) on a batch X[..., 2, m]; returns (X_factored, tau[..., 2]).
+def ql_X(X, return_flip=False):
+    """`ql_X!` (infqltoeplitz.jl:31-39) on a batch X[..., 2, m]; returns (X_factored, tau[..., 2]) (+ the mask of entries
+    whose sign normalisation (:34-37) fired, with return_flip).
 
     `ql!` of a 2×m matrix (MatrixFactorizations; the loop is restated in src/infql.jl:10-22 and
     examples/jacobi.jl:61-74): k = 2: reflector on (X[2,m], X[1,m]) applied to columns 1..m-1;
@@ -176,11 +182,16 @@ def ql_X(X):
     flip = s != np.sign(X[..., 0, m - 2].real)
     tau[..., 0] = np.where(flip, 2 - tau[..., 0], tau[..., 0])
     X[..., 0, :m - 1] = np.where(flip[..., None], -X[..., 0, :m - 1], X[..., 0, :m - 1])
+    if return_flip:
+        return X, tau, flip
     return X, tau
 
 
-def ql_toeplitz_tail(a, branch_rank=1, real_path=None):
+def ql_toeplitz_tail(a, branch_rank=1, real_path=None, sign_rule="lapack"):
     """`ql_hessenberg(::InfToeplitz)` data (infqltoeplitz.jl:56-65) for a batch of symbols.
+
+    sign_rule (real-typed path only, see the module docstring): "lapack" = the eigenvector sign LAPACK returns,
+    "householder" = the sign for which ql_X! does not flip (= the finite-section Householder QL limit).
 
     a: (..., m) = reverse(A.data.args[1]) = [a_{-l}, ..., a_0, a_{+1}].
     Returns dict with L11 (...), X (..., 2, m) factored, tau (..., 2), de, status, mu.
@@ -196,13 +207,23 @@ def ql_toeplitz_tail(a, branch_rank=1, real_path=None):
     X = np.zeros(a.shape[:-1] + (2, m), dtype=dt)
     X[..., 0, :] = a
     X[..., 1, 1:] = de
+    if real_path is None:
+        real_path = not np.iscomplexobj(a)
+    if sign_rule not in ("lapack", "householder"):
+        raise ValueError(sign_rule)
     with np.errstate(invalid="ignore", divide="ignore"):
-        Xf, tau = ql_X(X)
+        Xf, tau, flip = ql_X(X, return_flip=True)
+        if real_path and sign_rule == "householder" and np.any(flip):
+            # V -> -V: de -> -de; row 2 of X changes sign, s changes sign, and the normalisation no longer fires
+            de = np.where(np.asarray(flip)[..., None], -de, de)
+            X[..., 1, 1:] = de
+            Xf, tau, flip2 = ql_X(X, return_flip=True)
+            assert not np.any(flip2 & (status == 0))
     L11 = Xf[..., 0, m - 2]
     return dict(L11=L11, X=Xf, tau=tau, de=de, status=status, mu=mu)
 
 
-def ql_toeplitz_l11(coeffs_data_column, lambdas, branch_rank=1, real_path=None):
+def ql_toeplitz_l11(coeffs_data_column, lambdas, branch_rank=1, real_path=None, sign_rule="lapack"):
     """L[1,1] of ql(A - lambda*I) for the pure Toeplitz A whose BandedMatrices data column is
     `coeffs_data_column` = [a_{+u}, ..., a_0, ..., a_{-l}] with u == 1 (infqltoeplitz.jl:56-65, 191).
 
@@ -215,7 +236,7 @@ def ql_toeplitz_l11(coeffs_data_column, lambdas, branch_rank=1, real_path=None):
     a[...] = col[::-1]
     m = col.shape[0]
     a[..., m - 2] = col[1] - lambdas          # diagonal coefficient a_0 - lambda
-    out = ql_toeplitz_tail(a, branch_rank, real_path)
+    out = ql_toeplitz_tail(a, branch_rank, real_path, sign_rule)
     return out["L11"], out["status"]
 
 

@@ -117,6 +117,23 @@ def test_c2_full_size_properties(ila):
         assert np.max(np.abs(x - ref)) <= 4 * z * np.finfo(float).eps * np.max(np.abs(ref)) + 1e-13
 
 
+def test_c2_full_batch_bit_exact_vs_oracle(ila):
+    """BASELINE config C2 at full size: all 4096 solves (z up to 1e5, 2.2e8 columns) against the C oracle BIT for bit, and
+    the κ-aware comparison with the __float128 oracle (back-substitution amplifies rounding ∝ z)."""
+    import json, os
+    import parity_full
+    rep = parity_full.c2_full_report(ila)
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        json.dump(rep, open(os.path.join(root, "gpurun_out", "r02_parity_c2_full.json"), "w"), indent=1)
+    except OSError:
+        pass
+    assert rep["all_converged"], rep
+    assert rep["bit_exact"], rep
+    assert rep["max_rel_err_over_z_eps"] <= 4.0, rep
+
+
 def test_output_paths_identical(ila):
     """The back-substitution delivers x either straight into the ragged output (small batches) or through the interleaved
     stream + compaction (large batches): both must give the same bits, including the zero region up to datasize."""

@@ -120,3 +120,49 @@ def test_bullhead_finite_section_and_probe_values():
             A += np.diag(np.full(n - abs(d), v, dtype=complex), d)
         F, _ = tq.dense_ql(A)
         assert np.isclose(abs(F[0, 0]), abs(l11), rtol=1e-12)
+
+
+def test_real_path_householder_sign_rule_is_the_finite_section_limit():
+    """The C ABI's `_f64` sign rule (oracle sign_rule="householder").  Upstream the sign of the whole real-typed
+    factorization is whatever LAPACK's dgeev returns for the eigenvector (infqltoeplitz.jl:14-15) — (Q, L) or (-Q, -L).
+    Independent evidence for the rule: on random real Hessenberg Toeplitz symbols the householder-rule L equals the dense
+    finite-section Householder QL's L (sign included — what test/test_infql.jl:14-17 asserts), and the literal-LAPACK
+    outcome is always one of the two members of the pair."""
+    rng = np.random.default_rng(7)
+    checked = lapack_other = 0
+    for trial in range(120):
+        l = int(rng.integers(1, 5))
+        col = rng.normal(size=l + 2)
+        if abs(col[0]) < 0.3:
+            col[0] = 1.0
+        a = col[::-1].copy()
+        a[-2] -= rng.normal() * 4
+        o = tq.ql_toeplitz_tail(a, sign_rule="householder")
+        ol = tq.ql_toeplitz_tail(a, sign_rule="lapack")
+        assert o["status"] == ol["status"]
+        if o["status"] != 0:
+            continue
+        m = len(a)
+        def section(n):
+            A = np.zeros((n, n))
+            for i in range(n):
+                for j in range(max(0, i - l), min(n, i + 2)):
+                    A[i, j] = a[(j - i) + m - 2]
+            return tq.dense_ql(A)[0]
+        F1, F2 = section(120), section(170)
+        if abs(F1[0, 0] - F2[0, 0]) > 1e-9 * abs(F2[0, 0]):
+            continue                                                     # finite section not converged yet: skip
+        checked += 1
+        X = o["X"]
+        first_col = np.concatenate([[X[0, m - 2]], X[1, m - 2::-1]])     # [X[1,m-1]; X[2,m-1:-1:1]]
+        tail_col = X[1, ::-1]                                            # X[2,m:-1:1]
+        assert np.allclose(F2[:m, 0], first_col, rtol=1e-8, atol=1e-10)
+        assert np.allclose(F2[3:3 + m, 3], tail_col, rtol=1e-8, atol=1e-10)
+        same = np.allclose(ol["X"], X, rtol=1e-12, atol=1e-14)
+        # (Q,L) -> (-Q,-L): rows 1 (up to column m-1) and 2 of X negated, v = X[1,m] negated, tau1 -> 2 - tau1
+        other = np.allclose(ol["X"], -X, rtol=1e-12, atol=1e-14) and np.isclose(ol["tau"][0], 2 - o["tau"][0]) and \
+            np.isclose(ol["tau"][1], o["tau"][1])
+        assert same or other
+        lapack_other += int(other and not same)
+    assert checked >= 60
+    assert lapack_other > 0          # the ambiguity is real: LAPACK's sign is not the finite-section one everywhere
