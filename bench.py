@@ -237,6 +237,7 @@ def run_ours(args, rank, local_rank, world):
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")     # host-side barrier: a rank parked in it leaves its GPU idle
 
     def barrier():
         if dist is not None:
@@ -439,6 +440,8 @@ def run_ours(args, rank, local_rank, world):
     one_proc = None
     ndev_visible = lib.ila_device_count()
     if world > 1 and ndev_visible >= world:
+        # the other ranks wait in a gloo (CPU) barrier: an NCCL barrier would park a spinning kernel on their GPUs and rank 0's
+        # second context on those GPUs would be time-sliced against it
         barrier()
         if rank == 0:
             full = grid_shard(0, 1)
@@ -452,6 +455,7 @@ def run_ours(args, rank, local_rank, world):
             one_proc = {"value": full.size / (ms_full * 1e-3), "unit": "lambda-points/s", "ms_per_step": ms_full,
                         "api": f"ONE process, ila_ql_toeplitz_l11re_c64(..., ngpus={world}) on the whole 1024x1024 grid, pinned host buffers"}
             del f_lam, f_L, f_st
+        dist.barrier(group=cpu_group)
         barrier()
 
     # ---------------- large strong-scaling case: ONE 8192 x 8192 grid over the same window ----------------

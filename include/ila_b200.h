@@ -176,6 +176,32 @@ int ila_qr_banded_factor_f64_dev(int l, int u, int64_t batch, const double *d_p,
                                  double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
                                  const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
                                  int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int want_reflectors, void *stream);
+/* Resumable factorization state — the reference's AdaptiveQRData (src/infqr.jl:2-13): `ncols` plus the trailing columns
+ * that already carry the reflector updates, from which partialqr!(F, n) continues (:32-48; test/test_infqr.jl:19-28).
+ * Here: d_state, ila_qr_banded_state_doubles(l,u) doubles per instance (the register window, the Q'b window, counters).
+ *   ila_qr_banded_factor_resume_f64_dev  = ila_qr_banded_factor_f64_dev that, when the column limit `ncap` is reached,
+ *       keeps what it has: status 3, ncols = nswept = columns finished, state saved.  Calling it again with a larger
+ *       ncap (work buffer laid out for the larger capacity from the start: ila_qr_banded_work_layout) and resume = 1
+ *       continues from there; instances that had finished are left untouched.  Two calls give the same bits as one.
+ *   ila_qr_banded_partialqr_f64_dev      = partialqr!(F, n): factorize through column n (no right-hand side, no
+ *       convergence test; reflectors and tau are stored), resume = 1 continues from the state of an earlier call.  The
+ *       window left in d_state, W[j][i] = (Q_n' A)[n+i, n+j], is the reference's "extra columns have been modified".
+ *   ila_qr_banded_export_f64_dev         = records -> BandedMatrices band storage ((2l+u+1) x ncols, bandwidths (l, l+u)),
+ *       tau, Q'b; ragged at d_xoff like the host entry's factors_opt. */
+int ila_qr_banded_state_doubles(int l, int u);
+int ila_qr_banded_factor_resume_f64_dev(int l, int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                        const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
+                                        double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
+                                        const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
+                                        int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int want_reflectors,
+                                        double *d_state, int resume, void *stream);
+int ila_qr_banded_partialqr_f64_dev(int l, int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                    const double *d_shift, int hp, const double *d_head, int64_t n, int colgrowth,
+                                    const int64_t *d_gbase, void *d_work, double *d_state, int resume, int64_t *d_ncols,
+                                    int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, void *stream);
+int ila_qr_banded_export_f64_dev(int l, int u, int want_reflectors, int64_t batch, const int64_t *d_gbase, const void *d_work,
+                                 const int64_t *d_ncols, const int64_t *d_nswept, const int64_t *d_xoff, double *d_factors,
+                                 double *d_tau, double *d_qtb, void *stream);
 int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *d_gbase, const void *d_work, double *d_xi,
                                     const int64_t *d_ncols, const int64_t *d_nswept, const int64_t *d_xoff,
                                     const int32_t *d_status, double *d_x, int64_t xcap, int want_reflectors, void *stream);
@@ -199,6 +225,17 @@ int ila_chol_banded_factor_f64_dev(int u, int64_t batch, const double *d_p, cons
                                    double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
                                    const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
                                    int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int full_sweep, void *stream);
+
+/* Resumable form — AdaptiveCholeskyFactors.ncols and the Schur-updated next block partialcholesky! continues from
+ * (src/infcholesky.jl:42-59) plus the forward-substitution carry (:126-128): d_state holds
+ * ila_chol_banded_state_doubles(u) doubles per instance; semantics as ila_qr_banded_factor_resume_f64_dev. */
+int ila_chol_banded_state_doubles(int u);
+int ila_chol_banded_factor_resume_f64_dev(int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                          const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
+                                          double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
+                                          const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
+                                          int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int full_sweep,
+                                          double *d_state, int resume, void *stream);
 
 /* Complex eltype of the adaptive QR solve (e.g. a real operator minus a complex shift: the resolvent (A - λI) \ b by QR).
  * p, q, shift, head, b and x are complex; r (the per-diagonal denominators) is real; everything else as in

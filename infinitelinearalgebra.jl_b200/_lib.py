@@ -106,6 +106,17 @@ SIGNATURES = {
     "ila_chol_banded_factor_f64_dev": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp,
                                                  C.c_double, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                                  _vp, C.c_int, _vp]),
+    "ila_qr_banded_state_doubles": (C.c_int, [C.c_int, C.c_int]),
+    "ila_chol_banded_state_doubles": (C.c_int, [C.c_int]),
+    "ila_qr_banded_factor_resume_f64_dev": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int,
+                                                      _vp, C.c_double, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                      _vp, C.c_int, _vp, C.c_int, _vp]),
+    "ila_chol_banded_factor_resume_f64_dev": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp,
+                                                        C.c_double, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                        _vp, C.c_int, _vp, C.c_int, _vp]),
+    "ila_qr_banded_partialqr_f64_dev": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int64,
+                                                  C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "ila_qr_banded_export_f64_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ila_qr_banded_work_layout": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
     "ila_qr_banded_factor_f64_dev": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int,
                                                _vp, C.c_double, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -580,6 +580,10 @@ class QrBandedPlan:
             xcap = int(caps.sum()) if caps is not None else batch * int(ncap)
         self.xcap = int(xcap)
         self.d_x = torch.empty(self.xcap, dtype=torch.float64, device=dev)
+        # resumable state (the reference's AdaptiveQRData / AdaptiveCholeskyFactors: ncols + the trailing updated columns)
+        sd = lib().ila_chol_banded_state_doubles(u) if kind == "chol" else lib().ila_qr_banded_state_doubles(l, u)
+        self.state_doubles = int(sd)
+        self.d_state = torch.zeros(batch * self.state_doubles, dtype=torch.float64, device=dev)
 
     def _stream(self):
         lib().ila_set_device(self.device.index or 0)
@@ -589,6 +593,68 @@ class QrBandedPlan:
         self.run_factor()
         self.run_backsolve()
         return 4   # kernels launched: forward, scan, back-substitution, compaction
+
+    def run_factor_resumable(self, limit: int, resume: bool):
+        """Adaptive sweep with the column limit `limit` (<= the capacity the workspace was laid out for): an instance that
+        reaches it keeps its finished columns and its state (status 3, ncols = columns done); `resume=True` continues every
+        such instance from there — `partialqr!(F, n)` / `partialcholesky!(F, n)` called again with a larger n
+        (src/infqr.jl:32-48, src/infcholesky.jl:42-59).  Two calls give the same bits as one."""
+        s = self._stream()
+        if self.d_caps is not None:
+            raise ValueError("resumable sweeps use the uniform column limit")
+        if int(limit) > self.ncap:
+            raise ValueError("limit exceeds the capacity the workspace was laid out for")
+        if self.kind == "chol":
+            check(lib().ila_chol_banded_factor_resume_f64_dev(
+                self.u, self.batch, ptr(self.d_p), ptr(self.d_q), ptr(self.d_r), ptr(self.d_shift), self.hp,
+                ptr(self.d_head), self.nb, ptr(self.d_b), self.tol, self.colgrowth, int(limit), None,
+                ptr(self.d_gbase), ptr(self.d_work), ptr(self.d_ncols), ptr(self.d_nconv), ptr(self.d_nswept),
+                ptr(self.d_xoff), ptr(self.d_status), 0, ptr(self.d_state), 1 if resume else 0, s))
+        else:
+            check(lib().ila_qr_banded_factor_resume_f64_dev(
+                self.l, self.u, self.batch, ptr(self.d_p), ptr(self.d_q), ptr(self.d_r), ptr(self.d_shift), self.hp,
+                ptr(self.d_head), self.nb, ptr(self.d_b), self.tol, self.colgrowth, int(limit), None,
+                ptr(self.d_gbase), ptr(self.d_work), ptr(self.d_ncols), ptr(self.d_nconv), ptr(self.d_nswept),
+                ptr(self.d_xoff), ptr(self.d_status), self.refl, ptr(self.d_state), 1 if resume else 0, s))
+        return 2
+
+    def partialqr(self, n: int, resume: bool = False):
+        """`partialqr!(F, n)` (src/infqr.jl:32-48) for every operator of the plan: factorize through column n, reflectors and
+        tau stored in the records; no right-hand side.  `resume=True` continues from the state an earlier call left."""
+        if self.kind != "qr":
+            raise ValueError("partialqr is the QR plan's")
+        if int(n) > self.ncap:
+            raise ValueError("n exceeds the capacity the workspace was laid out for")
+        s = self._stream()
+        self.refl = 1
+        check(lib().ila_qr_banded_partialqr_f64_dev(
+            self.l, self.u, self.batch, ptr(self.d_p), ptr(self.d_q), ptr(self.d_r), ptr(self.d_shift), self.hp,
+            ptr(self.d_head), int(n), self.colgrowth, ptr(self.d_gbase), ptr(self.d_work), ptr(self.d_state),
+            1 if resume else 0, ptr(self.d_ncols), ptr(self.d_nswept), ptr(self.d_xoff), ptr(self.d_status), s))
+        return 2
+
+    def export_factors(self):
+        """Band storage of the factors, tau and Q'b of what has been swept so far (ragged at d_xoff): returns
+        (factors [total x (2l+u+1)], tau [total], qtb [total], xoff [batch+1]) as numpy arrays."""
+        torch = self.torch
+        s = self._stream()
+        xoff = self.d_xoff.cpu().numpy()
+        total = int(xoff[-1])
+        LD = 2 * self.l + self.u + 1
+        d_f = torch.zeros(max(total, 1) * LD, dtype=torch.float64, device=self.device)
+        d_t = torch.zeros(max(total, 1), dtype=torch.float64, device=self.device)
+        d_q = torch.zeros(max(total, 1), dtype=torch.float64, device=self.device)
+        check(lib().ila_qr_banded_export_f64_dev(self.l, self.u, self.refl, self.batch, ptr(self.d_gbase), ptr(self.d_work),
+                                                 ptr(self.d_ncols), ptr(self.d_nswept), ptr(self.d_xoff), ptr(d_f),
+                                                 ptr(d_t) if self.refl else None, ptr(d_q), s))
+        torch.cuda.synchronize(self.device)
+        return (d_f.cpu().numpy()[:total * LD].reshape(total, LD), d_t.cpu().numpy()[:total], d_q.cpu().numpy()[:total], xoff)
+
+    def state_window(self):
+        """The saved trailing window per instance: W[j][i] = (Q_n' A)[n+i, n+j], j = 0..l+u, i = 0..l (QR plans)."""
+        st = self.d_state.cpu().numpy().reshape(self.batch, self.state_doubles)
+        NC, NR = self.l + self.u + 1, self.l + 1
+        return st[:, :NC * NR].reshape(self.batch, NC, NR)
 
     def run_factor(self):
         s = self._stream()

@@ -1430,19 +1430,66 @@ int ila_qr_banded_work_layout(int l, int u, int64_t batch, int64_t ncap, const i
     return 0;
 }
 
+int ila_qr_banded_state_doubles(int l, int u) { return qr_state_doubles(l, u); }
+int ila_chol_banded_state_doubles(int u) { return chol_state_doubles(u); }
+
+int ila_qr_banded_factor_resume_f64_dev(int l, int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                        const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
+                                        double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
+                                        const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
+                                        int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int want_reflectors,
+                                        double *d_state, int resume, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0) return set_error(ILA_ERR_ARG, "qr_banded: bad sizes");
+    if (resume && !d_state) return set_error(ILA_ERR_ARG, "qr_banded: resume needs the state buffer of the earlier call");
+    QrFwdArgs a{batch, d_p, d_q, d_r, d_shift, d_head, d_b, hp, nb, colgrowth, tol, d_gbase, d_ncap_per, ncap,
+                (double2 *)d_work, d_ncols, d_nconv, d_nswept, d_status};
+    a.state = d_state;
+    a.resume = resume ? 1 : 0;
+    int rc = launch_qr_forward(l, u, a, want_reflectors != 0, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_qr_scan(d_ncols, batch, d_xoff, (cudaStream_t)stream);
+}
+
 int ila_qr_banded_factor_f64_dev(int l, int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
                                  const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
                                  double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
                                  const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
                                  int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int want_reflectors, void *stream)
 {
+    return ila_qr_banded_factor_resume_f64_dev(l, u, batch, d_p, d_q, d_r, d_shift, hp, d_head, nb, d_b, tol, colgrowth, ncap,
+                                               d_ncap_per, d_gbase, d_work, d_ncols, d_nconv, d_nswept, d_xoff, d_status,
+                                               want_reflectors, nullptr, 0, stream);
+}
+
+int ila_qr_banded_partialqr_f64_dev(int l, int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                    const double *d_shift, int hp, const double *d_head, int64_t n, int colgrowth,
+                                    const int64_t *d_gbase, void *d_work, double *d_state, int resume, int64_t *d_ncols,
+                                    int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, void *stream)
+{
     if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
-    if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0) return set_error(ILA_ERR_ARG, "qr_banded: bad sizes");
-    QrFwdArgs a{batch, d_p, d_q, d_r, d_shift, d_head, d_b, hp, nb, colgrowth, tol, d_gbase, d_ncap_per, ncap,
-                (double2 *)d_work, d_ncols, d_nconv, d_nswept, d_status};
-    int rc = launch_qr_forward(l, u, a, want_reflectors != 0, (cudaStream_t)stream);
+    if (batch < 0 || n < 0 || hp < 0 || colgrowth < 1 || !d_state || !d_ncols || !d_nswept || !d_xoff || !d_status)
+        return set_error(ILA_ERR_ARG, "qr_banded_partialqr: bad arguments");
+    QrFwdArgs a{batch, d_p, d_q, d_r, d_shift, d_head, nullptr, hp, 0, colgrowth, 0.0, d_gbase, nullptr, n,
+                (double2 *)d_work, d_ncols, d_nswept, d_nswept, d_status};     // nconv aliases nswept (written first)
+    a.state = d_state;
+    a.resume = resume ? 1 : 0;
+    a.factor_only = 1;
+    int rc = launch_qr_forward(l, u, a, true, (cudaStream_t)stream);
     if (rc) return rc;
     return launch_qr_scan(d_ncols, batch, d_xoff, (cudaStream_t)stream);
+}
+
+int ila_qr_banded_export_f64_dev(int l, int u, int want_reflectors, int64_t batch, const int64_t *d_gbase, const void *d_work,
+                                 const int64_t *d_ncols, const int64_t *d_nswept, const int64_t *d_xoff, double *d_factors,
+                                 double *d_tau, double *d_qtb, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    if (batch < 0 || !d_gbase || !d_work || !d_ncols || !d_nswept || !d_xoff) return set_error(ILA_ERR_ARG, "qr_banded_export: bad arguments");
+    if (batch == 0) return 0;
+    return launch_qr_export(l, u, want_reflectors ? 1 : 0, batch, d_gbase, (const double2 *)d_work, d_ncols, d_nswept, d_xoff,
+                            d_factors, d_tau, d_qtb, (cudaStream_t)stream);
 }
 
 int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *d_gbase, const void *d_work, double *d_xi,
@@ -1464,19 +1511,34 @@ int ila_qr_banded_backsolve_f64_dev(int l, int u, int64_t batch, const int64_t *
     return launch_qr_compact(batch, d_gbase, d_xi, d_ncols, d_nswept, d_xoff, d_x, xcap, (cudaStream_t)stream);
 }
 
+int ila_chol_banded_factor_resume_f64_dev(int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
+                                          const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
+                                          double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
+                                          const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
+                                          int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int full_sweep,
+                                          double *d_state, int resume, void *stream)
+{
+    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
+    if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0) return set_error(ILA_ERR_ARG, "chol_banded: bad sizes");
+    if (resume && !d_state) return set_error(ILA_ERR_ARG, "chol_banded: resume needs the state buffer of the earlier call");
+    CholFwdArgs a{batch, d_p, d_q, d_r, d_shift, d_head, d_b, hp, nb, colgrowth, full_sweep, tol, d_gbase, d_ncap_per, ncap,
+                  (double2 *)d_work, d_ncols, d_nconv, d_nswept, d_status};
+    a.state = d_state;
+    a.resume = resume ? 1 : 0;
+    int rc = launch_chol_forward(u, a, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_qr_scan(d_ncols, batch, d_xoff, (cudaStream_t)stream);
+}
+
 int ila_chol_banded_factor_f64_dev(int u, int64_t batch, const double *d_p, const double *d_q, const double *d_r,
                                    const double *d_shift, int hp, const double *d_head, int nb, const double *d_b,
                                    double tol, int colgrowth, int64_t ncap, const int64_t *d_ncap_per,
                                    const int64_t *d_gbase, void *d_work, int64_t *d_ncols, int64_t *d_nconv,
                                    int64_t *d_nswept, int64_t *d_xoff, int32_t *d_status, int full_sweep, void *stream)
 {
-    if (ila_device_count() <= 0) return set_error(ILA_ERR_NOGPU, "no CUDA device visible: libila_b200 has no CPU fallback");
-    if (batch < 0 || nb < 1 || colgrowth < 1 || hp < 0) return set_error(ILA_ERR_ARG, "chol_banded: bad sizes");
-    CholFwdArgs a{batch, d_p, d_q, d_r, d_shift, d_head, d_b, hp, nb, colgrowth, full_sweep, tol, d_gbase, d_ncap_per, ncap,
-                  (double2 *)d_work, d_ncols, d_nconv, d_nswept, d_status};
-    int rc = launch_chol_forward(u, a, (cudaStream_t)stream);
-    if (rc) return rc;
-    return launch_qr_scan(d_ncols, batch, d_xoff, (cudaStream_t)stream);
+    return ila_chol_banded_factor_resume_f64_dev(u, batch, d_p, d_q, d_r, d_shift, hp, d_head, nb, d_b, tol, colgrowth, ncap,
+                                                 d_ncap_per, d_gbase, d_work, d_ncols, d_nconv, d_nswept, d_xoff, d_status,
+                                                 full_sweep, nullptr, 0, stream);
 }
 
 // shared host driver of the two adaptive banded solves: kind 0 = QR (K1+K2), kind 1 = Cholesky (K5+K2, l == 0)

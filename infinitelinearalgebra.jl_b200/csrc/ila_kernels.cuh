@@ -39,7 +39,11 @@ struct QrFwdArgs {
     double2 *work;
     int64_t *ncols, *nconv, *nswept;
     int32_t *status;
+    double *state = nullptr;   // optional resumable state, qr_state_doubles(l,u) per instance (see qr_forward_kernel)
+    int resume = 0;            // continue from `state` instead of column 0
+    int factor_only = 0;       // partialqr!(F, ncap): sweep to column ncap, no right-hand side / convergence test
 };
+int qr_state_doubles(int l, int u);
 struct QrBwdArgs {
     int64_t batch;
     const int64_t *gbase;
@@ -190,7 +194,10 @@ struct CholFwdArgs {
     double2 *work;
     int64_t *ncols, *nconv, *nswept;
     int32_t *status;
+    double *state = nullptr;   // optional resumable state (AdaptiveCholeskyFactors.ncols + the trailing block), chol_state_doubles(u) per instance
+    int resume = 0;
 };
+int chol_state_doubles(int u);
 int launch_chol_forward(int u, const CholFwdArgs &a, cudaStream_t s);
 
 // from ql_blocktri.cu

@@ -23,6 +23,12 @@ def check(name, f):
     print(f"{name:34s} {'OK' if good else 'MISMATCH'}")
 
 check("ql_toeplitz_l11", lambda g: ila_b200.ql_toeplitz_l11(col, lam, ngpus=g))
+check("ql_toeplitz_l11_real (compact)", lambda g: ila_b200.ql_toeplitz_l11_real(col, lam, ngpus=g))
+big = (np.linspace(-10, 7, 1024)[None, :] + 1j * np.linspace(-7, 8, 1024)[:, None]).reshape(-1)
+def _full(g):
+    L, st = ila_b200.ql_toeplitz_l11_real(col, big, ngpus=g)
+    return (np.round(np.nan_to_num(L), 9), st)          # slab boundaries move the warm-start runs: last bits may differ
+check("ql_toeplitz_l11_real 1024x1024 (1e-9)", _full)
 check("ql_toeplitz_absl11_grid", lambda g: (ila_b200.ql_toeplitz_absl11_grid(col, np.linspace(-10, 7, 301), np.linspace(-7, 8, 77), ngpus=g),))
 check("ql_toeplitz_solve", lambda g: ila_b200.ql_toeplitz_solve(col, lam[:5000], [1.0, 0.5j], 7, ngpus=g))
 head = np.diag(np.full(6, 0.3 + 0j)) + 0.0
