@@ -8,6 +8,10 @@
 #   ql(A - λ*I) \ b                -> ILAB200.ql_solve(A, λs, b, nout)           (src/infql.jl:266-289)
 #   ql(::PertToeplitz), ql(::BlockTriPertToeplitz) -> ql_pert_L11, blocktri_L11   (src/infql.jl:70-93,189-209)
 # Exceptions of the reference are rebuilt from status[] (SURVEY §5).
+#
+# This file binds EVERY entry of include/ila_b200.h that a Julia caller needs (batched forms on plain arrays).  The
+# method overloads that make `ql(A - λ*I)`, `qr(A) \ b`, `cholesky(S) \ b` themselves route here live in
+# ILAB200Overloads.jl next to it.
 module ILAB200
 
 using LinearAlgebra
@@ -20,6 +24,41 @@ struct IlaError <: Exception
 end
 lasterror() = unsafe_string(ccall((:ila_last_error, lib), Cstring, ()))
 check(rc) = rc == 0 || throw(IlaError(rc, lasterror()))
+
+"""
+    PinnedVector{T}(n) -> Vector{T}
+
+A `Vector{T}` on page-locked host memory from `ila_host_alloc` (freed by a finalizer): the library copies such arrays by DMA
+with no staging.  Ordinary `Vector`s work too — they go through the library's pinned staging ring — so this only matters
+for result arrays that are produced over and over (the batch wrappers below allocate their outputs this way).
+"""
+function PinnedVector(::Type{T}, n::Integer) where {T}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ila_host_alloc, lib), Cint, (Ptr{Ptr{Cvoid}}, Int64), p, max(n, 1) * sizeof(T)))
+    v = unsafe_wrap(Array, Ptr{T}(p[]), n; own=false)
+    finalizer(_ -> ccall((:ila_host_free, lib), Cint, (Ptr{Cvoid},), p[]), v)
+    v
+end
+"Pin an existing array in place for the lifetime of `f()` (cudaHostRegister costs ~10 ms/MB: only for buffers reused many times)."
+function with_pinned(f, a::Array)
+    check(ccall((:ila_host_register, lib), Cint, (Ptr{Cvoid}, Int64), a, sizeof(a)))
+    try
+        GC.@preserve a f()
+    finally
+        ccall((:ila_host_unregister, lib), Cint, (Ptr{Cvoid},), a)
+    end
+end
+
+"Rebuild the reference's exception from a per-instance status (SURVEY §5)."
+function throw_status(st::Integer, what)
+    st == 0 && return nothing
+    st == 1 && throw(DomainError(what, STATUS_MSG[1]))
+    st == 2 && throw(DomainError(what, STATUS_MSG[2]))
+    st == 3 && error("Did not converge")                                   # src/infql.jl:181 / capacity reached
+    st == 4 && throw(PosDefException(1))                                   # pbtrf info > 0 (discarded upstream, infcholesky.jl:49)
+    st == 5 && error("Not-a-number encounted")                             # src/infqr.jl:324
+    error("libila_b200: status $st")
+end
 
 const STATUS_MSG = Dict(
     1 => "QL factorization does not exist. This could indicate that the operator is not Fredholm or that the dimension of the kernel exceeds that of the co-kernel. Try again with the adjoint.",
@@ -43,6 +82,46 @@ function ql_L11(datacolumn::AbstractVector, λs::AbstractVector; branch_rank::In
                 (Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Int64, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Int32}, Cint),
                 l, 1, a, λ, n, branch_rank, L11, C_NULL, status, ngpus))
     L11, status
+end
+
+"""
+    ql_L11_real(datacolumn, λs; branch_rank=1, ngpus=1) -> (L11::Vector{Float64}, status::Vector{UInt8})
+
+Compact form (`ila_ql_toeplitz_l11re_c64`): `L[1,1]` of a ComplexF64 factorization is real (`ql_X!`'s k = 1 reflector
+leaves `-ν`), so 8 B + 1 B per shift come back instead of 16 + 4.  Entries with `status != 0` are NaN with the status
+in the NaN payload.  Outputs are pinned arrays.
+"""
+function ql_L11_real(datacolumn::AbstractVector, λs::AbstractVector; branch_rank::Integer=1, ngpus::Integer=1)
+    a = Vector{ComplexF64}(datacolumn)
+    λ = λs isa Vector{ComplexF64} ? λs : Vector{ComplexF64}(λs)
+    n = length(λ)
+    L11 = PinnedVector(Float64, n); status = PinnedVector(UInt8, n)
+    check(ccall((:ila_ql_toeplitz_l11re_c64, lib), Cint,
+                (Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Int64, Cint, Ptr{Float64}, Ptr{UInt8}, Cint),
+                length(a) - 2, 1, a, λ, n, branch_rank, L11, status, ngpus))
+    L11, status
+end
+
+"""
+    ql_tail(datacolumn, λs; branch_rank=1, ngpus=1) -> (X::Array{T,3} (2 × m × n), τ::Matrix{T} (2 × n), status)
+
+The whole fixed-point record of `ql_hessenberg(::InfToeplitz)` (src/banded/infqltoeplitz.jl:56-65) per shift: `X` after
+`ql_X!` and `τ`, from which first L column = `[X[1,m-1]; X[2,m-1:-1:1]]`, tail L column = `X[2,m:-1:1]` and the 2×2 block
+`QL(X[:,m-1:m], τ).Q` follow (`:63-64`).  `T` is `Float64` when symbol and shifts are real (the `T<:Real` method, `:7-16`,
+with the sign rule documented in include/ila_b200.h), else `ComplexF64`.
+"""
+function ql_tail(datacolumn::AbstractVector, λs::AbstractVector; branch_rank::Integer=1, ngpus::Integer=1)
+    T = (eltype(datacolumn) <: Real && eltype(λs) <: Real) ? Float64 : ComplexF64
+    a = Vector{T}(datacolumn); λ = Vector{T}(λs); n = length(λ); m = length(a)
+    L11 = Vector{T}(undef, n); tail = Matrix{T}(undef, 2m + 2, n); status = Vector{Int32}(undef, n)
+    sym = T === Float64 ? :ila_ql_toeplitz_l11_f64 : :ila_ql_toeplitz_l11_c64
+    check(ccall((sym, lib), Cint, (Cint, Cint, Ptr{T}, Ptr{T}, Int64, Cint, Ptr{T}, Ptr{T}, Ptr{Int32}, Cint),
+                m - 2, 1, a, λ, n, branch_rank, L11, tail, status, ngpus))
+    X = Array{T,3}(undef, 2, m, n)
+    for i in 1:n, j in 1:m                       # record = X[1,1:m], X[2,1:m], τ[1], τ[2]
+        X[1, j, i] = tail[j, i]; X[2, j, i] = tail[m + j, i]
+    end
+    X, tail[2m+1:2m+2, :], status
 end
 
 "Scalar drop-in: rethrows the reference's DomainError (src/banded/infqltoeplitz.jl:12-13,23)."
@@ -229,5 +308,174 @@ function almostbanded_solve(lD::Integer, uD::Integer, dg::Matrix{Float64}, bg::M
     check(rc)
     x, ncols, status
 end
+
+
+# ---- the operator description shared by the adaptive QR / Cholesky entries -------------------------------------------
+# instance-major (C row-major) flattening of a batch × k Julia matrix
+_rm(M::AbstractMatrix) = vec(permutedims(Matrix{Float64}(M)))
+_rm(::Nothing) = C_NULL
+
+"""
+    chol_solve(u, p, q, r, b; shift, head, tol, colgrowth, ncap, ngpus) -> (x::Vector{Vector{Float64}}, ncols, nconv, status)
+
+Batched `cholesky(S_i) \ b_i` for ∞ symmetric positive definite banded operators (upper bandwidth `u`, generators of the
+UPPER bands only, data-row order +u … 0).  Replaces `adaptivecholesky` / `partialcholesky!` / the adaptive `L \ b` and
+`U \ b` (src/infcholesky.jl:42-59, 71-75, 94-140).  status 4 = not positive definite.
+"""
+function chol_solve(u::Integer, p::Matrix{Float64}, q::Matrix{Float64}, r::Union{Nothing,Matrix{Float64}}, b::Matrix{Float64};
+                    shift=nothing, head=nothing, tol=floatmin(Float64), colgrowth=1000, ncap::Integer, ngpus::Integer=1)
+    batch = size(p, 1); xcap = batch * ncap
+    x = Vector{Float64}(undef, xcap); xoff = Vector{Int64}(undef, batch + 1)
+    ncols = Vector{Int64}(undef, batch); nconv = similar(ncols); status = Vector{Int32}(undef, batch)
+    hp = head === nothing ? 0 : size(head, 2)
+    sh = shift === nothing ? C_NULL : Vector{Float64}(shift)
+    check(ccall((:ila_chol_banded_solve_f64, lib), Cint,
+                (Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64},
+                 Float64, Cint, Int64, Ptr{Int64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Int32}, Cint),
+                u, batch, _rm(p), _rm(q), _rm(r), sh, hp, head === nothing ? C_NULL : _rm(head), size(b, 2), _rm(b), tol,
+                colgrowth, ncap, C_NULL, x, xcap, xoff, ncols, nconv, C_NULL, C_NULL, status, ngpus))
+    [x[xoff[i]+1:xoff[i+1]] for i in 1:batch], ncols, nconv, status
+end
+
+"""
+    qr_solve_c64(l, u, p, q, r, b; shift, head, tol, colgrowth, ncap, ngpus)
+
+Complex eltype of `qr_solve` (`ila_qr_banded_solve_c64`): `(A - λ_i I) \ b` by adaptive QR with complex shifts / operators.
+"""
+function qr_solve_c64(l::Integer, u::Integer, p::Matrix{ComplexF64}, q::Matrix{ComplexF64}, r::Union{Nothing,Matrix{Float64}},
+                      b::Matrix{ComplexF64}; shift=nothing, head=nothing, tol=floatmin(Float64), colgrowth=1000,
+                      ncap::Integer, ngpus::Integer=1)
+    batch = size(p, 1); xcap = batch * ncap
+    cm(M) = vec(permutedims(M))
+    x = Vector{ComplexF64}(undef, xcap); xoff = Vector{Int64}(undef, batch + 1)
+    ncols = Vector{Int64}(undef, batch); nconv = similar(ncols); status = Vector{Int32}(undef, batch)
+    hp = head === nothing ? 0 : size(head, 2)
+    check(ccall((:ila_qr_banded_solve_c64, lib), Cint,
+                (Cint, Cint, Int64, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Float64}, Ptr{ComplexF64}, Cint, Ptr{ComplexF64}, Cint,
+                 Ptr{ComplexF64}, Float64, Cint, Int64, Ptr{Int64}, Ptr{ComplexF64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
+                 Ptr{Int32}, Cint),
+                l, u, batch, cm(p), cm(q), r === nothing ? C_NULL : _rm(r), shift === nothing ? C_NULL : Vector{ComplexF64}(shift),
+                hp, head === nothing ? C_NULL : cm(Matrix{ComplexF64}(head)), size(b, 2), cm(b), tol, colgrowth, ncap, C_NULL, x,
+                xcap, xoff, ncols, nconv, status, ngpus))
+    [x[xoff[i]+1:xoff[i+1]] for i in 1:batch], ncols, nconv, status
+end
+
+"""
+    ql_pert_solve(head, datacolumn, λs, b, nout; branch_rank=1, ngpus=1) -> (X::Matrix{ComplexF64} (n × nout), status)
+
+`(ql(A - λ I) \ b)[1:nout]` for a perturbed Toeplitz `A` (`ila_ql_perttoeplitz_solve_c64`): `ql_hessenberg!` assembly
+(src/infql.jl:70-93) + `ldiv!(F.L, lmul!(F.Q', b))` (src/infql.jl:266-289).  Pinned by test/test_infql.jl:147-160.
+"""
+function ql_pert_solve(head::AbstractMatrix, datacolumn::AbstractVector, λs::AbstractVector, b::AbstractVector, nout::Integer;
+                       branch_rank::Integer=1, ngpus::Integer=1)
+    a = Vector{ComplexF64}(datacolumn); λ = Vector{ComplexF64}(λs); h = Matrix{ComplexF64}(head); bb = Vector{ComplexF64}(b)
+    n = length(λ); X = Matrix{ComplexF64}(undef, n, nout); status = Vector{Int32}(undef, n)
+    check(ccall((:ila_ql_perttoeplitz_solve_c64, lib), Cint,
+                (Cint, Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Int64, Cint, Cint, Ptr{ComplexF64}, Int64,
+                 Ptr{ComplexF64}, Ptr{Int32}, Cint),
+                length(a) - 2, 1, size(h, 1), h, a, λ, n, branch_rank, length(bb), bb, nout, X, status, ngpus))
+    X, status
+end
+
+"""
+    revchol_tridiag(ga, gb, n; shift, a_head, b_head, ngpus) -> (la, lb, N, status)
+
+Batched `reversecholesky(SymTridiagonal(a, b))` leading `n` entries (`ila_revchol_tridiag_f64`;
+src/banded/infreversecholeskytridiagonal.jl:66-141).  `ga`, `gb`: batch × 5 rational generators `(c0, p, q, r, s)` of the
+diagonal / off-diagonal, value(k) = c0 + (p + q k)/(r + s k).  `la`, `lb` are n × batch.
+"""
+function revchol_tridiag(ga::Matrix{Float64}, gb::Matrix{Float64}, n::Integer; shift=nothing, a_head=nothing, b_head=nothing,
+                         ngpus::Integer=1)
+    batch = size(ga, 1)
+    la = Matrix{Float64}(undef, n, batch); lb = similar(la); N = Vector{Int64}(undef, batch); status = Vector{Int32}(undef, batch)
+    hp = a_head === nothing ? 0 : length(a_head)
+    check(ccall((:ila_revchol_tridiag_f64, lib), Cint,
+                (Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Int64}, Ptr{Int32}, Cint),
+                batch, _rm(ga), _rm(gb), shift === nothing ? C_NULL : Vector{Float64}(shift), hp,
+                a_head === nothing ? C_NULL : Vector{Float64}(a_head), b_head === nothing ? C_NULL : Vector{Float64}(b_head), n, la,
+                lb, N, status, ngpus))
+    la, lb, N, status
+end
+
+"""
+    finite_section_ql(l, u, g, shifts; j=50, tol=eps(), maxN=10000, head=nothing, ngpus=1) -> (Lband, V, τ, N, status)
+
+Batched `ql(A - λ I, tol)` for ∞ banded operators WITHOUT a Toeplitz tail (`ila_ql_finite_section_f64/_c64`;
+src/infql.jl:385-462).  `g`: (l+u+1) × 5 rational generators per diagonal (+u first), shared by the batch; `shifts` real or
+complex.  `Lband[c+1, k, i] = L[k, k-c]`, `V[r, k, i]`, `τ[k, i]` for the leading `j` columns.
+"""
+function finite_section_ql(l::Integer, u::Integer, g::Matrix, shifts::AbstractVector; j::Integer=50, tol::Real=eps(Float64),
+                           maxN::Integer=10000, head=nothing, ngpus::Integer=1)
+    T = (eltype(g) <: Real && eltype(shifts) <: Real && (head === nothing || eltype(head) <: Real)) ? Float64 : ComplexF64
+    batch = length(shifts); nd = l + u + 1
+    gg = repeat(vec(permutedims(Matrix{T}(g))), batch)
+    Lb = Array{T,3}(undef, nd, j, batch); V = Array{T,3}(undef, u, j, batch); τ = Matrix{T}(undef, j, batch)
+    N = Vector{Int64}(undef, batch); status = Vector{Int32}(undef, batch)
+    hp = head === nothing ? 0 : size(head, 2)
+    sym = T === Float64 ? :ila_ql_finite_section_f64 : :ila_ql_finite_section_c64
+    check(ccall((sym, lib), Cint,
+                (Cint, Cint, Int64, Ptr{T}, Ptr{T}, Cint, Ptr{T}, Int64, Float64, Int64, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{Int64}, Ptr{Int32}, Cint),
+                l, u, batch, gg, Vector{T}(shifts), hp, head === nothing ? C_NULL : vec(permutedims(Matrix{T}(head))), j, tol, maxN,
+                Lb, V, τ, N, status, ngpus))
+    Lb, V, τ, N, status
+end
+
+"""
+    biconj(U, C, n; upper=true, ngpus=1) -> (dv, ev)
+
+`BidiagonalConjugation(U, X, V, uplo)` bands (`ila_biconj_bands_f64`; src/banded/bidiagonalconjugation.jl:19-60) from the
+tridiagonal parts of `U` and `C = X*V`, each 3 × m (`[k+2,k+1]`, diagonal, `[k+1,k+2]`), m ≥ n+1.
+"""
+function biconj(U::Matrix{Float64}, Cm::Matrix{Float64}, n::Integer; upper::Bool=true, ngpus::Integer=1)
+    Ut = permutedims(U); Ct = permutedims(Cm); ld = size(Ut, 1)
+    dv = Vector{Float64}(undef, n); ev = Vector{Float64}(undef, n)
+    check(ccall((:ila_biconj_bands_f64, lib), Cint,
+                (Cint, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Cint),
+                upper ? 1 : 0, 1, n, Ut, Ct, ld, dv, ev, ngpus))
+    dv, ev
+end
+
+"""
+    chol_triconj(u, p, q, X, n; shift, head, ngpus) -> (Y::Array{Float64,3} (n × 3 × batch), status)
+
+`TridiagonalConjugation(cholesky(S_i).U, X)` in one call, `U` never leaves the device (`ila_chol_triconj_f64`;
+src/banded/tridiagonalconjugation.jl:224-282 behind src/infcholesky.jl:42-59).  `X`: 3 × m bands shared by the batch.
+"""
+function chol_triconj(u::Integer, p::Matrix{Float64}, q::Matrix{Float64}, X::Matrix{Float64}, n::Integer; shift=nothing,
+                      head=nothing, ngpus::Integer=1)
+    batch = size(p, 1); Xt = permutedims(X); hp = head === nothing ? 0 : size(head, 2)
+    Y = Array{Float64,3}(undef, n, 3, batch); status = Vector{Int32}(undef, batch)
+    check(ccall((:ila_chol_triconj_f64, lib), Cint,
+                (Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
+                 Cint, Ptr{Float64}, Ptr{Int32}, Cint),
+                u, batch, _rm(p), _rm(q), C_NULL, shift === nothing ? C_NULL : Vector{Float64}(shift), hp,
+                head === nothing ? C_NULL : _rm(head), n, Xt, size(Xt, 1), 1, Y, status, ngpus))
+    Y, status
+end
+
+"Complex eltype of `blocktri_L11` (`ila_ql_blocktri_l11_c64`, e.g. `A - 5im*I`, test/test_periodic.jl:20-26)."
+function blocktri_L11(dl_head::Vector{Matrix{ComplexF64}}, d_head::Vector{Matrix{ComplexF64}}, du_head::Vector{Matrix{ComplexF64}},
+                      c::Matrix{ComplexF64}, a::Matrix{ComplexF64}, b::Matrix{ComplexF64}, energies::AbstractVector;
+                      atol::Real=1e-10, maxit::Integer=1_000_000, ngpus::Integer=1)
+    n = size(c, 1); e = Vector{ComplexF64}(energies); m = length(e)
+    cat3(v) = isempty(v) ? ComplexF64[] : reduce(vcat, vec.(v))
+    L11 = Vector{ComplexF64}(undef, m); iters = Vector{Int32}(undef, m); status = Vector{Int32}(undef, m)
+    T = ComplexF64
+    check(ccall((:ila_ql_blocktri_l11_c64, lib), Cint,
+                (Cint, Ptr{T}, Ptr{T}, Ptr{T}, Cint, Ptr{T}, Cint, Ptr{T}, Cint, Ptr{T}, Ptr{T}, Int64, Float64, Cint, Ptr{T},
+                 Ptr{Int32}, Ptr{Int32}, Cint),
+                n, c, a, b, length(dl_head), cat3(dl_head), length(d_head), cat3(d_head), length(du_head), cat3(du_head), e, m,
+                atol, maxit, L11, iters, status, ngpus))
+    L11, iters, status
+end
+
+# ---- library plumbing ------------------------------------------------------------------------------------------------
+device_count() = Int(ccall((:ila_device_count, lib), Cint, ()))
+set_device(d::Integer) = check(ccall((:ila_set_device, lib), Cint, (Cint,), d))
+release() = check(ccall((:ila_release, lib), Cint, ()))
+"0 auto (pageable arrays are staged through the library's pinned ring), 1 plain cudaMemcpyAsync, 2 always staged"
+set_host_copy_mode(m::Integer) = check(ccall((:ila_set_host_copy_mode, lib), Cint, (Cint,), m))
 
 end # module
