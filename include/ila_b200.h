@@ -127,6 +127,10 @@ int ila_ql_set_shifts_per_thread(int spt);
  * iteration uses up its sweeps without reaching a root to rounding (backward error test) gets status
  * ILA_NOT_CONVERGED and NaN — never a silent value.  Lowering the limits is a test hook that forces that outcome. */
 int ila_ql_set_max_sweeps(int fp64_sweeps, int scout_sweeps);
+/* Cold start of a run's first shift: 1 (default) = closed-form FP32 seeds where the degree has them (l = 1: quadratic
+ * formula, l = 3: Ferrari's resolvent) polished by the usual sweeps; 0 = circle start + Aberth sweeps for every degree.
+ * Results do not depend on it beyond the last bits of the selected root's Newton refinement (validation knob). */
+int ila_ql_set_cold_start(int closed_form_seeds);
 
 /* ---- K1+K2: adaptive banded QR solve  x_i = A_i \ b_i ----------------------------------------
  * Replaces qr(A) -> adaptiveqr (src/infqr.jl:163-174) and `\` = ldiv!(F.R, F.Q'*b) (src/infqr.jl:370-374):

@@ -89,6 +89,7 @@ SIGNATURES = {
                                             _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "ila_ql_set_shifts_per_thread": (C.c_int, [C.c_int]),
     "ila_ql_set_max_sweeps": (C.c_int, [C.c_int, C.c_int]),
+    "ila_ql_set_cold_start": (C.c_int, [C.c_int]),
     "ila_ql_toeplitz_l11re_c64": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int]),
     "ila_ql_toeplitz_l11re_c64_dev": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp]),
     "ila_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),

@@ -1388,6 +1388,12 @@ int ila_ql_set_max_sweeps(int fp64_sweeps, int scout_sweeps)
     return 0;
 }
 
+int ila_ql_set_cold_start(int closed_form_seeds)
+{
+    tz_set_seeds(closed_form_seeds);
+    return 0;
+}
+
 int ila_ql_set_shifts_per_thread(int spt)
 {
     if (spt < 0 || spt > 16) return set_error(ILA_ERR_ARG, "shifts per thread must be in 0..16 (0 = automatic)");

@@ -10,6 +10,7 @@ int launch_ql_toeplitz(bool real_path, int l, int u, const double *a_host, int b
                        int64_t n, double *d_L11, double *d_tail, int32_t *d_status, cudaStream_t stream);
 
 void tz_set_spt(int v);
+void tz_set_seeds(int v);
 void tz_set_max_sweeps(int fp64_sweeps, int scout_sweeps);
 int launch_ql_toeplitz_l11re(int l, int u, const double *a_host, int branch_rank, const double *d_lambda, int64_t n,
                              double *d_L11re, uint8_t *d_status8, cudaStream_t stream);

@@ -28,6 +28,8 @@ constexpr int kAberthMaxIt = 48;
 constexpr int kScoutMaxIt = 16;
 static std::atomic<int> g_tz_spt{0};   // 0 = automatic; set by ila_ql_set_shifts_per_thread (1 = every shift starts cold)
 static std::atomic<int> g_tz_max_it{0}, g_tz_scout_max_it{0};   // 0 = kAberthMaxIt / kScoutMaxIt (ila_ql_set_max_sweeps: test hook)
+static std::atomic<int> g_tz_seeds{1};
+void tz_set_seeds(int v) { g_tz_seeds.store(v ? 1 : 0); }
 void tz_set_spt(int v) { g_tz_spt.store(v); }
 void tz_set_max_sweeps(int fp64_sweeps, int scout_sweeps)
 {
@@ -117,6 +119,7 @@ struct TzParams {
     double beta2;      // |β|^2
     int branch_rank;
     int max_it, scout_max_it;   // sweep limits of the FP64 / FP32 simultaneous iterations
+    int use_seeds;              // closed-form cold-start seeds (N = 2, 4); 0 = circle start everywhere (validation)
     int out_mode;      // complex-eltype L11-only output: 0 = ComplexF64 + int32 status, 1 = Float64 (NaN payload = status) + optional uint8 status
 };
 
@@ -197,6 +200,91 @@ __device__ __forceinline__ int dk_sweep_f32(const cplxf (&cf)[N + 1], cplxf (&w)
         big = big || (c2 > 1e-4f * w2) || !(w2 < 1e30f);
     }
     return big ? 2 : (notconv ? 1 : 0);
+}
+
+// ---- closed-form seeds for the cold start (FP32) --------------------------------------------------------------------
+// A run's first shift used to start on a circle and needed 6-14 Aberth sweeps (warp maximum ~8: ~2400 instructions, a third
+// of the kernel's issue slots on the 1024² grid and ALL of them on the sub-wave slabs of a strong-scaled grid).  For the
+// degrees with a closed form the roots are written down instead — Ferrari's resolvent for the quartic (the Bull-head and
+// every other l = 3 symbol), the quadratic formula for l = 1 — in FP32, to ~1e-3..1e-6 depending on cancellation; they
+// only SEED the same Durand–Kerner / Aberth polish the warm starts use, and anything degenerate (multiple roots, vanishing
+// resolvent root) falls back to the circle start, so no result depends on them.
+__device__ __forceinline__ cplxf csqrtf_(cplxf z)
+{
+    const float r = sqrtf(abs2f(z));
+    const float t = sqrtf(0.5f * (r + fabsf(z.re)));
+    if (!(t > 0.f)) return mkf(0.f);
+    const float h = 0.5f * z.im / t;
+    return (z.re >= 0.f) ? mkf(t, h) : mkf(fabsf(h), copysignf(t, z.im));
+}
+__device__ __forceinline__ cplxf crcpf_(cplxf z)
+{
+    const float d = abs2f(z);
+    return (d > 1e-36f && d < 1e36f) ? (1.0f / d) * conjf_(z) : mkf(0.f);
+}
+__device__ __forceinline__ cplxf ccbrtf_(cplxf z)
+{
+    const float r2 = abs2f(z);
+    if (!(r2 > 0.f)) return mkf(0.f);
+    const float r = cbrtf(sqrtf(r2));
+    float sn, cs;
+    __sincosf(atan2f(z.im, z.re) * (1.0f / 3.0f), &sn, &cs);
+    return mkf(r * cs, r * sn);
+}
+// quadratic y^2 + b y + c = 0: the larger root first (no cancellation), the other one from the product
+__device__ __forceinline__ void quadf_(cplxf b, cplxf c, cplxf &y1, cplxf &y2)
+{
+    cplxf sq = csqrtf_(b * b - 4.0f * c);
+    if (b.re * sq.re + b.im * sq.im < 0.f) sq = mkf(0.f) - sq;      // Re(conj(b) sq) >= 0: -(b + sq) does not cancel
+    y1 = -0.5f * (b + sq);
+    y2 = c * crcpf_(y1);
+}
+template <int N>
+__device__ __forceinline__ bool closed_form_seeds_f32(const cplxf (&cf)[N + 1], cplxf (&w)[N])
+{
+    if constexpr (N == 2) {
+        quadf_(cf[1], cf[2], w[0], w[1]);
+        return abs2f(w[0]) > 0.f;
+    } else if constexpr (N == 4) {
+        // depressed quartic y^4 + p y^2 + q y + r, w = y - a
+        const cplxf a = 0.25f * cf[1], a2 = a * a;
+        const cplxf p = cf[2] - 6.0f * a2;
+        const cplxf q = cf[3] - 2.0f * (a * cf[2]) + 8.0f * (a2 * a);
+        const cplxf r = cf[4] - a * cf[3] + a2 * cf[2] - 3.0f * (a2 * a2);
+        // resolvent cubic m^3 + p m^2 + (p^2/4 - r) m - q^2/8 = 0, m = t - p/3:  t^3 + P t + Q = 0
+        const cplxf p2 = p * p;
+        const cplxf P = mkf(0.f) - ((1.0f / 12.0f) * p2 + r);
+        const cplxf Q = (-1.0f / 108.0f) * (p2 * p) + (1.0f / 3.0f) * (p * r) - 0.125f * (q * q);
+        const cplxf sD = csqrtf_(0.25f * (Q * Q) + (1.0f / 27.0f) * (P * P * P));
+        const cplxf hQ = -0.5f * Q;
+        cplxf u3 = hQ + sD;
+        const cplxf u3b = hQ - sD;
+        if (abs2f(u3b) > abs2f(u3)) u3 = u3b;                        // Cardano: the cube without cancellation
+        const cplxf u = ccbrtf_(u3);
+        const cplxf v = (-1.0f / 3.0f) * (P * crcpf_(u));
+        // the three resolvent roots; the one of largest modulus keeps s = sqrt(2m) away from 0 (q ~ 0: biquadratic case)
+        const cplxf om = mkf(-0.5f, 0.8660254f), omc = mkf(-0.5f, -0.8660254f);
+        const cplxf p3 = (1.0f / 3.0f) * p;
+        cplxf m = u + v - p3;
+        const cplxf m1 = om * u + omc * v - p3, m2 = omc * u + om * v - p3;
+        if (abs2f(m1) > abs2f(m)) m = m1;
+        if (abs2f(m2) > abs2f(m)) m = m2;
+        const cplxf sm = csqrtf_(2.0f * m);
+        const float s2 = abs2f(sm);
+        if (!(s2 > 1e-12f * (1.0f + abs2f(p)))) return false;        // quadruple-root neighbourhood: circle start instead
+        const cplxf g = 0.5f * (q * crcpf_(sm));
+        const cplxf base = 0.5f * p + m;
+        cplxf y0, y1, y2, y3;
+        quadf_(mkf(0.f) - sm, base + g, y0, y1);                     // y^2 - s y + (p/2 + m + q/(2s)) = 0
+        quadf_(sm, base - g, y2, y3);                                // y^2 + s y + (p/2 + m - q/(2s)) = 0
+        w[0] = y0 - a; w[1] = y1 - a; w[2] = y2 - a; w[3] = y3 - a;
+        float chk = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) chk += abs2f(w[j]);
+        return chk < 1e30f;                                          // false on NaN / overflow
+    } else {
+        return false;
+    }
 }
 
 // One Gauss–Seidel Aberth–Ehrlich sweep over all N roots; returns 0 when every correction is below 1e-9 |w_j|
@@ -448,7 +536,11 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
 
     // ---- FP32 scout: cold start on a circle around the centroid with the geometric-mean radius |P(c)|^(1/N),
     //      warm start from the previous shift's roots
-    if (!have_roots) {
+    bool seeded = false;
+    if (!have_roots && P.use_seeds) {
+        seeded = closed_form_seeds_f32<N>(cff, wf);
+    }
+    if (!have_roots && !seeded) {
         const cplxf c = (1.0f / N) * mkf((float)g[1].re, (float)g[1].im);
         cplxf pc = mkf(1.f);
 #pragma unroll
@@ -473,6 +565,10 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
         scout = dk_sweep_f32<N>(cff, wf);
 #pragma unroll
         for (int j = 0; j < N; j++) dwf[j] = wf[j] - wold[j];
+    } else if (seeded) {
+        // cold with closed-form seeds: the same Durand–Kerner polish (a second one when the first still moved the roots)
+        scout = dk_sweep_f32<N>(cff, wf);
+        if (scout == 1) scout = dk_sweep_f32<N>(cff, wf);
     }
 #ifdef ILA_K3_DEBUG
     int dbg_f32 = 0, dbg_f64 = 0, dbg_flags = have_roots ? 1 : 0;
@@ -791,6 +887,7 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
     P.max_it = g_tz_max_it.load() > 0 ? g_tz_max_it.load() : kAberthMaxIt;
     P.scout_max_it = g_tz_scout_max_it.load() > 0 ? g_tz_scout_max_it.load() : kScoutMaxIt;
     P.out_mode = G.out_mode;
+    P.use_seeds = g_tz_seeds.load();
     for (int k = 0; k <= N; k++) {
         // cf0_k = (-1)^k a_{m-k}/β with a_{m-k} = a_rev[N-k]; cf0_0 = 1
         cplx v = (k == 0) ? cplx{1.0, 0.0} : cplx{a_rev[N - k].re * P.ginv.re - a_rev[N - k].im * P.ginv.im,
@@ -830,14 +927,20 @@ static int launch_n(const cplx *a_rev, int branch_rank, const double *d_lambda, 
         wave_blocks = sms * (per_sm > 0 ? per_sm : 1);
         if (dev == dslot) wave_cache[dslot][want_tail ? 1 : 0].store(wave_blocks);
     }
-    // Run length.  r = n / (threads of one full wave).  A warm shift costs about a quarter of a cold one, so below ~8 waves it
-    // pays to run HALF the resident threads with runs twice as long (measured on B200, 1024-wide grid rows, µs per launch:
-    // 64 Ki shifts 17.4 -> 15.4, 128 Ki 21.5 -> 19.5, 256 Ki 29.7 -> 25.6, 512 Ki 33.8, 1 Mi 52.2 at spt 8, 4 Mi 142 at 16;
-    // profiles/r02_k3_e2e_probe.json); from 8 waves up the run length that makes the grid one full wave is best.
+    // Run length.  r = n / (threads of one full wave).
+    //  * degrees with closed-form cold seeds (N = 2, 4): a cold shift costs ~1.25 warm ones, so occupancy wins — the smallest
+    //    run length for which the grid is one full wave (measured on B200, 1024-wide rows, µs per launch at the best spt:
+    //    16-128 Ki shifts 10-14 at spt 1, 256 Ki 18.4 at 2, 512 Ki 26.6 at 4, 1 Mi 43.0 at 8, 4 Mi 130 at 16;
+    //    profiles/r02_k3_kernel_vs_slab.json);
+    //  * other degrees (circle start + Aberth sweeps: a cold shift costs ~4 warm ones): below ~8 waves HALF the resident
+    //    threads with runs twice as long are faster; from 8 waves up the one-wave run length again.
     const double r = (double)n / ((double)wave_blocks * threads);
-    int spt = (int)ceil(2.0 * r + 0.5);
     const int full = (int)ceil(r);
-    if (spt > 8 && spt > full) spt = full > 8 ? full : 8;
+    int spt = full;
+    if (!((N == 2 || N == 4) && g_tz_seeds.load())) {
+        spt = (int)ceil(2.0 * r + 0.5);
+        if (spt > 8 && spt > full) spt = full > 8 ? full : 8;
+    }
     while (spt & (spt - 1)) spt &= spt - 1;   // power of two: runs then do not straddle the rows of power-of-two grids
     if (g_tz_spt.load() > 0) spt = g_tz_spt.load();
     if (spt < 1) spt = 1;

@@ -140,12 +140,14 @@ def test_not_converged_is_reported(ila):
     try:
         _lib.check(lib.ila_ql_set_max_sweeps(1, 1))
         _lib.check(lib.ila_ql_set_shifts_per_thread(1))
+        _lib.check(lib.ila_ql_set_cold_start(0))              # circle starts (the closed-form seeds would converge anyway)
         L, st = ila.ql_toeplitz_l11(BULLHEAD_COLUMN, lam)
         Lr, st8 = ila.ql_toeplitz_l11_real(BULLHEAD_COLUMN, lam)
         z = ila.ql_toeplitz_absl11_grid(BULLHEAD_COLUMN, np.linspace(-10.0, 7.0, 48), np.linspace(-7.0, 8.0, 48))
     finally:
         _lib.check(lib.ila_ql_set_max_sweeps(0, 0))
         _lib.check(lib.ila_ql_set_shifts_per_thread(0))
+        _lib.check(lib.ila_ql_set_cold_start(1))
     assert set(np.unique(st)) <= {0, 1, 3}
     assert (st == 3).mean() > 0.9                              # one sweep from a circle start is nowhere near a root
     assert np.all(np.isnan(L[st == 3].real))
@@ -157,6 +159,43 @@ def test_not_converged_is_reported(ila):
     # defaults restored: the same call converges everywhere again
     L2, st2 = ila.ql_toeplitz_l11(BULLHEAD_COLUMN, lam)
     assert np.array_equal(st2, st0) and not np.any(st2 == 3)
+
+
+def test_cold_start_seeds_do_not_change_results(ila):
+    """Closed-form FP32 seeds (Ferrari for l = 3, quadratic formula for l = 1) against circle starts + Aberth sweeps: same
+    statuses, L[1,1] equal to rounding (the seeds only start the polish), every shift cold and the production run lengths."""
+    from ila_b200 import _lib
+    from oracle import toeplitz_ql as tq
+    lib = ila.lib()
+    rng = np.random.default_rng(5)
+    cases = [(np.array(BULLHEAD_COLUMN), bullhead_grid(256, 192))]
+    for _ in range(4):
+        cases.append((rng.normal(size=5) + 1j * rng.normal(size=5), (rng.normal(size=3000) + 1j * rng.normal(size=3000)) * 3))
+        cases.append((rng.normal(size=3) + 1j * rng.normal(size=3), (rng.normal(size=3000) + 1j * rng.normal(size=3000)) * 3))
+    for col, lam in cases:
+        if abs(col[0]) < 0.3:
+            col[0] = 1.0
+        out = {}
+        try:
+            for seeds in (1, 0):
+                for spt in (0, 1):
+                    _lib.check(lib.ila_ql_set_cold_start(seeds))
+                    _lib.check(lib.ila_ql_set_shifts_per_thread(spt))
+                    out[(seeds, spt)] = ila.ql_toeplitz_l11(col, lam)
+        finally:
+            _lib.check(lib.ila_ql_set_cold_start(1))
+            _lib.check(lib.ila_ql_set_shifts_per_thread(0))
+        L0, st0 = out[(0, 1)]
+        Lo, sto = tq.ql_toeplitz_l11(col, lam)
+        assert np.array_equal(st0, sto)
+        for k, (L, st) in out.items():
+            assert np.array_equal(st, st0), k
+            ok = st0 == 0
+            err = np.abs(L[ok] - Lo[ok])
+            scale = abs(col[0])
+            assert err.max() <= 2e-12 * max(scale, 1.0), (k, err.max())
+            big = np.abs(Lo[ok]) >= 0.05 * scale
+            assert (err[big] / np.abs(Lo[ok][big])).max() <= 1e-11, k
 
 
 def test_compact_real_form_matches_complex_form(ila):
