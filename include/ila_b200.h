@@ -302,6 +302,28 @@ int ila_ql_blocktri_l11_c64_dev(int n, const ila_c64 *c, const ila_c64 *a, const
                                 int64_t batch, double atol, int maxit, ila_c64 *d_L11, int32_t *d_iters, int32_t *d_status,
                                 void *stream);
 
+/* The WHOLE block factorization and Q'b — what the reference's QL object holds (src/infql.jl:199-204) and what
+ * lmul!(Q', b) computes (src/infql.jl:213-243); compared in test/test_periodic.jl:12-18.  Same operator description.  With
+ * N = max(n_du + 1, n_d, n_dl) head block columns (src/infql.jl:190):
+ *   tail_opt      batch x (2n x 3n), column-major: P = the panel [c a b; 0 d e] after ql! with P[1:n,1:2n] = (d~, e~)
+ *                 (:175-176).  Tail block column of the ∞ factors = [P[1:n,2n+1:3n]; P[n+1:2n,2n+1:3n]; P[n+1:2n,n+1:2n];
+ *                 P[n+1:2n,1:n]] (:203); the rows below the head are P[n+1:2n,1:2n] and P[n+1:2n,1:n] (:199-200)
+ *   tau_tail_opt  batch x n: τ of every tail block column (F.τ[n+1:2n], :176)
+ *   head_opt      batch x (Nn x Nn), column-major: ql! of the head with its last block row replaced by (d~, e~) (:197-198)
+ *   head_tau_opt  batch x Nn
+ *   qtb_opt       batch x nout: (Q'b)[1:nout] for b = rhs[0..nb) (nb <= 16, nout <= 16 + 2n + 1), shared by the batch
+ * Real eltype: bit-exact against the oracle; NaN where status != 0. */
+int ila_ql_blocktri_factors_f64(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
+                                int n_d, const double *d_head, int n_du, const double *du_head, const double *energy,
+                                int64_t batch, double atol, int maxit, double *L11, double *tail_opt, double *tau_tail_opt,
+                                double *head_opt, double *head_tau_opt, int nb, const double *rhs, int64_t nout, double *qtb_opt,
+                                int32_t *iters, int32_t *status, int ngpus);
+int ila_ql_blocktri_factors_c64(int n, const ila_c64 *c, const ila_c64 *a, const ila_c64 *b, int n_dl, const ila_c64 *dl_head,
+                                int n_d, const ila_c64 *d_head, int n_du, const ila_c64 *du_head, const ila_c64 *energy,
+                                int64_t batch, double atol, int maxit, ila_c64 *L11, ila_c64 *tail_opt, ila_c64 *tau_tail_opt,
+                                ila_c64 *head_opt, ila_c64 *head_tau_opt, int nb, const ila_c64 *rhs, int64_t nout,
+                                ila_c64 *qtb_opt, int32_t *iters, int32_t *status, int ngpus);
+
 /* ---- K8: adaptive reverse Cholesky  A = L'L  of ∞ symmetric tridiagonal operators ------------------
  * Replaces reversecholesky(::SymTridiagonal) -> LazySymTridiagonalReverseCholeskyFactors
  * (src/banded/infreversecholeskytridiagonal.jl:66-141): finite reverse Cholesky of the N x N section (:118-129), convergence

@@ -82,6 +82,12 @@ SIGNATURES = {
                                                    C.c_int, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "ila_qr_almostbanded_solve_f64": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int, _vp, C.c_double, C.c_int,
                                                 C.c_int64, _vp, _vp, _vp, _vp, C.c_int]),
+    "ila_ql_blocktri_factors_f64": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int64,
+                                              C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int64, _vp, _vp, _vp,
+                                              C.c_int]),
+    "ila_ql_blocktri_factors_c64": (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int64,
+                                              C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int64, _vp, _vp, _vp,
+                                              C.c_int]),
     "ila_release": (C.c_int, []),
     "ila_ql_finite_section_f64": (C.c_int, [C.c_int, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp, C.c_int64, C.c_double, C.c_int64,
                                             _vp, _vp, _vp, _vp, _vp, C.c_int]),

@@ -268,14 +268,80 @@ class QLHessenberg:
 
 
 class _BlockQL:
-    def __init__(self, l11):
-        self._l11 = l11
+    """Result of ql on a block-tridiagonal perturbed Toeplitz operator: the reference's
+    QL(_BlockSkylineMatrix(Vcat(head data, Fill(tail column))), Vcat(F.τ, Fill(τ))) (src/infql.jl:199-204), laid out from the
+    records the library returns (factored head, its τ, the fixed point P, τ tail).  `.factors[i, j]`, `.tau[k]`, `.L[i, j]`
+    are index arithmetic on those records (no floating-point work here); `.Q[i, j]` = conj((Q'e_i)[j]) runs the library's
+    block Q'b (lmul!(Q', b), src/infql.jl:213-243; getindex :245-246) for i <= 16."""
+
+    def __init__(self, rec, args):
+        self._rec, self._args = rec, args
+        self.n, self.N = rec["n"], rec["N"]
+        self._l11 = rec["L11"]
         self.L = _OneBased(self._L)
+        self.Q = _OneBased(self._Q)
+        self.factors = _OneBased(self._F)
+        self.tau = _OneBased1(self._tau)
+        self._qrows = {}
+
+    def _P(self, I, J):
+        n = self.n
+        return self._rec["tail"][(I - 1) * n:I * n, (J - 1) * n:J * n]
+
+    def _F(self, i, j):
+        n, N = self.n, self.N
+        hn = N * n
+        I, J = (i - 1) // n + 1, (j - 1) // n + 1              # block indices
+        r, c = (i - 1) % n, (j - 1) % n
+        if i <= hn and j <= hn:
+            return self._rec["head"][i - 1, j - 1]
+        if J <= N:                                              # rows below the head (src/infql.jl:199-200)
+            if I == N + 1 and J == N - 1:
+                return self._P(2, 1)[r, c]
+            if I == N + 1 and J == N:
+                return self._P(2, 2)[r, c]
+            if I == N + 2 and J == N:
+                return self._P(2, 1)[r, c]
+            return 0.0
+        d = I - J                                               # Toeplitz tail column (:203)
+        if d == -1:
+            return self._P(1, 3)[r, c]
+        if d == 0:
+            return self._P(2, 3)[r, c]
+        if d == 1:
+            return self._P(2, 2)[r, c]
+        if d == 2:
+            return self._P(2, 1)[r, c]
+        return 0.0
+
+    def _tau(self, k):
+        hn = self.N * self.n
+        return self._rec["head_tau"][k - 1] if k <= hn else self._rec["tau_tail"][(k - 1) % self.n]
 
     def _L(self, i, j):
-        if (i, j) == (1, 1):
-            return self._l11
-        raise IndexError("only L[1,1] is materialised for block operators")
+        return self._F(i, j) if i >= j else 0.0
+
+    def _Q(self, i, j):
+        if i > 16:
+            raise IndexError("Q[i, j] is served by the library's Q'b for i <= 16")
+        if i not in self._qrows:
+            e = np.zeros(i)
+            e[i - 1] = 1.0
+            dlh, dh, duh, c, a, b, shift = self._args
+            o = _b.ql_blocktri_factors(dlh, dh, duh, c, a, b, [shift], rhs=e, nout=i + 2 * self.n - 1)
+            self._qrows[i] = np.conj(o["qtb"][0])
+        row = self._qrows[i]
+        return row[j - 1] if j <= row.size else 0.0
+
+
+class _OneBased1:
+    def __init__(self, fn):
+        self._fn = fn
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return np.array([self._fn(a) for a in range(k.start or 1, k.stop + 1)])
+        return self._fn(k)
 
 
 class BlockTridiagonal:
@@ -311,9 +377,11 @@ def ql(A, branch=1):
     """ql(A; branch) for ∞ Toeplitz / perturbed Toeplitz (u == 1) and block-tridiagonal perturbed Toeplitz operators."""
     if isinstance(A, BlockTridiagonal):
         dlh, dh, duh = A._heads()
-        L, it, st = _b.ql_blocktri_l11(dlh, dh, duh, A.dl[1], A.d[1], A.du[1], [A.shift])
-        _raise_status(st[0], "ql(BlockTridiagonal)")
-        return _BlockQL(complex(L[0]) if np.iscomplexobj(L) else float(L[0]))
+        o = _b.ql_blocktri_factors(dlh, dh, duh, A.dl[1], A.d[1], A.du[1], [A.shift])
+        _raise_status(o["status"][0], "ql(BlockTridiagonal)")
+        rec = {k: (v[0] if isinstance(v, np.ndarray) else v) for k, v in o.items() if k != "qtb"}
+        rec["L11"] = complex(rec["L11"]) if np.iscomplexobj(o["L11"]) else float(rec["L11"])
+        return _BlockQL(rec, (dlh, dh, duh, A.dl[1], A.d[1], A.du[1], A.shift))
     l, u = A.bandwidths
     if u != 1:
         raise NotImplementedError("only u == 1 (ql_pruneband is undefined upstream)")

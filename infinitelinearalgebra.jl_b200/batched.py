@@ -215,6 +215,51 @@ def ql_blocktri_l11(dl_head, d_head, du_head, c, a, b, energies, atol=1e-10, max
     return L11.reshape(shape), iters.reshape(shape), status.reshape(shape)
 
 
+def ql_blocktri_factors(dl_head, d_head, du_head, c, a, b, energies, atol=1e-10, maxit=1_000_000, ngpus=1, rhs=None,
+                        nout=None):
+    """The whole factorization of ql(A - x*I) per energy — what the reference's QL object holds (src/infql.jl:199-204) — and,
+    with `rhs`, (Q'rhs)[1:nout] (lmul!(Q', b), src/infql.jl:213-243).  Returns a dict: L11, tail (…, 2n, 3n) = P,
+    tau_tail (…, n), head (…, Nn, Nn) factored head, head_tau (…, Nn), qtb (…, nout) or None, iters, status, n, N."""
+    mats = [c, a, b] + list(dl_head or []) + list(d_head or []) + list(du_head or [])
+    cplx = np.iscomplexobj(np.asarray(energies)) or any(np.iscomplexobj(np.asarray(m)) for m in mats) or \
+        (rhs is not None and np.iscomplexobj(np.asarray(rhs)))
+    dt = np.complex128 if cplx else np.float64
+    c = np.asarray(c, dtype=dt)
+    n = c.shape[0]
+    flat = lambda m: np.ascontiguousarray(np.asarray(m, dtype=dt).reshape(-1, order="F"))
+    cc, aa, bb = flat(c), flat(a), flat(b)
+    dlh, ndl = _blocks(dl_head, n, dt)
+    dh, nd = _blocks(d_head, n, dt)
+    duh, ndu = _blocks(du_head, n, dt)
+    N = max(ndu + 1, nd, ndl)
+    hn = N * n
+    shape = np.asarray(energies).shape
+    e = np.ascontiguousarray(np.asarray(energies, dtype=dt).reshape(-1))
+    m = e.size
+    L11 = np.empty(m, dtype=dt)
+    tail = np.empty((m, 3 * n, 2 * n), dtype=dt)            # column-major 2n x 3n per energy
+    tau_tail = np.empty((m, n), dtype=dt)
+    head = np.empty((m, hn, hn), dtype=dt)
+    head_tau = np.empty((m, hn), dtype=dt)
+    iters = np.empty(m, dtype=np.int32)
+    status = np.empty(m, dtype=np.int32)
+    qtb = rb = None
+    nb = 0
+    if rhs is not None:
+        rb = np.ascontiguousarray(np.asarray(rhs, dtype=dt).reshape(-1))
+        nb = rb.size
+        nout = int(nout if nout is not None else nb + 2 * n - 1)
+        qtb = np.empty((m, nout), dtype=dt)
+    fn = lib().ila_ql_blocktri_factors_c64 if cplx else lib().ila_ql_blocktri_factors_f64
+    check(fn(n, ptr(cc), ptr(aa), ptr(bb), ndl, ptr(dlh), nd, ptr(dh), ndu, ptr(duh), ptr(e), m, float(atol), int(maxit),
+             ptr(L11), ptr(tail), ptr(tau_tail), ptr(head), ptr(head_tau), nb, ptr(rb), int(nout or 0), ptr(qtb), ptr(iters),
+             ptr(status), ngpus))
+    return dict(L11=L11.reshape(shape), tail=np.swapaxes(tail, 1, 2).reshape(shape + (2 * n, 3 * n)),
+                tau_tail=tau_tail.reshape(shape + (n,)), head=np.swapaxes(head, 1, 2).reshape(shape + (hn, hn)),
+                head_tau=head_tau.reshape(shape + (hn,)), qtb=None if qtb is None else qtb.reshape(shape + (nout,)),
+                iters=iters.reshape(shape), status=status.reshape(shape), n=n, N=N)
+
+
 def periodic_schrodinger_blocks():
     """Blocks of examples/periodicschrodinger.jl:8-17: (dl_head, d_head, du_head, c, a, b)."""
     c = np.array([[0.0, 1.0], [0.0, 0.0]])

@@ -1343,7 +1343,99 @@ static int blocktri_host(int n, const T *c, const T *a, const T *b, int n_dl, co
     return 0;
 }
 
+// the whole block factorization + Q'b (host entry): per energy the fixed point P (2n x 3n), τ tail, the factored head
+// (Nn x Nn), its τ and, for a finitely supported b, (Q'b)[1:nout]
+template <typename T>
+static int blocktri_factors_host(int n, const T *c, const T *a, const T *b, int n_dl, const T *dl_head, int n_d, const T *d_head,
+                                 int n_du, const T *du_head, const T *energy, int64_t batch, double atol, int maxit, T *L11,
+                                 T *tail, T *tau_tail, T *head, T *head_tau, int nb, const T *rhs, int64_t nout, T *qtb,
+                                 int32_t *iters, int32_t *status, int ngpus)
+{
+    if (batch < 0 || (batch > 0 && (!energy || !L11 || !iters || !status))) return set_error(ILA_ERR_ARG, "ql_blocktri_factors: bad arguments");
+    if (qtb && (!rhs || nb < 1 || nb > kBtMaxB || nout < 1 || nout > kBtMaxB + 2 * n + 1))
+        return set_error(ILA_ERR_ARG, "ql_blocktri_factors: Q'b needs 1 <= nb <= 16 and 1 <= nout <= 16 + 2n + 1");
+    BlockTriParamsT<T> P;
+    int rc = blocktri_params<T>(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, atol, maxit, &P);
+    if (rc) return rc;
+    int N = n_du + 1;
+    if (n_d > N) N = n_d;
+    if (n_dl > N) N = n_dl;
+    const int64_t hn = (int64_t)N * n, tl = 6 * (int64_t)n * n;
+    int G = 0;
+    if ((rc = resolve_ngpus(ngpus, &G))) return rc;
+    if (batch == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    HostGuard guard(G);
+    if (G > batch) G = (int)batch;
+    const int64_t per = (batch + G - 1) / G;
+    for (int d = 0; d < G; d++) {
+        const int64_t lo = d * per, cnt = (lo + per <= batch ? per : batch - lo);
+        if (cnt <= 0) continue;
+        const int pd = phys(d, G);
+        if ((rc = dev_init(pd))) return rc;
+        T *d_e, *d_L;
+        int32_t *d_it, *d_st;
+        BlockTriOutT<T> O;
+        if ((rc = dev_buf_t(pd, 0, (size_t)cnt, &d_e))) return rc;
+        if ((rc = dev_buf_t(pd, 1, (size_t)cnt, &d_L))) return rc;
+        if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
+        if ((rc = dev_buf_t(pd, 3, (size_t)cnt, &d_it))) return rc;
+        if (tail && (rc = dev_buf_t(pd, 4, (size_t)cnt * tl, &O.tail))) return rc;
+        if (tau_tail && (rc = dev_buf_t(pd, 5, (size_t)cnt * n, &O.tau_tail))) return rc;
+        if (head && (rc = dev_buf_t(pd, 6, (size_t)cnt * hn * hn, &O.head))) return rc;
+        if (head_tau && (rc = dev_buf_t(pd, 7, (size_t)cnt * hn, &O.head_tau))) return rc;
+        if (qtb) {
+            if ((rc = dev_buf_t(pd, 8, (size_t)cnt * nout, &O.qtb))) return rc;
+            O.nb = nb;
+            O.nout = (int)nout;
+            for (int k = 0; k < kBtMaxB; k++) O.b[k] = k < nb ? rhs[k] : T{};
+        }
+        cudaStream_t s = g_dev[pd].stream;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(d_e, energy + lo, sizeof(T) * cnt, cudaMemcpyHostToDevice, s));
+        if ((rc = launch_ql_blocktri_any(P, d_e, cnt, d_L, d_it, d_st, s, O))) return rc;
+        ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + lo, d_L, sizeof(T) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(iters + lo, d_it, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+        ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
+        if (tail) ILA_CUDA_CHECK(cudaMemcpyAsync(tail + lo * tl, O.tail, sizeof(T) * cnt * tl, cudaMemcpyDeviceToHost, s));
+        if (tau_tail) ILA_CUDA_CHECK(cudaMemcpyAsync(tau_tail + lo * n, O.tau_tail, sizeof(T) * cnt * n, cudaMemcpyDeviceToHost, s));
+        if (head) ILA_CUDA_CHECK(cudaMemcpyAsync(head + lo * hn * hn, O.head, sizeof(T) * cnt * hn * hn, cudaMemcpyDeviceToHost, s));
+        if (head_tau) ILA_CUDA_CHECK(cudaMemcpyAsync(head_tau + lo * hn, O.head_tau, sizeof(T) * cnt * hn, cudaMemcpyDeviceToHost, s));
+        if (qtb) ILA_CUDA_CHECK(cudaMemcpyAsync(qtb + lo * nout, O.qtb, sizeof(T) * cnt * nout, cudaMemcpyDeviceToHost, s));
+    }
+    for (int d = 0; d < G; d++) {
+        const int pd = phys(d, G);
+        if (!g_dev[pd].init) continue;
+        ILA_CUDA_CHECK(cudaSetDevice(pd));
+        ILA_CUDA_CHECK(cudaStreamSynchronize(g_dev[pd].stream));
+    }
+    guard.done = true;
+    ILA_CUDA_CHECK(cudaSetDevice(g_base_dev));
+    return 0;
+}
+
 extern "C" {
+
+int ila_ql_blocktri_factors_f64(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
+                                int n_d, const double *d_head, int n_du, const double *du_head, const double *energy,
+                                int64_t batch, double atol, int maxit, double *L11, double *tail_opt, double *tau_tail_opt,
+                                double *head_opt, double *head_tau_opt, int nb, const double *rhs, int64_t nout, double *qtb_opt,
+                                int32_t *iters, int32_t *status, int ngpus)
+{
+    return blocktri_factors_host<double>(n, c, a, b, n_dl, dl_head, n_d, d_head, n_du, du_head, energy, batch, atol, maxit, L11,
+                                         tail_opt, tau_tail_opt, head_opt, head_tau_opt, nb, rhs, nout, qtb_opt, iters, status, ngpus);
+}
+
+int ila_ql_blocktri_factors_c64(int n, const ila_c64 *c, const ila_c64 *a, const ila_c64 *b, int n_dl, const ila_c64 *dl_head,
+                                int n_d, const ila_c64 *d_head, int n_du, const ila_c64 *du_head, const ila_c64 *energy,
+                                int64_t batch, double atol, int maxit, ila_c64 *L11, ila_c64 *tail_opt, ila_c64 *tau_tail_opt,
+                                ila_c64 *head_opt, ila_c64 *head_tau_opt, int nb, const ila_c64 *rhs, int64_t nout,
+                                ila_c64 *qtb_opt, int32_t *iters, int32_t *status, int ngpus)
+{
+    return blocktri_factors_host<cplx>(n, (const cplx *)c, (const cplx *)a, (const cplx *)b, n_dl, (const cplx *)dl_head, n_d,
+                                       (const cplx *)d_head, n_du, (const cplx *)du_head, (const cplx *)energy, batch, atol, maxit,
+                                       (cplx *)L11, (cplx *)tail_opt, (cplx *)tau_tail_opt, (cplx *)head_opt, (cplx *)head_tau_opt,
+                                       nb, (const cplx *)rhs, nout, (cplx *)qtb_opt, iters, status, ngpus);
+}
 
 int ila_ql_blocktri_l11_f64_dev(int n, const double *c, const double *a, const double *b, int n_dl, const double *dl_head,
                                 int n_d, const double *d_head, int n_du, const double *du_head, const double *d_energy,

@@ -213,15 +213,29 @@ struct BlockTriParamsT {
     T d_head[kBtMaxHead][kBtMaxN * kBtMaxN];
     T du_head[kBtMaxHead][kBtMaxN * kBtMaxN];
 };
+// optional outputs of K6: the whole factorization (what the reference's QL object holds, src/infql.jl:203-204) and Q'b
+constexpr int kBtMaxB = 16;
+template <typename T>
+struct BlockTriOutT {
+    T *tail = nullptr;       // batch x (2n x 3n), column-major: the fixed point P after ql! with P[1:n,1:2n] = (d~, e~)  (:175-176)
+    T *tau_tail = nullptr;   // batch x n: F.τ[n+1:2n]
+    T *head = nullptr;       // batch x (Nn x Nn), column-major: the factored head (L in the lower triangle, reflectors above)
+    T *head_tau = nullptr;   // batch x Nn
+    T *qtb = nullptr;        // batch x nout: (Q'b)[1:nout] for the finitely supported right-hand side b  (:213-243)
+    int nb = 0, nout = 0;
+    T b[kBtMaxB];
+};
 using BlockTriParams = BlockTriParamsT<double>;
 using BlockTriParamsC = BlockTriParamsT<cplx>;
 int launch_ql_blocktri(const BlockTriParams &P, const double *d_energy, int64_t batch, double *d_L11, int32_t *d_iters,
-                       int32_t *d_status, cudaStream_t s);
+                       int32_t *d_status, const BlockTriOutT<double> &O, cudaStream_t s);
 int launch_ql_blocktri_c(const BlockTriParamsC &P, const cplx *d_energy, int64_t batch, cplx *d_L11, int32_t *d_iters,
-                         int32_t *d_status, cudaStream_t s);
+                         int32_t *d_status, const BlockTriOutT<cplx> &O, cudaStream_t s);
 static inline int launch_ql_blocktri_any(const BlockTriParams &P, const double *e, int64_t batch, double *L, int32_t *it,
-                                         int32_t *st, cudaStream_t s) { return launch_ql_blocktri(P, e, batch, L, it, st, s); }
+                                         int32_t *st, cudaStream_t s, const BlockTriOutT<double> &O = BlockTriOutT<double>{})
+{ return launch_ql_blocktri(P, e, batch, L, it, st, O, s); }
 static inline int launch_ql_blocktri_any(const BlockTriParamsC &P, const cplx *e, int64_t batch, cplx *L, int32_t *it,
-                                         int32_t *st, cudaStream_t s) { return launch_ql_blocktri_c(P, e, batch, L, it, st, s); }
+                                         int32_t *st, cudaStream_t s, const BlockTriOutT<cplx> &O = BlockTriOutT<cplx>{})
+{ return launch_ql_blocktri_c(P, e, batch, L, it, st, O, s); }
 
 } // namespace ila

@@ -136,7 +136,7 @@ __device__ __forceinline__ void dense_ql(T (&X)[R][C], T (&tau)[(R < C ? R : C)]
 template <typename T, int n>
 __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParamsT<T> P, const T *__restrict__ energy, int64_t batch,
                                                              T *__restrict__ L11, int32_t *__restrict__ iters,
-                                                             int32_t *__restrict__ status)
+                                                             int32_t *__restrict__ status, BlockTriOutT<T> O)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= batch) return;
@@ -169,9 +169,9 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParamsT<T> 
     int32_t st = ILA_NOT_CONVERGED;
     int it = 0;
     T dn[n][n], en[n][n];
+    T X[2 * n][3 * n];      // the panel of the last iteration: with (d~, e~) written back it is the reference's P (src/infql.jl:175-176)
+    T tau[2 * n];
     for (it = 1; it <= P.maxit; it++) {
-        T X[2 * n][3 * n];
-        T tau[2 * n];
 #pragma unroll
         for (int i = 0; i < n; i++)
 #pragma unroll
@@ -266,8 +266,77 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParamsT<T> 
             }
         // dense QL of the hn x hn head (runtime size, local memory; executed once per energy)
         auto at = [&](int i, int j) -> T & { return H[i][j]; };
-        for (int k = hn; k >= (is_cplx<T>::value ? 1 : 2); k--) ql_step<T>(at, k, k - 1);
+        T htau[HM];
+        for (int k = 0; k < HM; k++) htau[k] = bzero<T>();
+        for (int k = hn; k >= (is_cplx<T>::value ? 1 : 2); k--) htau[k - 1] = ql_step<T>(at, k, k - 1);
         l11 = H[0][0];
+        // ---- the rest of the factorization (src/infql.jl:199-204): P = X with (d~, e~) in its first block row, τ tail, head
+#pragma unroll
+        for (int i = 0; i < n; i++)
+#pragma unroll
+            for (int j = 0; j < n; j++) {
+                X[i][j] = dn[i][j];
+                X[i][n + j] = en[i][j];
+            }
+        if (O.tail) {
+            T *o = O.tail + idx * (int64_t)(6 * n * n);
+#pragma unroll
+            for (int j = 0; j < 3 * n; j++)
+#pragma unroll
+                for (int i = 0; i < 2 * n; i++) o[i + j * 2 * n] = X[i][j];
+        }
+        if (O.tau_tail)
+#pragma unroll
+            for (int k = 0; k < n; k++) O.tau_tail[idx * n + k] = tau[n + k];
+        if (O.head) {
+            T *o = O.head + idx * (int64_t)hn * hn;
+            for (int j = 0; j < hn; j++)
+                for (int i = 0; i < hn; i++) o[i + j * hn] = H[i][j];
+        }
+        if (O.head_tau)
+            for (int k = 0; k < hn; k++) O.head_tau[idx * (int64_t)hn + k] = htau[k];
+        if (O.qtb) {
+            // ---- Q'b for a finitely supported b (lmul!(Q', b), src/infql.jl:213-243): reflector k acts on rows
+            //      max(1, k-u)..k with u = 2n-1 (the reference hard-codes 2u_block+1 = 3, its "todo: generalize" — the same
+            //      number for the n = 2 blocks of its tests); columns k <= Nn take their reflector from the factored head,
+            //      later ones from the Toeplitz tail column [P[Block(1,3)]; P[Block(2,3)]] with τ tail.
+            constexpr int KW = kBtMaxB + 2 * n + 1;
+            constexpr int u = 2 * n - 1;
+            T t[KW];
+            for (int k = 0; k < KW; k++) t[k] = (k < O.nb) ? O.b[k] : bzero<T>();
+            int kmax = O.nb + u;
+            if (kmax > KW) kmax = KW;
+            for (int k = kmax; k >= 1; k--) {          // 1-based column / row index
+                const int ilo = (k - u > 1) ? k - u : 1;
+                const int jc = (k - 1) % n;            // column inside its block (0-based)
+                const int r0 = ((k - 1) / n) * n;      // first row (0-based) of the diagonal block of column k
+                auto F = [&](int i) -> T {              // Afactors[i, k], i < k, 1-based
+                    if (k <= hn) return H[i - 1][k - 1];
+                    const int r = i - 1;
+                    if (r >= r0) return X[n + (r - r0)][2 * n + jc];          // P[Block(2,3)], strictly above the diagonal
+                    const int rr = r - (r0 - n);
+                    return (rr >= 0) ? X[rr][2 * n + jc] : bzero<T>();          // P[Block(1,3)]
+                };
+                const T tk = (k <= hn) ? htau[k - 1] : tau[n + jc];
+                T vB = t[k - 1];
+                for (int i = ilo; i <= k - 1; i++) vB = badd(vB, bmul(bconj(F(i)), t[i - 1]));
+                vB = bmul(bconj(tk), vB);
+                t[k - 1] = bsub(t[k - 1], vB);
+                for (int i = ilo; i <= k - 1; i++) t[i - 1] = bsub(t[i - 1], bmul(F(i), vB));
+            }
+            for (int k = 0; k < O.nout; k++) O.qtb[idx * (int64_t)O.nout + k] = (k < KW) ? t[k] : bzero<T>();
+        }
+    } else {
+        T qn;
+        bset_real(qn, __longlong_as_double(0x7ff8000000000000LL));
+        if (is_cplx<T>::value) qn = bmul(qn, qn);
+        int N2 = N;
+        const int hn = N2 * n;
+        if (O.tail) for (int k = 0; k < 6 * n * n; k++) O.tail[idx * (int64_t)(6 * n * n) + k] = qn;
+        if (O.tau_tail) for (int k = 0; k < n; k++) O.tau_tail[idx * n + k] = qn;
+        if (O.head) for (int k = 0; k < hn * hn; k++) O.head[idx * (int64_t)hn * hn + k] = qn;
+        if (O.head_tau) for (int k = 0; k < hn; k++) O.head_tau[idx * (int64_t)hn + k] = qn;
+        if (O.qtb) for (int k = 0; k < O.nout; k++) O.qtb[idx * (int64_t)O.nout + k] = qn;
     }
     L11[idx] = l11;
     iters[idx] = it > P.maxit ? P.maxit : it;
@@ -276,16 +345,16 @@ __global__ void __launch_bounds__(64) ql_blocktri_l11_kernel(BlockTriParamsT<T> 
 
 template <typename T>
 static int launch_ql_blocktri_t(const BlockTriParamsT<T> &P, const T *d_energy, int64_t batch, T *d_L11, int32_t *d_iters,
-                                int32_t *d_status, cudaStream_t s)
+                                int32_t *d_status, const BlockTriOutT<T> &O, cudaStream_t s)
 {
     if (batch <= 0) return 0;
     const int threads = 64;
     const unsigned blocks = (unsigned)((batch + threads - 1) / threads);
     switch (P.n) {
-    case 1: ql_blocktri_l11_kernel<T, 1><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
-    case 2: ql_blocktri_l11_kernel<T, 2><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
-    case 3: ql_blocktri_l11_kernel<T, 3><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
-    case 4: ql_blocktri_l11_kernel<T, 4><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status); break;
+    case 1: ql_blocktri_l11_kernel<T, 1><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status, O); break;
+    case 2: ql_blocktri_l11_kernel<T, 2><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status, O); break;
+    case 3: ql_blocktri_l11_kernel<T, 3><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status, O); break;
+    case 4: ql_blocktri_l11_kernel<T, 4><<<blocks, threads, 0, s>>>(P, d_energy, batch, d_L11, d_iters, d_status, O); break;
     default: return set_error(ILA_ERR_UNSUPPORTED, "ql_blocktri: block size n must be in 1..4");
     }
     count_launch();
@@ -294,14 +363,14 @@ static int launch_ql_blocktri_t(const BlockTriParamsT<T> &P, const T *d_energy, 
 }
 
 int launch_ql_blocktri(const BlockTriParams &P, const double *d_energy, int64_t batch, double *d_L11, int32_t *d_iters,
-                       int32_t *d_status, cudaStream_t s)
+                       int32_t *d_status, const BlockTriOutT<double> &O, cudaStream_t s)
 {
-    return launch_ql_blocktri_t<double>(P, d_energy, batch, d_L11, d_iters, d_status, s);
+    return launch_ql_blocktri_t<double>(P, d_energy, batch, d_L11, d_iters, d_status, O, s);
 }
 int launch_ql_blocktri_c(const BlockTriParamsC &P, const cplx *d_energy, int64_t batch, cplx *d_L11, int32_t *d_iters,
-                         int32_t *d_status, cudaStream_t s)
+                         int32_t *d_status, const BlockTriOutT<cplx> &O, cudaStream_t s)
 {
-    return launch_ql_blocktri_t<cplx>(P, d_energy, batch, d_L11, d_iters, d_status, s);
+    return launch_ql_blocktri_t<cplx>(P, d_energy, batch, d_L11, d_iters, d_status, O, s);
 }
 
 } // namespace ila

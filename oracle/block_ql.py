@@ -149,7 +149,7 @@ def blocktri_ql_l11(dl_head, d_head, du_head, c, a, b, shift=0.0, atol=1e-10, ma
         H[(N - 1) * n:, (N - 2) * n:(N - 1) * n] = X[:n, :n]
     H[(N - 1) * n:, (N - 1) * n:] = X[:n, n:2 * n]
     F, tau = dense_ql_seq(H)
-    return F[0, 0], iters, STATUS_OK, dict(head_factors=F, head_tau=tau, tail_X=X, tail_tau=tau_tail)
+    return F[0, 0], iters, STATUS_OK, dict(head_factors=F, head_tau=tau, tail_X=X, tail_tau=tau_tail, n=n, N=N)
 
 
 def periodic_schrodinger(x):
@@ -160,3 +160,65 @@ def periodic_schrodinger(x):
     a0 = a.copy()
     a0[0, 0] = 2.0
     return blocktri_ql_l11([c], [a0], [b], c, a, b, shift=x)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the whole ∞ factorization object (src/infql.jl:197-204) and lmul!(Q', b) (src/infql.jl:213-243), on a leading section
+# ----------------------------------------------------------------------------------------------------------------
+
+def assemble_inf_factors(ex, n, N, nblocks):
+    """Leading (nblocks*n)^2 section of the ∞ `factors` and the first nblocks*n entries of `τ` of
+    QL(_BlockSkylineMatrix(Vcat(BB.data, Fill(tail column))), Vcat(F.τ, Fill(τ))) (src/infql.jl:199-204) from
+    ex = dict(head_factors, head_tau, tail_X, tail_tau) — block bandwidths (2, 1)."""
+    H, ht, X, tt = ex["head_factors"], ex["head_tau"], ex["tail_X"], ex["tail_tau"]
+    dt = np.result_type(H, X)
+    M = nblocks * n
+    F = np.zeros((M + 3 * n, M + n), dtype=dt)
+    hn = N * n
+    F[:hn, :hn] = H
+    P = lambda I, J: X[(I - 1) * n:I * n, (J - 1) * n:J * n]          # P[Block(I, J)], 1-based
+    blk = lambda I, J: (slice((I - 1) * n, I * n), slice((J - 1) * n, J * n))
+    if N >= 2:
+        F[blk(N + 1, N - 1)] = P(2, 1)                                 # BB[Block(N+1), Block.(N-1:N)] = P[Block(2), Block.(1:2)]
+    F[blk(N + 1, N)] = P(2, 2)
+    F[blk(N + 2, N)] = P(2, 1)                                         # BB[Block(N+2), Block(N)] = P[Block(2), Block(1)]
+    for J in range(N + 1, nblocks + 1):                                # Toeplitz tail columns (:203)
+        F[blk(J - 1, J)] = P(1, 3)
+        F[blk(J, J)] = P(2, 3)
+        F[blk(J + 1, J)] = P(2, 2)
+        F[blk(J + 2, J)] = P(2, 1)
+    tau = np.concatenate([ht, np.tile(tt, nblocks - N + 1)])[:M]
+    return F[:M, :M], tau
+
+
+def qt_times_b(F, tau, b, n, nout):
+    """lmul!(Q', b) of src/infql.jl:213-243 on a section of the ∞ factors: k = last(colsupport(b)) + u : -1 : 1 with
+    u = 2n - 1 entries above the diagonal (the reference hard-codes 2u_block + 1 = 3: the same for its n = 2 tests)."""
+    u = 2 * n - 1
+    nb = len(b)
+    dt = np.result_type(F, np.asarray(b), np.float64)
+    t = np.zeros(F.shape[0], dtype=dt)
+    t[:nb] = b
+    for k in range(nb + u, 0, -1):
+        lo = max(1, k - u)
+        vB = t[k - 1]
+        for i in range(lo, k):
+            vB = vB + np.conj(F[i - 1, k - 1]) * t[i - 1]
+        vB = np.conj(tau[k - 1]) * vB
+        t[k - 1] = t[k - 1] - vB
+        for i in range(lo, k):
+            t[i - 1] = t[i - 1] - F[i - 1, k - 1] * vB
+    return t[:nout]
+
+
+def dense_Q_L(F, tau, n):
+    """Dense Q (leading rows) and L of a section of the ∞ factors: L = lower triangle, Q column i = conj(Q' e_i)."""
+    M = F.shape[0]
+    L = np.tril(F)
+    m = M - 3 * n                                                       # rows whose reflectors all lie inside the section
+    Q = np.zeros((m, m), dtype=np.result_type(F, np.float64))
+    for i in range(m):
+        e = np.zeros(i + 1)
+        e[i] = 1.0
+        Q[i, :] = np.conj(qt_times_b(F, tau, e, n, m))
+    return Q, L

@@ -105,3 +105,61 @@ def test_complex_eltype_vs_oracle(ila):
         r = bq.blocktri_ql_l11([c], [a0], [b], c, a, b, shift=x, maxit=5000)
         assert st[i] == r[2] == 0 and it[i] == r[1]
         assert abs(L[i] - r[0]) <= 1e-12 * abs(r[0])
+
+
+def test_block_factors_tau_and_qtb_vs_oracle(ila):
+    """Row a12 in full: head factors, head τ, fixed point P, τ tail (src/infql.jl:199-204) and Q'b (:213-243) for the
+    periodic Schrödinger operator over energies — real eltype bit-exact against the oracle; then the reference's own checks
+    (test/test_periodic.jl:12-18) through the interface mirror."""
+    from oracle import block_ql as bq
+    blocks = ila.periodic_schrodinger_blocks()
+    xs = np.concatenate([np.linspace(-0.95, 0.95, 9), np.linspace(2.25, 4.0, 8)])
+    rhs = np.array([1.0, -2.0, 0.5])
+    o = ila.ql_blocktri_factors(*blocks, xs, rhs=rhs, nout=8)
+    assert np.all(o["status"] == 0)
+    for i, x in enumerate(xs):
+        L11, it, st, ex = bq.blocktri_ql_l11(*blocks, shift=x)
+        assert st == 0 and it == o["iters"][i]
+        assert np.array_equal(o["L11"][i], L11)
+        assert np.array_equal(o["tail"][i], ex["tail_X"]), f"fixed point P differs at x = {x}"
+        assert np.array_equal(o["tau_tail"][i], ex["tail_tau"])
+        assert np.array_equal(o["head"][i], ex["head_factors"])
+        assert np.array_equal(o["head_tau"][i], ex["head_tau"])
+        F, tau = bq.assemble_inf_factors(ex, 2, ex["N"], 12)
+        q = bq.qt_times_b(F, tau, rhs, 2, 8)
+        assert np.array_equal(o["qtb"][i], q), f"Q'b differs at x = {x}"
+
+
+def test_block_ql_object_like_test_periodic(ila):
+    """test/test_periodic.jl:5-18 through the interface mirror: factors / τ / L against the 100-block finite section,
+    Q[1:10,1:12] L[1:12,1:10] = A[1:10,1:10] (real, complex non-selfadjoint, degenerate and its adjoint-like case)."""
+    from ila_b200.api import BlockTridiagonal, I, ql
+    from oracle import block_ql as bq
+    c = np.array([[0., 1.], [0., 0.]]); a = np.array([[-1., 1.], [1., 1.]]); b = np.array([[0., 0.], [1., 0.]])
+    A = BlockTridiagonal(([c], c), ([a], a), ([b], b))
+    F = ql(A)
+    nb = 100
+    Ad = np.zeros((2 * nb, 2 * nb))
+    for k in range(nb):
+        Ad[2 * k:2 * k + 2, 2 * k:2 * k + 2] = a
+        if k + 1 < nb:
+            Ad[2 * k:2 * k + 2, 2 * k + 2:2 * k + 4] = b
+            Ad[2 * k + 2:2 * k + 4, 2 * k:2 * k + 2] = c
+    Ff, tf = bq.dense_ql_seq(Ad)
+    assert np.abs(F.factors[1:100, 1:100] - Ff[:100, :100]).max() < 1e-9        # Q̃.factors[1:100,1:100] ≈ Q.factors[1:100,1:100]
+    assert np.abs(F.tau[1:100] - tf[:100]).max() < 1e-9                          # Q̃.τ[1:100] ≈ Q.τ[1:100]
+    assert np.abs(F.L[1:100, 1:100] - np.tril(Ff)[:100, :100]).max() < 1e-9     # L ≈ L̃
+    assert np.abs(F.Q[1:10, 1:12] @ F.L[1:12, 1:10] - Ad[:10, :10]).max() < 1e-9
+    # complex non-selfadjoint (test_periodic.jl:20-26) and the degenerate real operator (:28-31)
+    c2, a2, b2 = np.array([[0, 0.5], [0, 0]]), np.array([[0, 2.0], [0.5, 0]]), np.array([[0, 0.0], [2.0, 0]])
+    for shift in (5j, 0.0):
+        A2 = BlockTridiagonal(([c2], c2), ([a2], a2), ([b2], b2)) - shift * I
+        F2 = ql(A2)
+        Ad2 = np.zeros((12, 12), dtype=complex)
+        for k in range(6):
+            Ad2[2 * k:2 * k + 2, 2 * k:2 * k + 2] = a2 - shift * np.eye(2)
+            if k + 1 < 6:
+                Ad2[2 * k:2 * k + 2, 2 * k + 2:2 * k + 4] = b2
+                Ad2[2 * k + 2:2 * k + 4, 2 * k:2 * k + 2] = c2
+        assert np.abs(F2.Q[1:10, 1:12] @ F2.L[1:12, 1:10] - Ad2[:10, :10]).max() < 1e-9
+    assert abs(F2.L[1, 1]) <= 1e-11                                              # degenerate

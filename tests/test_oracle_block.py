@@ -71,3 +71,42 @@ def test_complex_nonselfadjoint_shift():
         assert abs(np.imag(l11)) <= 1e-15 * abs(l11)          # the k = 1 reflector makes L[1,1] real
         # (the phase of the tail's fixed point is fixed by the iteration's start, so only |L[1,1]| is comparable)
         assert np.isclose(abs(l11), abs(F[0, 0]), rtol=0, atol=5e-9)
+
+
+def test_inf_block_factors_against_the_finite_section():
+    """test/test_periodic.jl:5-18: the ∞ factors assembled from (factored head, τ, fixed point P, τ tail) — the data the GPU
+    path exports — agree with the Householder QL of the 100-block finite section: factors[1:100,1:100], τ[1:100],
+    L[1:100,1:100], and Q[1:10,1:12] L[1:12,1:10] = A[1:10,1:10] (the reference compares with ≈, i.e. 1.5e-8; the fixed point
+    is iterated to 1e-10)."""
+    c = np.array([[0., 1.], [0., 0.]])
+    a = np.array([[-1., 1.], [1., 1.]])
+    b = np.array([[0., 0.], [1., 0.]])
+    L11, it, st, ex = bq.blocktri_ql_l11([c], [a], [b], c, a, b)
+    assert st == 0
+    F, tau = bq.assemble_inf_factors(ex, 2, ex["N"], 60)
+    nb = 100
+    A = np.zeros((2 * nb, 2 * nb))
+    for k in range(nb):
+        A[2 * k:2 * k + 2, 2 * k:2 * k + 2] = a
+        if k + 1 < nb:
+            A[2 * k:2 * k + 2, 2 * k + 2:2 * k + 4] = b
+            A[2 * k + 2:2 * k + 4, 2 * k:2 * k + 2] = c
+    Ff, tf = bq.dense_ql_seq(A)
+    assert np.abs(Ff[:100, :100] - F[:100, :100]).max() < 1e-9
+    assert np.abs(tf[:100] - tau[:100]).max() < 1e-9
+    assert np.abs(np.tril(Ff)[:100, :100] - np.tril(F)[:100, :100]).max() < 1e-9
+    Q, L = bq.dense_Q_L(F, tau, 2)
+    assert np.abs(Q[:10, :12] @ L[:12, :10] - A[:10, :10]).max() < 1e-9
+    # complex non-selfadjoint operator of test_periodic.jl:20-26
+    c2, a2, b2 = np.array([[0, 0.5], [0, 0]]), np.array([[0, 2.0], [0.5, 0]]), np.array([[0, 0.0], [2.0, 0]])
+    L11, it, st, ex = bq.blocktri_ql_l11([c2], [a2], [b2], c2, a2, b2, shift=5j)
+    assert st == 0
+    F, tau = bq.assemble_inf_factors(ex, 2, ex["N"], 30)
+    Q, L = bq.dense_Q_L(F, tau, 2)
+    A = np.zeros((20, 20), dtype=complex)
+    for k in range(10):
+        A[2 * k:2 * k + 2, 2 * k:2 * k + 2] = a2 - 5j * np.eye(2)
+        if k + 1 < 10:
+            A[2 * k:2 * k + 2, 2 * k + 2:2 * k + 4] = b2
+            A[2 * k + 2:2 * k + 4, 2 * k:2 * k + 2] = c2
+    assert np.abs(Q[:10, :12] @ L[:12, :10] - A[:10, :10]).max() < 1e-9
