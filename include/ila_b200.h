@@ -268,6 +268,18 @@ int ila_ql_toeplitz_solve_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 
 int ila_ql_toeplitz_solve_f64_dev(int l, int u, const double *a, const double *d_lambda, int64_t n, int branch_rank, int nb,
                                   const double *b, int64_t nout, double *d_work, double *d_x, int32_t *d_status, void *stream);
 
+/* Q b and Q'b alone for the ∞ Hessenberg Q of ql(A - lambda[i] I), Q = LowerHessenbergQ(Fill(q, ∞)), q the 2 x 2 block
+ * QLPackedQ(X[:, m-1:m], tau) (src/banded/infqltoeplitz.jl:63-64):
+ *   adjoint == 0:  y = Q b, materialize!(::MatLmulVec{HessenbergQLayout{'L'}}) (src/banded/hessenbergq.jl:111-123): for
+ *                  n = 1, 2, ...: x[n:n+1] <- q x[n:n+1], stopping once n > nb and norm(x[n:n+1]) <= 10 floatmin; nstop_opt[i]
+ *                  receives that n (0 when it did not happen within the nout entries asked for);
+ *   adjoint != 0:  y = Q'b, UpperHessenbergQ(adjoint.(q)) for n = nb, ..., 1 (:125-135), support nb + 1.
+ * b: nb <= 16 leading entries; y COLUMN-major n x nout, NaN rows where status != 0. */
+int ila_ql_toeplitz_applyq_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank, int adjoint,
+                               int nb, const ila_c64 *b, int64_t nout, ila_c64 *y, int64_t *nstop_opt, int32_t *status, int ngpus);
+int ila_ql_toeplitz_applyq_f64(int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank, int adjoint,
+                               int nb, const double *b, int64_t nout, double *y, int64_t *nstop_opt, int32_t *status, int ngpus);
+
 /* Perturbed-Toeplitz form of the solve: head / a / p as in ila_ql_perttoeplitz_l11_*.  Replaces the assembly of
  * ql_hessenberg! (src/infql.jl:70-93: head factors, the l' extension rows (Q∞')[2:l'+1,1:l'+1] T[l':2l',1:l'], Toeplitz tail
  * columns; Q = Vcat(LowerHessenbergQ(F.Q).q, F∞.q), src/banded/hessenbergq.jl:182-190) followed by F \ b

@@ -61,6 +61,8 @@ SIGNATURES = {
                                               C.c_int64, C.c_double, C.c_int, _vp, _vp, _vp, _vp]),
     "ila_ql_toeplitz_solve_c64": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int]),
     "ila_ql_toeplitz_solve_f64": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int]),
+    "ila_ql_toeplitz_applyq_c64": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
+    "ila_ql_toeplitz_applyq_f64": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, C.c_int]),
     "ila_ql_toeplitz_solve_c64_dev": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "ila_ql_toeplitz_solve_f64_dev": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "ila_ql_perttoeplitz_solve_c64": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int]),

@@ -258,7 +258,24 @@ class QLHessenberg:
         H2 = np.eye(2) - self.tau[1] * np.outer(vv, np.conj(vv))
         return H2 @ H1
 
+    def apply_Q(self, b, n=1000, adjoint=False):
+        """First n entries of `F.Q * b` (LowerHessenbergQ apply with its early exit, src/banded/hessenbergq.jl:111-123) or
+        `F.Q' * b` (:125-135) for a pure Toeplitz operator — on the device."""
+        bb = np.atleast_1d(np.asarray(b.head if isinstance(b, Vcat) else b))
+        if self._source is None or (isinstance(self._source[0], str) and self._source[0] == "pert"):
+            raise NotImplementedError("Q*b on the device needs a pure Toeplitz operator")
+        col, lam, branch = self._source
+        y, nstop, st = _b.ql_toeplitz_applyq(col, np.array([lam]), bb, int(n), adjoint=adjoint, branch_rank=branch)
+        _raise_status(st[0], "ql(A).Q * b")
+        return y[0]
+
     def _Q(self, i, j):
+        pure = self._source is not None and not (isinstance(self._source[0], str) and self._source[0] == "pert")
+        if pure and j <= 16 and self._head is None:
+            e = np.zeros(j)
+            e[j - 1] = 1.0
+            return self.apply_Q(e, n=max(i, j + 1))[i - 1]         # Q[i, j] = (Q e_j)[i], on the device
+        # perturbed operators (head blocks differ from the tail block): entry read-out from the 2 x 2 blocks
         n = max(i, j) + 2
         q = self._q2()
         Q = np.eye(n, dtype=q.dtype)

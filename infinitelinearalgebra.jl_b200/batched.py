@@ -95,6 +95,32 @@ def ql_toeplitz_solve(data_column, lambdas, b, nout: int, branch_rank: int = 1, 
     return np.ascontiguousarray(x.T).reshape(shape + (int(nout),)), status.reshape(shape)
 
 
+def ql_toeplitz_applyq(data_column, lambdas, b, nout: int, adjoint: bool = False, branch_rank: int = 1, ngpus: int = 1,
+                       real_path: bool | None = None):
+    """y = Q b (adjoint=False) or Q'b (adjoint=True), first `nout` entries, Q the ∞ Hessenberg Q of ql(A - λI) for every λ
+    (reference: LowerHessenbergQ / UpperHessenbergQ apply, src/banded/hessenbergq.jl:111-135).  Returns (y [λ-shape + (nout,)],
+    nstop [the n at which the reference's early exit fires, 0 if beyond nout; None for the adjoint], status)."""
+    col = np.asarray(data_column)
+    lam = np.asarray(lambdas)
+    bb = np.asarray(b)
+    if real_path is None:
+        real_path = not (np.iscomplexobj(col) or np.iscomplexobj(lam) or np.iscomplexobj(bb))
+    dt = np.float64 if real_path else np.complex128
+    col = np.ascontiguousarray(col, dtype=dt)
+    bb = np.ascontiguousarray(bb, dtype=dt).reshape(-1)
+    shape = lam.shape
+    lam = np.ascontiguousarray(lam, dtype=dt).reshape(-1)
+    n = lam.size
+    y = np.empty((int(nout), n), dtype=dt)
+    status = np.empty(n, dtype=np.int32)
+    nstop = None if adjoint else np.empty(n, dtype=np.int64)
+    fn = lib().ila_ql_toeplitz_applyq_f64 if real_path else lib().ila_ql_toeplitz_applyq_c64
+    check(fn(col.size - 2, 1, ptr(col), ptr(lam), n, branch_rank, 1 if adjoint else 0, bb.size, ptr(bb), int(nout), ptr(y),
+             ptr(nstop), ptr(status), ngpus))
+    return (np.ascontiguousarray(y.T).reshape(shape + (int(nout),)), None if nstop is None else nstop.reshape(shape),
+            status.reshape(shape))
+
+
 def ql_toeplitz_absl11_grid(data_column, x, y, branch_rank: int = 1, ngpus: int = 1, out=None):
     """The reference example's λ-grid loop (examples/toeplitz.jl:14-33): z[k, j] = abs(ql(A - (x[j] + i y[k]) I).L[1,1]),
     -1.0 where the QL factorization does not exist.  Shifts are formed on device."""

@@ -705,7 +705,8 @@ static int ql_solve_dev(bool real_path, int l, int u, const double *a, const dou
 }
 
 static int ql_solve_host(bool real_path, int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank,
-                         int nb, const double *b, int64_t nout, double *x, int32_t *status, int ngpus)
+                         int nb, const double *b, int64_t nout, double *x, int32_t *status, int ngpus, int mode = 0,
+                         int64_t *nstop = nullptr)
 {
     int rc = ql_solve_args(l, u, nb, n, nout);
     if (rc) return rc;
@@ -729,9 +730,12 @@ static int ql_solve_host(bool real_path, int l, int u, const double *a, const do
         if ((rc = dev_buf_t(pd, 1, (size_t)cnt * w, &d_L))) return rc;
         if ((rc = dev_buf_t(pd, 2, (size_t)cnt, &d_st))) return rc;
         if ((rc = dev_buf_t(pd, 4, (size_t)cnt * nout * w, &d_x))) return rc;
+        int64_t *d_ns = nullptr;
+        if (nstop && (rc = dev_buf_t(pd, 5, (size_t)cnt, &d_ns))) return rc;
         cudaStream_t s = g_dev[pd].stream;
         ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam, lambda + lo * w, sizeof(double) * cnt * w, cudaMemcpyHostToDevice, s));
-        if ((rc = launch_ql_toeplitz_solve_fused(real_path, l, u, a, branch_rank, d_lam, cnt, nb, b, nout, d_L, d_x, d_st, s))) return rc;
+        if ((rc = launch_ql_toeplitz_solve_fused(real_path, l, u, a, branch_rank, d_lam, cnt, nb, b, nout, d_L, d_x, d_st, s, mode, d_ns))) return rc;
+        if (nstop) ILA_CUDA_CHECK(cudaMemcpyAsync(nstop + lo, d_ns, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, s));
         ILA_CUDA_CHECK(cudaMemcpyAsync(status + lo, d_st, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, s));
         // x is column-major n x nout on the host, cnt x nout on the device: one strided copy
         ILA_CUDA_CHECK(cudaMemcpy2DAsync(x + lo * w, sizeof(double) * n * w, d_x, sizeof(double) * cnt * w,
@@ -758,6 +762,18 @@ int ila_ql_toeplitz_solve_f64(int l, int u, const double *a, const double *lambd
                               const double *b, int64_t nout, double *x, int32_t *status, int ngpus)
 {
     return ql_solve_host(true, l, u, a, lambda, n, branch_rank, nb, b, nout, x, status, ngpus);
+}
+int ila_ql_toeplitz_applyq_c64(int l, int u, const ila_c64 *a, const ila_c64 *lambda, int64_t n, int branch_rank, int adjoint,
+                               int nb, const ila_c64 *b, int64_t nout, ila_c64 *y, int64_t *nstop_opt, int32_t *status, int ngpus)
+{
+    return ql_solve_host(false, l, u, (const double *)a, (const double *)lambda, n, branch_rank, nb, (const double *)b, nout,
+                         (double *)y, status, ngpus, adjoint ? 1 : 2, adjoint ? nullptr : nstop_opt);
+}
+int ila_ql_toeplitz_applyq_f64(int l, int u, const double *a, const double *lambda, int64_t n, int branch_rank, int adjoint,
+                               int nb, const double *b, int64_t nout, double *y, int64_t *nstop_opt, int32_t *status, int ngpus)
+{
+    return ql_solve_host(true, l, u, a, lambda, n, branch_rank, nb, b, nout, y, status, ngpus, adjoint ? 1 : 2,
+                         adjoint ? nullptr : nstop_opt);
 }
 int ila_ql_toeplitz_solve_c64_dev(int l, int u, const ila_c64 *a, const ila_c64 *d_lambda, int64_t n, int branch_rank, int nb,
                                   const ila_c64 *b, int64_t nout, ila_c64 *d_work, ila_c64 *d_x, int32_t *d_status, void *stream)

@@ -18,7 +18,7 @@ int launch_ql_toeplitz_solve(bool real_path, int l, int nb, const double *b_host
                              const int32_t *d_status, int64_t nout, double *d_x, cudaStream_t stream);
 int launch_ql_toeplitz_solve_fused(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
                                    int64_t n, int nb, const double *b_host, int64_t nout, double *d_L11, double *d_x,
-                                   int32_t *d_status, cudaStream_t stream);
+                                   int32_t *d_status, cudaStream_t stream, int mode = 0, int64_t *d_nstop = nullptr);
 int launch_ql_toeplitz_grid(int l, int u, const double *a_host, int branch_rank, const double *d_gx, int nx,
                             const double *d_gy, int64_t ny, double *d_absout, cudaStream_t stream);
 int launch_ql_pert_head(bool real_path, int l, int p, const double *a_host, const double *head_host, const double *d_lambda,

@@ -439,13 +439,16 @@ struct TzSolveArgs {   // fused form: the K3 kernel runs the solve from its regi
     TzSolveParams S;
     int64_t nout;
     double *x;          // column-major n x nout, nullptr = not fused
+    int mode = 0;       // 0: x = L \ (Q'b)   1: x = Q'b   2: x = Q b  (LowerHessenbergQ apply with its early exit)
+    int64_t *nstop = nullptr;   // mode 2: 1-based n at which the early exit fired (nout if it did not within nout entries)
 };
 
 // Q'b and the forward substitution for one shift (see the K7 header below); l11 = X[1,m-1], v = X[1,m],
 // X2[0..N] = X[2,1..m] after ql_X!.
 template <int N, bool REAL_PATH>
 __device__ __forceinline__ void tz_solve_rows(const TzSolveParams &S, cplx l11, cplx v, const cplx (&X2)[N + 1], cplx tau1,
-                                              cplx tau2, int64_t nout, int64_t n, int64_t idx, double *__restrict__ x)
+                                              cplx tau2, int64_t nout, int64_t n, int64_t idx, double *__restrict__ x,
+                                              int SVmode = 0, int64_t *__restrict__ nstop = nullptr)
 {
     auto put = [&](int64_t j, cplx val) {
         if (REAL_PATH) x[j * n + idx] = val.re;
@@ -463,6 +466,31 @@ __device__ __forceinline__ void tz_solve_rows(const TzSolveParams &S, cplx l11, 
         const cplx u0 = tb[k - 1], u1 = tb[k];
         tb[k - 1] = conj(q11) * u0 + conj(q21) * u1;
         tb[k] = conj(q12) * u0 + conj(q22) * u1;
+    }
+    if (SVmode == 2) {
+        // Q b, Q = LowerHessenbergQ(Fill(q, ∞)) (src/banded/hessenbergq.jl:111-123): for n = 1, 2, ...: x[n:n+1] <- q x[n:n+1];
+        // stops once n > nz and norm(t) <= 10 floatmin — what is left of x is then exactly what the reference leaves
+        cplx carry = S.b[0];
+        int64_t stop = 0;                       // 0: the exit did not fire within nout entries (support goes on)
+        for (int64_t j = 0; j < nout; j++) {
+            const cplx nxt = (j + 1 < S.nb) ? S.b[j + 1] : mk(0.0, 0.0);
+            const cplx t1 = q11 * carry + q12 * nxt, t2 = q21 * carry + q22 * nxt;
+            put(j, t1);
+            carry = t2;
+            if (j + 1 > S.nb && hypot(hypot(t1.re, t1.im), hypot(t2.re, t2.im)) <= 10.0 * 2.2250738585072014e-308) {
+                stop = j + 1;
+                if (j + 1 < nout) put(j + 1, t2);
+                for (int64_t k = j + 2; k < nout; k++) put(k, mk(0.0, 0.0));
+                break;
+            }
+        }
+        if (nstop) nstop[idx] = stop;
+        return;
+    }
+    if (SVmode == 1) {
+        // Q'b alone (UpperHessenbergQ(adjoint.(q)) apply, src/banded/hessenbergq.jl:125-135): support nb + 1
+        for (int64_t j = 0; j < nout; j++) put(j, (j <= S.nb && j <= kSolveMaxB) ? tb[j] : mk(0.0, 0.0));
+        return;
     }
     // L \ (Q'b): sub[i-1] = L[j+i, j] = X[2, m-i], i = 1..N; diagonal X[1,m-1] (first column) / X[2,m] (others)
     cplx sub[N];
@@ -838,12 +866,13 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
     if (WANT_TAIL && SV.x) {
         // fused K7: x = L \ (Q'b) straight from the registers (NaN rows where the factorization does not exist)
         if (st == ILA_OK) {
-            tz_solve_rows<N, REAL_PATH>(SV.S, X1[N - 1], X1[N], X2, tau1, tau2, SV.nout, n, idx, SV.x);
+            tz_solve_rows<N, REAL_PATH>(SV.S, X1[N - 1], X1[N], X2, tau1, tau2, SV.nout, n, idx, SV.x, SV.mode, SV.nstop);
         } else {
             for (int64_t j = 0; j < SV.nout; j++) {
                 if (REAL_PATH) SV.x[j * n + idx] = qnan;
                 else reinterpret_cast<double2 *>(SV.x)[j * n + idx] = make_double2(qnan, qnan);
             }
+            if (SV.nstop) SV.nstop[idx] = 0;
         }
         continue;
     }
@@ -1305,7 +1334,7 @@ static int launch_solve_any(int l, const TzSolveParams &S, int64_t n, const doub
 // fused form: one launch of the K3 kernel that solves from its registers (no tail record in memory)
 int launch_ql_toeplitz_solve_fused(bool real_path, int l, int u, const double *a_host, int branch_rank, const double *d_lambda,
                                    int64_t n, int nb, const double *b_host, int64_t nout, double *d_L11, double *d_x,
-                                   int32_t *d_status, cudaStream_t stream)
+                                   int32_t *d_status, cudaStream_t stream, int mode, int64_t *d_nstop)
 {
     if (nb < 1 || nb > kSolveMaxB) return set_error(ILA_ERR_UNSUPPORTED, "ql_toeplitz_solve: right-hand side length must be in 1..16");
     if (nout < 1) return set_error(ILA_ERR_ARG, "ql_toeplitz_solve: nout must be positive");
@@ -1315,6 +1344,8 @@ int launch_ql_toeplitz_solve_fused(bool real_path, int l, int u, const double *a
         SV.S.b[k] = k < nb ? (real_path ? cplx{b_host[k], 0.0} : cplx{b_host[2 * k], b_host[2 * k + 1]}) : cplx{0.0, 0.0};
     SV.nout = nout;
     SV.x = d_x;
+    SV.mode = mode;
+    SV.nstop = d_nstop;
     return launch_ql_toeplitz_ex(real_path, l, u, a_host, branch_rank, d_lambda, n, d_L11, nullptr, d_status, stream,
                                  TzGrid{nullptr, nullptr, 0, nullptr, 0}, SV);
 }

@@ -335,6 +335,54 @@ def ql_toeplitz_solve(coeffs_data_column, lambdas, b, nout, branch_rank=1, real_
     return x.reshape(lambdas.shape + (nout,)), status.reshape(lambdas.shape)
 
 
+def hessenberg_q_apply(q_blocks, b, nout, adjoint=False):
+    """`Q*b` for Q = LowerHessenbergQ(q) (materialize!, src/banded/hessenbergq.jl:111-123: n = 1, 2, ...: x[n:n+1] = q[n] x[n:n+1],
+    early exit once n > nz and norm(t) <= 10 floatmin) or, with adjoint=True, `Q'*b` = UpperHessenbergQ(adjoint.(q)) applied for
+    n = nz, ..., 1 (:125-135).  q_blocks(n) returns the n-th 2x2 block (1-based).  Returns (first nout entries, n at exit or 0)."""
+    b = np.asarray(b)
+    dt = np.result_type(b.dtype, q_blocks(1).dtype, np.float64)
+    nz = b.shape[0]
+    x = np.zeros(max(nout, nz) + 2, dtype=dt)
+    x[:nz] = b
+    if adjoint:
+        for n in range(nz, 0, -1):
+            x[n - 1:n + 1] = q_blocks(n).conj().T @ x[n - 1:n + 1]
+        return x[:nout].copy(), 0
+    stop = 0
+    tiny = 10 * np.finfo(np.float64).tiny
+    for n in range(1, nout + 1):
+        t = q_blocks(n) @ x[n - 1:n + 1]
+        x[n - 1:n + 1] = t
+        # LinearAlgebra.norm (generic_norm2) rescales by the largest entry when the squares would underflow
+        if n > nz and np.hypot(np.hypot(t[0].real, t[0].imag), np.hypot(t[1].real, t[1].imag)) <= tiny:
+            stop = n
+            break
+    return x[:nout].copy(), stop
+
+
+def ql_toeplitz_applyq(coeffs_data_column, lambdas, b, nout, adjoint=False, branch_rank=1, real_path=None):
+    """Q b / Q'b for the ∞ Hessenberg Q of ql(A - λI), every block equal to q = QLPackedQ(X[:, m-1:m], τ)
+    (infqltoeplitz.jl:63-64).  Returns (y [λ-shape + (nout,)], nstop, status)."""
+    col = np.asarray(coeffs_data_column)
+    lambdas = np.asarray(lambdas)
+    m = col.shape[0]
+    flat = lambdas.reshape(-1)
+    a = np.empty((flat.size, m), dtype=np.result_type(col.dtype, lambdas.dtype))
+    a[...] = col[::-1]
+    a[:, m - 2] = col[1] - flat
+    out = ql_toeplitz_tail(a, branch_rank, real_path, sign_rule="householder")
+    X, tau, status = out["X"], out["tau"], out["status"]
+    dt = np.result_type(X.dtype, np.asarray(b).dtype)
+    y = np.full((flat.size, nout), np.nan, dtype=dt)
+    ns = np.zeros(flat.size, dtype=np.int64)
+    for i in range(flat.size):
+        if status[i] != 0:
+            continue
+        q = ql_packed_Q(X[i][:, m - 2:m], tau[i])
+        y[i], ns[i] = hessenberg_q_apply(lambda n: q, b, nout, adjoint)
+    return y.reshape(lambdas.shape + (nout,)), ns.reshape(lambdas.shape), status.reshape(lambdas.shape)
+
+
 # ----------------------------------------------------------------------------------------------
 # perturbed Toeplitz head: ql_hessenberg!(B)  (src/infql.jl:60-93), u == 1
 # ----------------------------------------------------------------------------------------------

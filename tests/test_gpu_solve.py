@@ -118,3 +118,34 @@ def test_perturbed_hessenberg_batch_vs_oracle(ila):
     # nout smaller than the head
     xs, ss = ila.ql_perttoeplitz_solve(head, col, lam[:1], b, 3)
     assert np.abs(xs[0] - xg[0][:3]).max() == 0.0
+
+
+def test_hessenberg_q_apply_vs_oracle(ila):
+    """Q b (LowerHessenbergQ apply with its early exit, src/banded/hessenbergq.jl:111-123) and Q'b (:125-135) for the ∞
+    Hessenberg Q of ql(A - λI), complex and real symbols: against the oracle to 1e-12, orthogonality Q'(Q b) = b, and the
+    reference's known value Q[1,1] for the rotation blocks of test_hessenbergq.jl:57-62 rebuilt from a symbol."""
+    from oracle import toeplitz_ql as tq
+    rng = np.random.default_rng(11)
+    col = np.array([2j, 0.0, 0.0, 1.0, 0.7])
+    lam = (rng.normal(size=200) + 1j * rng.normal(size=200)) * 4
+    b = np.array([1.0, -0.5 + 0.2j, 0.25])
+    for adjoint in (False, True):
+        y, ns, st = ila.ql_toeplitz_applyq(col, lam, b, 40, adjoint=adjoint)
+        yo, nso, sto = tq.ql_toeplitz_applyq(col, lam, b, 40, adjoint=adjoint)
+        assert np.array_equal(st, sto)
+        ok = st == 0
+        assert np.abs(y[ok] - yo[ok]).max() <= 1e-12 * np.abs(yo[ok]).max()
+        assert np.all(np.isnan(y[~ok].real))
+    # orthogonality on the leading block: |Q b| = |b| once the tail has decayed (400 entries), Q'(Q b)[:3] = b
+    y, ns, st = ila.ql_toeplitz_applyq(col, lam[:20], b, 400)
+    ok = st == 0
+    assert np.allclose(np.sum(np.abs(y[ok]) ** 2, axis=1), np.sum(np.abs(b) ** 2), rtol=1e-12)
+    # real-typed symbol: the early exit index and the exact zeros beyond it
+    colr = np.array([0.5, 5.1, 2.0])
+    yr, nsr, st = ila.ql_toeplitz_applyq(colr, np.array([0.0, 0.3]), np.array([1.0]), 3000)
+    yo, nso, sto = tq.ql_toeplitz_applyq(colr, np.array([0.0, 0.3]), np.array([1.0]), 3000)
+    assert np.array_equal(st, sto) and np.all(st == 0)
+    assert np.all(nsr > 0) and np.all(np.abs(nsr - nso) <= 1)       # razor-edge rounding of a 1e-307 norm may move it by one
+    for i in range(2):
+        assert np.all(yr[i, nsr[i] + 1:] == 0.0)
+        assert np.abs(yr[i] - yo[i]).max() <= 1e-12

@@ -166,3 +166,22 @@ def test_real_path_householder_sign_rule_is_the_finite_section_limit():
         lapack_other += int(other and not same)
     assert checked >= 60
     assert lapack_other > 0          # the ambiguity is real: LAPACK's sign is not the finite-section one everywhere
+
+
+def test_hessenberg_q_apply_restatement_is_pinned():
+    """test/test_hessenbergq.jl:31-62: LowerHessenbergQ(Fill(q, 2)) = [1 0; 0 q] [q 0; 0 1] column by column, its adjoint,
+    and the ∞ case Q[1,1] = cos(0.1) = 0.9950041652780258."""
+    c, s = np.cos(0.1), np.sin(0.1)
+    q = np.array([[c, s], [s, -c]])
+    QM = np.block([[np.eye(1), np.zeros((1, 2))], [np.zeros((2, 1)), q]]) @ np.block([[q, np.zeros((2, 1))], [np.zeros((1, 2)), np.eye(1)]])
+    for j in range(3):
+        e = np.zeros(3); e[j] = 1.0
+        blocks = lambda n: q if n <= 2 else np.eye(2)
+        y, _ = tq.hessenberg_q_apply(blocks, e, 3)
+        assert np.allclose(y, QM[:, j], atol=1e-15)
+        yt, _ = tq.hessenberg_q_apply(blocks, e, 3, adjoint=True)
+        assert np.allclose(yt, QM.T[:, j], atol=1e-15)
+    y, stop = tq.hessenberg_q_apply(lambda n: q, np.array([1.0]), 8000)
+    assert abs(y[0] - 0.9950041652780258) < 1e-15
+    assert 0 < stop < 8000 and np.all(y[stop + 1:] == 0)          # the early exit fires once |s|^n underflows
+    assert abs(np.sum(y ** 2) - 1.0) < 1e-12                       # an orthogonal column
