@@ -164,7 +164,9 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
  * results bit for bit inside an exponent box (redo with intrinsics outside it); 1 = plain __ddiv_rn/__dsqrt_rn
  * (validation mode: both must give identical bits).  Modes 2 / 3 / 4 select how the back-substitution delivers x: auto
  * (direct ragged stores when the batch is at most two warps per SM, coalesced interleaved stream + compaction otherwise) /
- * always compaction / always direct — all three must give identical bits too. */
+ * always compaction / always direct — all three must give identical bits too.  Modes 5 / 6 select the loader of the
+ * back-substitution ring: per-lane 16-byte cp.async (LDGSTS; default, the faster one on the latency-bound C2 batch) / one
+ * cp.async.bulk per group completing on an mbarrier — same bits. */
 int ila_qr_set_arith_mode(int mode);
 
 /* device-resident two-phase form (no host round trip between the phases; the caller owns all buffers):

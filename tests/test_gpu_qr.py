@@ -150,3 +150,27 @@ def test_output_paths_identical(ila):
     for k in (1, 2):
         assert np.array_equal(outs[0][1], outs[k][1]) and np.array_equal(outs[0][2], outs[k][2])
         assert np.array_equal(outs[0][0].view(np.int64), outs[k][0].view(np.int64))
+
+
+def test_bulk_and_ldgsts_loaders_identical(ila):
+    """The back-substitution ring is filled either by per-lane 16-byte cp.async (LDGSTS) or by one cp.async.bulk per group
+    completing on an mbarrier (default): same bits, for plain records and for records that carry reflectors."""
+    from ila_b200 import _lib
+    from scipy.special import jv
+    z = np.linspace(50.0, 6000.0, 70)
+    p, q, r = ila.bessel_operator(z)
+    outs = {}
+    try:
+        for mode in (5, 6):
+            _lib.check(_lib.lib().ila_qr_set_arith_mode(mode))
+            for wf in (False, True):
+                o = ila.qr_banded_solve(1, 1, p, q, r, b=jv(1, z)[:, None], ncap_per=ila.bessel_ncap(z), want_factors=wf)
+                outs[(mode, wf)] = (o["xflat"].copy(), o["ncols"].copy(), o["status"].copy())
+            o5 = ila.qr_banded_solve(2, 2, [[1, 0, 3, 0, 1]] * 40, [[0] * 5] * 40, shift=np.linspace(-0.5, 0.5, 40), b=[3., 4, 5], ncap=9000)
+            outs[(mode, "5band")] = (o5["xflat"].copy(), o5["ncols"].copy(), o5["status"].copy())
+    finally:
+        _lib.check(_lib.lib().ila_qr_set_arith_mode(5))
+    for key in (False, True, "5band"):
+        a, b = outs[(5, key)], outs[(6, key)]
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert np.array_equal(a[0].view(np.int64), b[0].view(np.int64)), key
