@@ -450,6 +450,7 @@ static int ql_toeplitz_host(bool real_path, int out_mode, int l, int u, const do
     const bool staged = !tail_opt && (mode == 2 || (mode == 0 && !(pin_in && pin_out) && n >= 4096));
     const bool stage_in = staged && (mode == 2 || !pin_in), stage_out = staged && (mode == 2 || !pin_out);
     std::vector<TzStageJob> jobs;
+    std::vector<std::function<int()>> direct;      // per-device enqueue loops of the pinned path
     for (int d = 0; d < G; d++) {
         const int64_t lo = d * per, cnt = (lo + per <= n ? per : n - lo);
         if (cnt <= 0) continue;
@@ -479,38 +480,63 @@ static int ql_toeplitz_host(bool real_path, int out_mode, int l, int u, const do
         // keeping that copy engine busy from the first microsecond to the last: ALL input chunks go back to back on one
         // stream; the kernels (two alternating streams) and the D2H copies (their own stream) hang off events.  Chunk sizes
         // shrink geometrically so that what is left after the last input byte has arrived — one small kernel and its
-        // small D2H — is short.
-        DevState &S = g_dev[pd];
-        cudaStream_t s_in = S.pipe[0], s_out = S.pipe[1];
-        const int64_t min_chunk = g_chunk_min.load() > 0 ? g_chunk_min.load() : (1 << 16);
-        const int shrink = g_chunk_div.load() > 1 ? g_chunk_div.load() : 3;
-        int ci = 0;
-        for (int64_t c0 = 0; c0 < cnt; ci++) {
-            int64_t cc = (cnt - c0) / shrink;
-            cc = (cc + 1023) & ~(int64_t)1023;           // whole grid rows of the usual power-of-two widths
-            if (cc < min_chunk) cc = min_chunk;
-            if (c0 + cc > cnt || cnt - (c0 + cc) < min_chunk / 2) cc = cnt - c0;
-            if (ci >= kMaxChunkEv) cc = cnt - c0;
-            cudaStream_t s_k = S.pipe[2 + (ci & 1)];
-            ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam + c0 * w, lambda + (lo + c0) * w, sizeof(double) * cc * w, cudaMemcpyHostToDevice, s_in));
-            ILA_CUDA_CHECK(cudaEventRecord(S.cev[ci][0], s_in));
-            ILA_CUDA_CHECK(cudaStreamWaitEvent(s_k, S.cev[ci][0], 0));
-            if (out_mode == 1)
-                rc = launch_ql_toeplitz_l11re(l, u, a, branch_rank, d_lam + c0 * w, cc, d_L + c0,
-                                              status ? reinterpret_cast<uint8_t *>(d_st) + c0 : nullptr, s_k);
-            else
-                rc = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam + c0 * w, cc, d_L + c0 * w,
-                                        d_tail ? d_tail + c0 * tl * w : nullptr, reinterpret_cast<int32_t *>(d_st) + c0, s_k);
-            if (rc) return rc;
-            ILA_CUDA_CHECK(cudaEventRecord(S.cev[ci][1], s_k));
-            ILA_CUDA_CHECK(cudaStreamWaitEvent(s_out, S.cev[ci][1], 0));
-            ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + (lo + c0) * ow, d_L + c0 * ow, sizeof(double) * cc * ow, cudaMemcpyDeviceToHost, s_out));
-            if (status)
-                ILA_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(status) + (lo + c0) * sb, d_st + c0 * sb, (size_t)cc * sb, cudaMemcpyDeviceToHost, s_out));
-            if (tail_opt)
-                ILA_CUDA_CHECK(cudaMemcpyAsync(tail_opt + (lo + c0) * tl * w, d_tail + c0 * tl * w, sizeof(double) * cc * tl * w, cudaMemcpyDeviceToHost, s_out));
-            c0 += cc;
+        // small D2H — is short.  With several devices each device's enqueue loop runs on its own pool thread (a single
+        // thread needs ~250 µs to queue 8 devices' worth of copies and launches — longer than the work itself).
+        direct.push_back([=]() -> int {
+            ILA_CUDA_CHECK(cudaSetDevice(pd));
+            DevState &S = g_dev[pd];
+            cudaStream_t s_in = S.pipe[0], s_out = S.pipe[1];
+            const int64_t min_chunk = g_chunk_min.load() > 0 ? g_chunk_min.load() : (1 << 16);
+            const int shrink = g_chunk_div.load() > 1 ? g_chunk_div.load() : 3;
+            int ci = 0, rc2 = 0;
+            for (int64_t c0 = 0; c0 < cnt; ci++) {
+                int64_t cc = (cnt - c0) / shrink;
+                cc = (cc + 1023) & ~(int64_t)1023;           // whole grid rows of the usual power-of-two widths
+                if (cc < min_chunk) cc = min_chunk;
+                if (c0 + cc > cnt || cnt - (c0 + cc) < min_chunk / 2) cc = cnt - c0;
+                if (ci >= kMaxChunkEv) cc = cnt - c0;
+                cudaStream_t s_k = S.pipe[2 + (ci & 1)];
+                ILA_CUDA_CHECK(cudaMemcpyAsync(d_lam + c0 * w, lambda + (lo + c0) * w, sizeof(double) * cc * w, cudaMemcpyHostToDevice, s_in));
+                ILA_CUDA_CHECK(cudaEventRecord(S.cev[ci][0], s_in));
+                ILA_CUDA_CHECK(cudaStreamWaitEvent(s_k, S.cev[ci][0], 0));
+                if (out_mode == 1)
+                    rc2 = launch_ql_toeplitz_l11re(l, u, a, branch_rank, d_lam + c0 * w, cc, d_L + c0,
+                                                   status ? reinterpret_cast<uint8_t *>(d_st) + c0 : nullptr, s_k);
+                else
+                    rc2 = launch_ql_toeplitz(real_path, l, u, a, branch_rank, d_lam + c0 * w, cc, d_L + c0 * w,
+                                             d_tail ? d_tail + c0 * tl * w : nullptr, reinterpret_cast<int32_t *>(d_st) + c0, s_k);
+                if (rc2) return rc2;
+                ILA_CUDA_CHECK(cudaEventRecord(S.cev[ci][1], s_k));
+                ILA_CUDA_CHECK(cudaStreamWaitEvent(s_out, S.cev[ci][1], 0));
+                ILA_CUDA_CHECK(cudaMemcpyAsync(L11 + (lo + c0) * ow, d_L + c0 * ow, sizeof(double) * cc * ow, cudaMemcpyDeviceToHost, s_out));
+                if (status)
+                    ILA_CUDA_CHECK(cudaMemcpyAsync(static_cast<char *>(status) + (lo + c0) * sb, d_st + c0 * sb, (size_t)cc * sb, cudaMemcpyDeviceToHost, s_out));
+                if (tail_opt)
+                    ILA_CUDA_CHECK(cudaMemcpyAsync(tail_opt + (lo + c0) * tl * w, d_tail + c0 * tl * w, sizeof(double) * cc * tl * w, cudaMemcpyDeviceToHost, s_out));
+                c0 += cc;
+            }
+            return 0;
+        });
+    }
+    if (!direct.empty()) {
+        std::vector<int> rcs(direct.size(), 0);
+        std::vector<std::string> errs(direct.size());
+        if (direct.size() > 1) {
+            if (!g_pool) g_pool = new WorkerPool();
+            g_pool->ensure((int)direct.size() - 1);
+            for (size_t j = 1; j < direct.size(); j++)
+                g_pool->submit([&, j] {
+                    rcs[j] = direct[j]();
+                    if (rcs[j]) errs[j] = g_last_error;
+                });
         }
+        rcs[0] = direct[0]();
+        if (direct.size() > 1) g_pool->wait();
+        for (size_t j = 0; j < rcs.size(); j++)
+            if (rcs[j]) {
+                if (j) snprintf(g_last_error, sizeof(g_last_error), "%s", errs[j].c_str());
+                return rcs[j];
+            }
     }
     if (!jobs.empty()) {
         // workers: kPipe per device from the persistent pool; worker (job 0, stream 0) runs on the calling thread
