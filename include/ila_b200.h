@@ -131,6 +131,12 @@ int ila_ql_set_max_sweeps(int fp64_sweeps, int scout_sweeps);
  * formula, l = 3: Ferrari's resolvent) polished by the usual sweeps; 0 = circle start + Aberth sweeps for every degree.
  * Results do not depend on it beyond the last bits of the selected root's Newton refinement (validation knob). */
 int ila_ql_set_cold_start(int closed_form_seeds);
+/* compute-sanitizer substitute.  `make -C csrc debug` builds libila_b200_dbg.so with -DILA_BOUNDS: the kernels whose index
+ * arithmetic is not trivial (K1/K2 group-interleaved records and ring slots, K5 records, K11 circular shared-memory panel,
+ * R slab, back-substitution scratch) then address their buffers through bounds-checked pointers that record every
+ * out-of-range index instead of performing it.  This returns (and clears) what they recorded: count (-1 in the release
+ * build: not instrumented), and site id / index / extent of the first failure. */
+int ila_debug_bounds_report(int64_t *count, int64_t *site, int64_t *index, int64_t *extent);
 
 /* ---- K1+K2: adaptive banded QR solve  x_i = A_i \ b_i ----------------------------------------
  * Replaces qr(A) -> adaptiveqr (src/infqr.jl:163-174) and `\` = ldiv!(F.R, F.Q'*b) (src/infqr.jl:370-374):

@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libila_b200.so")
+# ILA_B200_DEBUG_LIB=1 selects the bounds-checked debug build (`make -C csrc debug`; the compute-sanitizer substitute)
+SO_PATH = os.path.join(_HERE, "libila_b200_dbg.so" if os.environ.get("ILA_B200_DEBUG_LIB") == "1" else "libila_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ILA_OK, ILA_NO_QL, ILA_NOT_REAL, ILA_NOT_CONVERGED, ILA_NOT_POSDEF, ILA_NAN = range(6)
@@ -98,6 +99,7 @@ SIGNATURES = {
     "ila_ql_set_shifts_per_thread": (C.c_int, [C.c_int]),
     "ila_ql_set_max_sweeps": (C.c_int, [C.c_int, C.c_int]),
     "ila_ql_set_cold_start": (C.c_int, [C.c_int]),
+    "ila_debug_bounds_report": (C.c_int, [_vp, _vp, _vp, _vp]),
     "ila_ql_toeplitz_l11re_c64": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, C.c_int]),
     "ila_ql_toeplitz_l11re_c64_dev": (C.c_int, [C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp]),
     "ila_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),

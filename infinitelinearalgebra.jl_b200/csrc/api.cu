@@ -1522,6 +1522,31 @@ int ila_ql_set_max_sweeps(int fp64_sweeps, int scout_sweeps)
     return 0;
 }
 
+/* Debug build (-DILA_BOUNDS, libila_b200_dbg.so): out-of-range accesses recorded by the bounds-checked pointers of K1/K2,
+ * K5 and K11 since the last call.  count = -1 in the release build (not instrumented). */
+int ila_debug_bounds_report(int64_t *count, int64_t *site, int64_t *index, int64_t *extent)
+{
+    unsigned long long v[3][4] = {};
+    int inst = 0;
+    int rc;
+    if ((rc = qr_banded_bounds_report(v[0])) < 0) return rc;
+    inst += rc;
+    if ((rc = chol_banded_bounds_report(v[1])) < 0) return rc;
+    inst += rc;
+    if ((rc = qr_blockbanded_bounds_report(v[2])) < 0) return rc;
+    inst += rc;
+    int64_t c = 0, s = 0, i = 0, e = 0;
+    for (int k = 0; k < 3; k++) {
+        if (v[k][0] && !c) { s = (int64_t)v[k][1]; i = (int64_t)v[k][2]; e = (int64_t)v[k][3]; }
+        c += (int64_t)v[k][0];
+    }
+    if (count) *count = inst ? c : -1;
+    if (site) *site = s;
+    if (index) *index = i;
+    if (extent) *extent = e;
+    return 0;
+}
+
 int ila_ql_set_cold_start(int closed_form_seeds)
 {
     tz_set_seeds(closed_form_seeds);

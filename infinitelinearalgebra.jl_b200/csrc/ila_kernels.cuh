@@ -200,6 +200,9 @@ struct CholFwdArgs {
     int resume = 0;
 };
 int chol_state_doubles(int u);
+int chol_banded_bounds_report(unsigned long long *out4);
+int qr_banded_bounds_report(unsigned long long *out4);
+int qr_blockbanded_bounds_report(unsigned long long *out4);
 int launch_chol_forward(int u, const CholFwdArgs &a, cudaStream_t s);
 
 // from ql_blocktri.cu

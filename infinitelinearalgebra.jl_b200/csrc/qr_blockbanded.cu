@@ -56,7 +56,7 @@ constexpr int kThreads = 448;          // 14 warps x 16 column pairs = 224 >= 3*
 constexpr int kWarps = kThreads / 32;
 
 struct Panel {
-    double *P;        // HMAX x LD, row-major; column slot wmax is the right-hand side
+    ILA_BP(double) P; // HMAX x LD, row-major; column slot wmax is the right-hand side (bounds-checked in the debug build)
     int hmask, wmax, ld;
     __device__ __forceinline__ int rs(int g) const { return g & hmask; }
     __device__ __forceinline__ int cs(int c) const { return c % wmax; }
@@ -323,12 +323,13 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t inst = blockIdx.x;
     const int hmax = A.hmax, wmax = A.wmax, ld = wmax + 1;
-    Panel pn{smem, hmax - 1, wmax, ld};
+    Panel pn{ILA_MKBP(double, smem, (size_t)hmax * ld, 1101), hmax - 1, wmax, ld};
     const double al = A.alpha[inst], be = A.beta[inst], lam = A.lam[inst];
     // the 1-D operators' bands staged in shared memory (behind the panel, the V buffers and the panel scalars): the row
     // generator reads them once per fresh row
     constexpr int tld = 72;
-    double *T1 = smem + (size_t)hmax * ld + 2 * (size_t)hmax * 4 + 32, *T2 = T1 + 3 * tld;
+    ILA_BP(double) T1 = ILA_MKBP(double, smem + (size_t)hmax * ld + 2 * (size_t)hmax * 4 + 32, 3 * tld, 1108);
+    ILA_BP(double) T2 = ILA_MKBP(double, smem + (size_t)hmax * ld + 2 * (size_t)hmax * 4 + 32 + 3 * tld, 3 * tld, 1109);
     for (int i = tid; i < 3 * tld; i += kThreads) {
         const int band = i / tld, k = i % tld;
         T1[i] = k <= A.maxblocks ? A.T1[band * A.tld + k] : 0.0;
@@ -337,15 +338,15 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     __syncthreads();
     const double *bi = A.b + inst * A.nb;
     const int nb = A.nb, cg = A.colgrowth, maxblocks = A.maxblocks;
-    double *Rw = A.work + inst * A.work_stride;
-    double *qtb = A.qtb + inst * A.xld;
+    ILA_BP(double) Rw = ILA_MKBP(double, A.work + inst * A.work_stride, A.work_stride, 1102);
+    ILA_BP(double) qtb = ILA_MKBP(double, A.qtb + inst * A.xld, A.xld, 1103);
 
     // rows of block K (1-based) into the panel (one warp per row): zero the columns of blocks Klo..K+1, then the (at most
     // five) entries of the row and its right-hand-side entry
     auto load_block_rows = [&](int K, int Klo) {
         const int c_lo = bstart(Klo), w = bstart(K + 2) - c_lo, r0 = bstart(K), s_lo = pn.cs(c_lo);
         for (int k = warp; k < K; k += kWarps) {
-            double *row = pn.P + pn.rs(r0 + k) * ld;
+            ILA_BP(double) row = pn.P + pn.rs(r0 + k) * ld;
             for (int ci = lane; ci < w; ci += 32) {
                 int sl = s_lo + ci;
                 if (sl >= wmax) sl -= wmax;
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
             {
                 const int s2 = pn.cs(bstart(J + 2)), w2 = J + 2;
                 for (int k = warp; k < J; k += kWarps) {
-                    double *row = pn.P + pn.rs(c0 + k) * ld;
+                    ILA_BP(double) row = pn.P + pn.rs(c0 + k) * ld;
                     for (int ci = lane; ci < w2; ci += 32) {
                         int sl = s2 + ci;
                         if (sl >= wmax) sl -= wmax;
@@ -466,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                     const bool act = tq <= ntrail;
                     int scol = pn.cs(first) + tq;
                     if (scol >= wmax) scol -= wmax;
-                    double *__restrict__ col = pn.P + (tq < ntrail ? scol : wmax);
+                    ILA_BP(double) col = pn.P + (tq < ntrail ? scol : wmax);
                     const int cnt = act ? (m - half + 1) >> 1 : 0;       // rows i = half, half+2, ... < m
                     const int hm = pn.hmask;
                     const double2 *__restrict__ V2 = reinterpret_cast<const double2 *>(Vb);
@@ -552,8 +553,8 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                 const bool act = tp <= ntrail;
                 int scol = csc + 1 + tp;
                 if (scol >= wmax) scol -= wmax;
-                const double *__restrict__ piv = pn.P + csc;
-                double *__restrict__ col = pn.P + (tp < ntrail ? scol : wmax);
+                ILA_BP(const double) piv = pn.P + csc;
+                ILA_BP(double) col = pn.P + (tp < ntrail ? scol : wmax);
                 const int cnt = (act && m > half) ? (m - half) >> 1 : 0;      // this lane's rows: i = 1+half, 3+half, ...
                 const int hm = pn.hmask;
                 const int rd = pn.rs(c) * ld;
@@ -621,10 +622,10 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
             // (c) rows of block J are final: R[J, J..J+2] and (Q'b)[J] leave the panel (one warp per row, coalesced)
             K11_ACC(tp_j);
             {
-                double *dst = Rw + (int64_t)(J - 1) * J * (J + 1);
+                ILA_BP(double) dst = Rw + (int64_t)(J - 1) * J * (J + 1);
                 const int s0 = pn.cs(c0);
                 for (int k = warp; k < J; k += kWarps) {
-                    const double *row = pn.P + pn.rs(c0 + k) * ld;
+                    ILA_BP(const double) row = pn.P + pn.rs(c0 + k) * ld;
                     for (int ci = lane; ci < ncols; ci += 32) {
                         int sl = s0 + ci;
                         if (sl >= wmax) sl -= wmax;
@@ -663,15 +664,15 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
             const int K = findblock(last + 1);
             n2 = bstart(K + 1);
             // ---- back-substitution on the leading K x K blocks (infqr.jl:358-366)
-            double *Ts = smem;                           // diagonal block, stride ldt (odd)
-            double *cs_ = smem + 64 * 65;                // right-hand side of the current block row
-            double *xs = cs_ + 64;                       // solution
+            ILA_BP(double) Ts = ILA_MKBP(double, smem, 64 * 65, 1104);                   // diagonal block, stride ldt (odd)
+            ILA_BP(double) cs_ = ILA_MKBP(double, smem + 64 * 65, 64, 1105);              // right-hand side of the current block row
+            ILA_BP(double) xs = ILA_MKBP(double, smem + 64 * 65 + 64, maxblocks * (maxblocks + 1) / 2 + 8, 1106);   // solution
             for (int Kc = K; Kc >= 1; Kc--) {
                 const int s = bstart(Kc), wrow = 3 * Kc + 3, ldt = Kc | 1;
                 const int wlim = min(wrow, n2 - s);
-                const double *src = Rw + (int64_t)(Kc - 1) * Kc * (Kc + 1);
+                ILA_BP(const double) src = Rw + (int64_t)(Kc - 1) * Kc * (Kc + 1);
                 for (int k = warp; k < Kc; k += kWarps) {
-                    const double *row = src + (int64_t)k * wrow;
+                    ILA_BP(const double) row = src + (int64_t)k * wrow;
                     double acc = 0.0;
                     for (int ci = lane; ci < wlim; ci += 32) {
                         const double v = row[ci];
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                 }
                 __syncthreads();
             }
-            double *xo = A.x + inst * A.xld;
+            ILA_BP(double) xo = ILA_MKBP(double, A.x + inst * A.xld, A.xld, 1107);
             for (int i = tid; i < A.xld; i += kThreads) xo[i] = i < n2 ? xs[i] : 0.0;
         }
     }
@@ -758,5 +759,7 @@ int launch_qr_blockbanded(BlockQrArgs a, cudaStream_t s)
     ILA_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
+
+ILA_BOUNDS_REPORT_FN(qr_blockbanded_bounds_report)
 
 } // namespace ila
