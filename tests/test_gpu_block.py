@@ -163,3 +163,33 @@ def test_block_ql_object_like_test_periodic(ila):
                 Ad2[2 * k + 2:2 * k + 4, 2 * k:2 * k + 2] = c2
         assert np.abs(F2.Q[1:10, 1:12] @ F2.L[1:12, 1:10] - Ad2[:10, :10]).max() < 1e-9
     assert abs(F2.L[1, 1]) <= 1e-11                                              # degenerate
+
+
+def test_c5_full_batch_bit_exact_vs_oracle(ila):
+    """BASELINE config C5 at full size: all 512 energies of the periodic Schrödinger operator (256 in (-0.95, 0.95), 256 in
+    (2.25, 4)) against the oracle: L[1,1], iteration counts and statuses identical, fixed point and τ bit for bit."""
+    import json, os
+    from oracle import block_ql as bq
+    xs = np.concatenate([np.linspace(-0.95, 0.95, 256), np.linspace(2.25, 4.0, 256)])
+    blocks = ila.periodic_schrodinger_blocks()
+    o = ila.ql_blocktri_factors(*blocks, xs)
+    bad = dict(status=0, iters=0, L11=0, tail=0, tau=0, head=0)
+    for i, x in enumerate(xs):
+        L11, it, st, ex = bq.blocktri_ql_l11(*blocks, shift=x)
+        bad["status"] += int(st != o["status"][i])
+        if st != 0:
+            continue
+        bad["iters"] += int(it != o["iters"][i])
+        bad["L11"] += int(L11 != o["L11"][i])
+        bad["tail"] += int(not np.array_equal(o["tail"][i], ex["tail_X"]))
+        bad["tau"] += int(not (np.array_equal(o["tau_tail"][i], ex["tail_tau"]) and np.array_equal(o["head_tau"][i], ex["head_tau"])))
+        bad["head"] += int(not np.array_equal(o["head"][i], ex["head_factors"]))
+    rep = dict(config="C5 512 periodic-Schrödinger energies", mismatches=bad, iterations_min_max=[int(o["iters"].min()), int(o["iters"].max())],
+               converged=int((o["status"] == 0).sum()))
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        json.dump(rep, open(os.path.join(root, "gpurun_out", "r02_parity_c5_full.json"), "w"), indent=1)
+    except OSError:
+        pass
+    assert all(v == 0 for v in bad.values()), rep
+    assert rep["converged"] == 512, rep

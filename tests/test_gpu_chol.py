@@ -90,3 +90,43 @@ def test_c4_full_size_properties(ila):
     for j, i in enumerate(range(0, 2048, 256)):
         m = min(len(g["x"][i]), len(gq["x"][j]))
         assert np.allclose(g["x"][i][:m], gq["x"][j][:m], rtol=1e-9, atol=1e-14)
+
+
+def test_c4_full_batch_bit_exact_vs_oracle(ila):
+    """BASELINE config C4 at full size: all 2048 pentadiagonal shifts against the C oracle bit for bit (status, ncols, nconv, x),
+    and cholesky(S) \\ b == qr(S) \\ b on every 64th shift (test/test_infcholesky.jl:5-11)."""
+    import json, os
+    from oracle import banded as ob
+    sigma = 0.01 + (10 - 0.01) * np.arange(2048) / 2047
+    p, q = ila.pentadiagonal_operator(sigma)
+    g = ila.chol_banded_solve(2, p, q, b=[1.0], ncap=12000)
+    mism = dict(status=0, ncols=0, nconv=0, x_entries=0)
+    cols = 0
+    for lo in range(0, 2048, 256):
+        hi = lo + 256
+        o = ob.chol_banded_solve(2, p[lo:hi], q[lo:hi], b=[1.0], ncap=12000, nthreads=os.cpu_count() or 1)
+        mism["status"] += int((g["status"][lo:hi] != o["status"]).sum())
+        mism["ncols"] += int((g["ncols"][lo:hi] != o["ncols"]).sum())
+        mism["nconv"] += int((g["nconv"][lo:hi] != o["nconv"]).sum())
+        for i in range(lo, hi):
+            n = int(o["ncols"][i - lo])
+            cols += n
+            mism["x_entries"] += int((g["x"][i].view(np.int64) != o["x"][i - lo, :n].view(np.int64)).sum()) if len(g["x"][i]) == n else n
+    # full symmetric band description for the QR entry (data rows +2, +1, 0, -1, -2)
+    p5 = np.stack([p[::64, 0], p[::64, 1], p[::64, 2], p[::64, 1], p[::64, 0]], axis=1)
+    q5 = np.zeros_like(p5)
+    q5[:, 2] = q[::64, 2]
+    r = ila.qr_banded_solve(2, 2, p5, q5, b=[1.0], ncap=12000)
+    worst = 0.0
+    for k, i in enumerate(range(0, 2048, 64)):
+        m = min(len(g["x"][i]), len(r["x"][k]))
+        worst = max(worst, float(np.abs(g["x"][i][:m] - r["x"][k][:m]).max() / np.abs(r["x"][k][:m]).max()))
+    rep = dict(config="C4 2048 pentadiagonal Cholesky shifts", columns_compared=cols, mismatches_vs_c_oracle=mism,
+               all_ok=bool(np.all(g["status"] == 0)), chol_vs_qr_max_rel=worst)
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        json.dump(rep, open(os.path.join(root, "gpurun_out", "r02_parity_c4_full.json"), "w"), indent=1)
+    except OSError:
+        pass
+    assert rep["all_ok"] and all(v == 0 for v in mism.values()), rep
+    assert worst <= 1e-12, rep
