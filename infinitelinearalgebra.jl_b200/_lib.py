@@ -13,6 +13,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # ILA_B200_DEBUG_LIB=1 selects the bounds-checked debug build (`make -C csrc debug`; the compute-sanitizer substitute)
 SO_PATH = os.path.join(_HERE, "libila_b200_dbg.so" if os.environ.get("ILA_B200_DEBUG_LIB") == "1" else "libila_b200.so")
+if os.environ.get("ILA_B200_SO"):        # explicit override (profiling builds)
+    SO_PATH = os.environ["ILA_B200_SO"]
 CSRC = os.path.join(_HERE, "csrc")
 
 ILA_OK, ILA_NO_QL, ILA_NOT_REAL, ILA_NOT_CONVERGED, ILA_NOT_POSDEF, ILA_NAN = range(6)

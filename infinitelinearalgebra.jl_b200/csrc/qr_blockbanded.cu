@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
     };
 
 #ifdef ILA_K11_PROFILE
-    long long tp_a = 0, tp_n = 0, tp_j = 0, tp_c = 0, tp_bs = 0, tp_t0, tp_w0 = 0, tp_w1 = 0;
+    long long tp_a = 0, tp_n = 0, tp_j = 0, tp_c = 0, tp_bs = 0, tp_t0, tp_w0 = 0, tp_w1 = 0, tp_a2 = 0, tp_bar = 0, tp_pf = 0, tp_sync = 0;
+    int tp_np = 0;
 #define K11_T0() tp_t0 = clock64()
 #define K11_ACC(v) do { const long long t_ = clock64(); v += t_ - tp_t0; tp_t0 = t_; } while (0)
 #else
@@ -456,10 +457,22 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
                     // two-warp named barrier, then warp 0 factorizes the four columns
                     if (kbn > 0) {
                         const int coff = warp == 0 ? 0 : 2;
+#ifdef ILA_K11_PROFILE
+                        const long long ta = clock64();
+#endif
                         if (kbn > coff) panel_apply2(pn, Vb, psb, cp, m, cp + kb + coff, min(2, kbn - coff), lane);
+#ifdef ILA_K11_PROFILE
+                        const long long tb = clock64();
+#endif
                         asm volatile("bar.sync 1, 64;" ::: "memory");
+#ifdef ILA_K11_PROFILE
+                        const long long tc = clock64();
+#endif
                         if (warp == 0)
                             panel_factor(pn, Vp + (size_t)(buf ^ 1) * hmax * 4, ps + (buf ^ 1) * 16, cp + kb, kbn, m - kb, lane);
+#ifdef ILA_K11_PROFILE
+                        if (warp == 0 && lane == 0) { tp_a2 += tb - ta; tp_bar += tc - tb; tp_pf += clock64() - tc; tp_np++; }
+#endif
                     }
                 } else {
                     const int tq = (warp - 1) * 16 + (lane & 15);      // 12 trailing warps x 16 pairs = 192 >= 3*63 + 4 - 8
@@ -519,8 +532,12 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
 #ifdef ILA_K11_PROFILE
                 if (lane == 0 && warp == 0) tp_w0 += clock64() - tw0;
                 if (lane == 0 && warp == 1) tp_w1 += clock64() - tw0;
+                const long long ts0 = clock64();
 #endif
                 __syncthreads();
+#ifdef ILA_K11_PROFILE
+                if (lane == 0 && warp == 0) tp_sync += clock64() - ts0;
+#endif
                 buf ^= 1;
             }
             } else {
@@ -714,6 +731,7 @@ __global__ void __launch_bounds__(kThreads, 1) qr_blockbanded_kernel(BlockQrArgs
         double *xo = A.x + inst * A.xld + A.xld - 5;
         xo[0] = (double)tp_a; xo[1] = (double)tp_n; xo[2] = (double)tp_j; xo[3] = (double)tp_c; xo[4] = (double)tp_bs;
         xo[-1] = (double)tp_w0;
+        xo[-3] = (double)tp_a2; xo[-4] = (double)tp_bar; xo[-5] = (double)tp_pf; xo[-6] = (double)tp_sync; xo[-7] = (double)tp_np;
     }
     if (tid == 32) A.x[inst * A.xld + A.xld - 7] = (double)tp_w1;
 #endif

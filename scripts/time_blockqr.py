@@ -47,3 +47,5 @@ if os.environ.get("K11_PROFILE"):
     i = int(np.argmax(nb_))
     print("phase cycles (operator with most blocks): load %.0f  first-norm %.0f  columns %.0f  write-out %.0f  back-substitution %.0f" % tuple(xc[i, -5:]))
     print("panel loop work before the barrier: warp 0 (panel) %.0f cycles, warp 1 (trailing) %.0f cycles" % (xc[i, -6], xc[i, -7]))
+    print("warp 0 per panel step (%d steps): apply2 %.0f  two-warp barrier %.0f  panel_factor %.0f  block barrier wait %.0f cycles" %
+          (xc[i, -12], xc[i, -8] / xc[i, -12], xc[i, -9] / xc[i, -12], xc[i, -10] / xc[i, -12], xc[i, -11] / xc[i, -12]))
