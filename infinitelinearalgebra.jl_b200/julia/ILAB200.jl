@@ -471,6 +471,51 @@ function blocktri_L11(dl_head::Vector{Matrix{ComplexF64}}, d_head::Vector{Matrix
     L11, iters, status
 end
 
+"""
+    apply_Q(datacolumn, λs, b, nout; adjoint=false, branch_rank=1, ngpus=1) -> (Y::Matrix (n × nout), nstop, status)
+
+`Q*b` (`adjoint=false`: `LowerHessenbergQ` apply with the reference's early exit, src/banded/hessenbergq.jl:111-123; `nstop[i]` =
+the n at which it fired, 0 if beyond `nout`) or `Q'*b` (`:125-135`) for the ∞ Hessenberg Q of `ql(A - λs[i]*I)`.
+"""
+function apply_Q(datacolumn::AbstractVector, λs::AbstractVector, b::AbstractVector, nout::Integer; adjoint::Bool=false,
+                 branch_rank::Integer=1, ngpus::Integer=1)
+    a = Vector{ComplexF64}(datacolumn); λ = Vector{ComplexF64}(λs); bb = Vector{ComplexF64}(b); n = length(λ)
+    Y = Matrix{ComplexF64}(undef, n, nout); nstop = Vector{Int64}(undef, n); status = Vector{Int32}(undef, n)
+    check(ccall((:ila_ql_toeplitz_applyq_c64, lib), Cint,
+                (Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Int64, Cint, Cint, Cint, Ptr{ComplexF64}, Int64, Ptr{ComplexF64},
+                 Ptr{Int64}, Ptr{Int32}, Cint),
+                length(a) - 2, 1, a, λ, n, branch_rank, adjoint ? 1 : 0, length(bb), bb, nout, Y, adjoint ? C_NULL : nstop, status, ngpus))
+    Y, nstop, status
+end
+
+"""
+    blocktri_factors(dl_head, d_head, du_head, c, a, b, energies; rhs=nothing, nout=0, atol=1e-10, maxit=1_000_000, ngpus=1)
+
+The whole block QL per energy (`ila_ql_blocktri_factors_f64`): `(L11, P (2n × 3n × m), τtail (n × m), head (Nn × Nn × m),
+headτ (Nn × m), qtb (nout × m) or nothing, iters, status)` — the records `QL(_BlockSkylineMatrix(Vcat(BB.data, Fill(tail
+column))), Vcat(F.τ, Fill(τ,∞)))` is assembled from (src/infql.jl:199-204), and `(Q'rhs)[1:nout]` (`:213-243`).
+"""
+function blocktri_factors(dl_head::Vector{Matrix{Float64}}, d_head::Vector{Matrix{Float64}}, du_head::Vector{Matrix{Float64}},
+                          c::Matrix{Float64}, a::Matrix{Float64}, b::Matrix{Float64}, energies::AbstractVector{<:Real};
+                          rhs=nothing, nout::Integer=0, atol::Real=1e-10, maxit::Integer=1_000_000, ngpus::Integer=1)
+    n = size(c, 1); e = Vector{Float64}(energies); m = length(e)
+    N = max(length(du_head) + 1, length(d_head), length(dl_head)); hn = N * n
+    cat3(v) = isempty(v) ? Float64[] : reduce(vcat, vec.(v))
+    L11 = Vector{Float64}(undef, m); P = Array{Float64,3}(undef, 2n, 3n, m); τt = Matrix{Float64}(undef, n, m)
+    H = Array{Float64,3}(undef, hn, hn, m); Hτ = Matrix{Float64}(undef, hn, m)
+    iters = Vector{Int32}(undef, m); status = Vector{Int32}(undef, m)
+    rb = rhs === nothing ? Float64[] : Vector{Float64}(rhs)
+    qtb = rhs === nothing ? nothing : Matrix{Float64}(undef, nout, m)
+    check(ccall((:ila_ql_blocktri_factors_f64, lib), Cint,
+                (Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64},
+                 Ptr{Float64}, Int64, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint,
+                 Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Cint),
+                n, c, a, b, length(dl_head), cat3(dl_head), length(d_head), cat3(d_head), length(du_head), cat3(du_head), e, m,
+                atol, maxit, L11, P, τt, H, Hτ, length(rb), isempty(rb) ? C_NULL : rb, nout, qtb === nothing ? C_NULL : qtb,
+                iters, status, ngpus))
+    L11, P, τt, H, Hτ, qtb, iters, status
+end
+
 # ---- library plumbing ------------------------------------------------------------------------------------------------
 device_count() = Int(ccall((:ila_device_count, lib), Cint, ()))
 set_device(d::Integer) = check(ccall((:ila_set_device, lib), Cint, (Cint,), d))
