@@ -163,8 +163,8 @@ __device__ __forceinline__ int aberth_sweep_f32(const cplxf (&cf)[N + 1], cplxf 
             w2 = abs2f(w[j]);
             big = true;
         }
-        notconv = notconv || (c2 > 2.5e-5f * w2);   // |corr| > 5e-3 |w|: the cubic step then lands at ~1e-6 or better
-        big = big || (c2 > 1e-4f * w2) || !(w2 < 1e30f);
+        notconv = notconv || !(c2 <= 2.5e-5f * w2);   // |corr| > 5e-3 |w| (or NaN): the cubic step then lands at ~1e-6 or better
+        big = big || !(c2 <= 1e-4f * w2) || !(w2 < 1e30f);
     }
     return big ? 2 : (notconv ? 1 : 0);
 }
@@ -196,8 +196,8 @@ __device__ __forceinline__ int dk_sweep_f32(const cplxf (&cf)[N + 1], cplxf (&w)
         else big = true;
         w[j] = w[j] - corr;
         const float w2 = abs2f(w[j]), c2 = abs2f(corr);
-        notconv = notconv || (c2 > 1e-6f * w2);    // |corr| > 1e-3 |w|: the quadratic step then lands at ~1e-6
-        big = big || (c2 > 1e-4f * w2) || !(w2 < 1e30f);
+        notconv = notconv || !(c2 <= 1e-6f * w2);    // |corr| > 1e-3 |w| (or NaN): the quadratic step then lands at ~1e-6
+        big = big || !(c2 <= 1e-4f * w2) || !(w2 < 1e30f);
     }
     return big ? 2 : (notconv ? 1 : 0);
 }
@@ -311,12 +311,13 @@ __device__ __forceinline__ int aberth_sweep(const cplx (&cf)[N + 1], cplx (&w)[N
         const double b2 = abs2(bot);
         cplx corr = mk(0.0, 0.0);
         if (b2 > 1e-280 && b2 < 1e280) corr = fast_rcp(b2) * (top * conj(bot));
-        else if (b2 > 0.0) corr = (1.0 / b2) * (top * conj(bot));
+        else if (b2 > 0.0 && b2 < 1.7e308) corr = (1.0 / b2) * (top * conj(bot));
+        else big = notconv = true;      // overflow / NaN in the products: a zero correction here must not read as convergence
         w[j] = w[j] - corr;
         const double w2 = abs2(w[j]);
         const double c2 = abs2(corr);
-        notconv = notconv || (c2 > 1e-18 * w2);
-        big = big || (c2 > 1e-4 * w2);
+        notconv = notconv || !(c2 <= 1e-18 * w2) || !(w2 < 1e300);     // NaN/Inf-safe: a non-finite iterate is never "converged"
+        big = big || !(c2 <= 1e-4 * w2);
     }
     return big ? 2 : (notconv ? 1 : 0);
 }
@@ -718,17 +719,50 @@ ql_toeplitz_l11_kernel(TzParams<N> P, const double *__restrict__ lambda, int64_t
             if (abs2(corr) < 1e-6 * abs2(ws)) ws = ws - corr;
         }
     }
-    if (lost) {
-        // sweeps exhausted (infqltoeplitz.jl has no counterpart: LAPACK's QR iteration reports info > 0 and `eigen` throws):
-        // accept the root only if it is one to rounding — backward error |P(w)| <= 1e-13 sum_k |cf_k||w|^(N-k), the
-        // criterion that also holds at multiple roots, where the corrections stay large — else ILA_NOT_CONVERGED.
+    if (full && st == ILA_OK) {
+        // Whatever the FP64 simultaneous iteration returned (a handful of shifts per grid get here) is VERIFIED, whether or not
+        // it reported convergence: the root is accepted only if it is one to rounding — backward error |P(w)| <= 1e-13
+        // sum_k |cf_k||w|^(N-k), the criterion that also holds at multiple roots, where the corrections stay large — else
+        // ILA_NOT_CONVERGED (infqltoeplitz.jl has no counterpart: LAPACK's QR iteration reports info > 0 and `eigen` throws).
         const cplx pv = horner1<N>(cf, ws);
         const double aw = sqrt(abs2(ws));
         double bnd = 1.0;
 #pragma unroll
         for (int k = 1; k <= N; k++) bnd = fma(bnd, aw, sqrt(abs2(cf[k])));
         if (!(abs2(pv) <= 1e-26 * bnd * bnd)) st = ILA_NOT_CONVERGED;
+        if (st == ILA_NOT_CONVERGED && P.branch_rank == 1) {
+            // Rescue for shifts far outside the symbol's range (|λ - a_0| >> the other coefficients: one root ~ -cf_1 of modulus
+            // up to 1e150, the others tiny — the simultaneous iteration cannot cross that many decades in its sweeps and P(w)
+            // overflows).  The dominant root is the SMALLEST root of the reversed polynomial Q(u) = u^N P(1/u) = sum_k cf_k u^k:
+            // Newton from u = -1/cf_1, nothing overflows; Pellet's test at r = |w|/2 (|cf_1| r^(N-1) > r^N + sum_{k>=2}|cf_k| r^(N-k):
+            // exactly N-1 roots inside r) proves it is the one `findmax` selects.
+            const double a1 = abs2(cf[1]);
+            if (a1 > 0.0 && a1 < 1e300) {
+                cplx u = -((1.0 / a1) * conj(cf[1]));
+                bool okn = false;
+                for (int it = 0; it < 12; it++) {
+                    cplx q = cf[N], dq = mk(0.0, 0.0);
+#pragma unroll
+                    for (int k = N - 1; k >= 0; k--) { dq = cfma(dq, u, q); q = cfma(q, u, k == 0 ? mk(1.0, 0.0) : cf[k]); }
+                    const double d2 = abs2(dq);
+                    if (!(d2 > 0.0) || !(d2 < 1e300)) break;
+                    const cplx du = (1.0 / d2) * (q * conj(dq));
+                    u = u - du;
+                    if (abs2(du) <= 1e-24 * abs2(u)) { okn = true; break; }   // |du| <= 1e-12 |u|: quadratic, the step applied lands at rounding level
+                }
+                const double u2 = abs2(u);
+                if (okn && u2 > 0.0) {
+                    const cplx wr = (1.0 / u2) * conj(u);
+                    const double rinv = 2.0 * sqrt(u2);            // 1/r, r = |w|/2
+                    double rest = 1.0, pw = rinv;
+#pragma unroll
+                    for (int k = 2; k <= N; k++) { pw *= rinv; rest = fma(sqrt(abs2(cf[k])), pw, rest); }
+                    if (sqrt(a1) * rinv > rest) { ws = wr; st = ILA_OK; }
+                }
+            }
+        }
     }
+    if (st == ILA_OK && !(abs2(ws) < 1e300)) st = ILA_NOT_CONVERGED;       // non-finite or overflowing root: flagged, never NO_QL
 
     // μ = β w ; n2 = |μ|^2 ; existence test n2 >= |β|^2 (infqltoeplitz.jl:13,23)
     const cplx beta = P.a[N];

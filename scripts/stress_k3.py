@@ -16,14 +16,13 @@ for l in range(1, 8):
         lam = (rng.normal(size=400) * 3 + 1j * rng.normal(size=400) * 3) if cplx else rng.normal(size=400) * 4
         for branch in (1, 2) if l >= 1 else (1,):
             Lg, sg = ila_b200.ql_toeplitz_l11(col, lam, branch_rank=branch)
-            Lo, so = tq.ql_toeplitz_l11(col, lam, branch_rank=branch)
+            # the C ABI's documented sign rule for the real-typed path ("householder" = the finite-section limit)
+            Lo, so = tq.ql_toeplitz_l11(col, lam, branch_rank=branch, sign_rule="householder")
             mism = int((sg != so).sum())
             ok = (sg == 0) & (so == 0)
             scale = np.abs(col[0])
-            # real-typed path: the sign of L[1,1] follows LAPACK's eigenvector sign (unpinned beyond the
-            # reference's tests) -> compare magnitudes there and count the sign flips separately
-            a, b = (Lg[ok], Lo[ok]) if cplx else (np.abs(Lg[ok]), np.abs(Lo[ok]))
-            flips = 0 if cplx else int((np.sign(Lg[ok].real) != np.sign(Lo[ok].real)).sum())
+            a, b = Lg[ok], Lo[ok]                      # signed comparison on both paths
+            flips = int((np.sign(Lg[ok].real) != np.sign(Lo[ok].real)).sum())
             err = np.abs(a - b)
             rel = err / np.maximum(np.abs(Lo[ok]), 0.05 * scale)
             w = float(rel.max()) if ok.any() else 0.0
