@@ -154,3 +154,46 @@ def test_concurrent_callers(ila):
     for t in th:
         t.join()
     assert not errs, errs
+
+
+def test_adaptive_solves_non_finite_and_scaled_inputs(ila):
+    """K1+K2 / K5 edge cases against the C oracle, bit for bit: a NaN right-hand side (the reference's driver meets NaN in its
+    convergence test — status 5 here), operators and right-hand sides scaled by 1e±100 (the sweeps are scale-free apart from
+    the floatmin tolerance), a zero right-hand side (datasize 0), a right-hand side longer than one COLGROWTH chunk."""
+    from oracle import banded as ob
+    from scipy.special import jv
+    z = np.array([200.0, 800.0])
+    p, q, r = ila.bessel_operator(z)
+    cases = {
+        "nan rhs": dict(b=np.array([[np.nan], [0.3]])),
+        "zero rhs": dict(b=np.zeros((2, 1))),
+        "tiny rhs": dict(b=jv(1, z)[:, None] * 1e-200),
+        "huge rhs": dict(b=jv(1, z)[:, None] * 1e200),
+        "long rhs": dict(b=np.cos(np.arange(1500.0))[None, :].repeat(2, 0) * 0.5 ** np.arange(1500)[None, :] + 1e-3),
+        "tolerance 1e-8": dict(b=jv(1, z)[:, None], tol=1e-8),
+    }
+    for name, kw in cases.items():
+        g = ila.qr_banded_solve(1, 1, p, q, r, ncap=6000, **kw)
+        o = ob.qr_banded_solve(1, 1, p, q, r, ncap=6000, **kw)
+        assert np.array_equal(g["status"], o["status"]), name
+        assert np.array_equal(g["ncols"], o["ncols"]) and np.array_equal(g["nconv"], o["nconv"]), name
+        for i in range(2):
+            n = int(o["ncols"][i])
+            assert np.array_equal(g["x"][i], o["x"][i, :n], equal_nan=True), (name, i)
+    assert ila.qr_banded_solve(1, 1, p, q, r, b=np.array([[np.nan], [0.3]]), ncap=6000)["status"][0] == 5
+    for s in (1e-100, 1e100):                      # operator scaled: x scales by 1/s, counts unchanged
+        g1 = ila.qr_banded_solve(1, 1, p, q, r, b=jv(1, z)[:, None], ncap=6000)
+        gs = ila.qr_banded_solve(1, 1, p * s, q * s, r, b=jv(1, z)[:, None], ncap=6000)
+        os_ = ob.qr_banded_solve(1, 1, p * s, q * s, r, b=jv(1, z)[:, None], ncap=6000)
+        assert np.array_equal(gs["status"], os_["status"]) and np.array_equal(gs["ncols"], os_["ncols"])
+        for i in range(2):
+            assert np.array_equal(gs["x"][i], os_["x"][i, :int(os_["ncols"][i])], equal_nan=True)
+    # Cholesky: NaN shift / indefinite / scaled
+    p4, q4 = ila.pentadiagonal_operator(np.array([0.5, 2.0]), eps=1e-2)
+    for name, kw in {"plain": {}, "scaled rhs": dict(b=[1e-150]), "nan rhs": dict(b=[np.nan])}.items():
+        kw = dict(dict(b=[1.0]), **kw)
+        g = ila.chol_banded_solve(2, p4, q4, ncap=6000, **kw)
+        o = ob.chol_banded_solve(2, p4, q4, ncap=6000, **kw)
+        assert np.array_equal(g["status"], o["status"]) and np.array_equal(g["ncols"], o["ncols"]), name
+        for i in range(2):
+            assert np.array_equal(g["x"][i], o["x"][i, :int(o["ncols"][i])], equal_nan=True), (name, i)
