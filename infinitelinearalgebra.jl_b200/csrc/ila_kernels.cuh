@@ -58,6 +58,7 @@ struct QrBwdArgs {
 int qr_record_doubles(int l, int u, bool refl);
 void qr_set_arith_mode(int mode);
 void qr_set_bulk_loader(int v);
+void qr_set_fwd_duo(int v);
 int qr_get_arith_mode();
 int launch_qr_forward(int l, int u, const QrFwdArgs &a, bool refl, cudaStream_t s);
 int launch_qr_scan(const int64_t *d_ncols, int64_t batch, int64_t *d_xoff, cudaStream_t s);
