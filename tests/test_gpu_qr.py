@@ -174,3 +174,73 @@ def test_bulk_and_ldgsts_loaders_identical(ila):
         a, b = outs[(5, key)], outs[(6, key)]
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
         assert np.array_equal(a[0].view(np.int64), b[0].view(np.int64)), key
+
+
+def _solve_both_sweeps(ila, *args, **kw):
+    """The same solve with the one-warp forward sweep (mode 7) and the scout / verifier / clerk sweep (mode 8, default)."""
+    from ila_b200 import _lib
+    outs = []
+    try:
+        for mode in (7, 8):
+            _lib.check(_lib.lib().ila_qr_set_arith_mode(mode))
+            o = ila.qr_banded_solve(*args, **kw)
+            outs.append(o)
+    finally:
+        _lib.check(_lib.lib().ila_qr_set_arith_mode(8))
+    a, b = outs
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["ncols"], b["ncols"]) and np.array_equal(a["nconv"], b["nconv"])
+    assert np.array_equal(a["xflat"].view(np.int64), b["xflat"].view(np.int64))
+    return b
+
+
+def test_three_warp_sweep_regimes_bit_exact(ila):
+    """The l = 1 forward sweep on three warps (candidates from a shortened chain, proved correctly rounded before use) against
+    the one-warp sweep and the oracle, bit for bit, in the regimes that stress the proofs: candidates that are powers of two
+    (tau = 1 when the pivot entry vanishes, tau = 2 when the subdiagonal is negligible, normu = |b|), operands outside the
+    tests' exponent boxes (every column takes the IEEE path, the verifier goes on alone), subdiagonals outside the sweep's box
+    (the group falls back to one warp), chunk boundaries inside every other group, ragged groups, capacity and NaN exits."""
+    from oracle import banded as ob
+    rng = np.random.default_rng(11)
+
+    def check(l, u, p, q, r=None, **kw):
+        g = _solve_both_sweeps(ila, l, u, p, q, r, **kw)
+        okw = {k: v for k, v in kw.items() if k != "ncap_per"}
+        o = ob.qr_banded_solve(l, u, p, q, r, **okw)
+        _compare(g, o, len(np.atleast_2d(p)))
+        return g
+
+    # zero main diagonal at the start (pivot entry 0: tau = 1, x1 = +-1), slowly growing diagonal
+    batch = 37
+    p = np.zeros((batch, 3)); p[:, 0] = 1.0; p[:, 2] = 1.0
+    q = np.zeros((batch, 3)); q[:, 1] = np.linspace(0.002, 0.02, batch)
+    g = check(1, 1, p, q, b=[1.0, 0.5], ncap=60000)
+    assert np.all(g["status"] == 0)
+    # subdiagonal negligible against a fast-growing diagonal (normu = |a|, tau = 2 exactly), scaled subdiagonals inside the box
+    for sub in (1e-9, 1e-60, 3e70):
+        p = np.tile([[0.7 * sub, 2.0, sub]], (5, 1)); p[:, 1] = sub * np.array([1.0, -3.0, 0.25, 1e3, -1e-3])
+        q = np.zeros((5, 3)); q[:, 1] = sub * np.array([1e4, 2.0, 1e8, -5.0, 0.5])
+        check(1, 1, p, q, b=[sub, -sub, 2 * sub], ncap=20000, tol=1e-300)
+    # diagonal so large that s leaves the proofs' box (2^900): IEEE columns throughout; subdiagonal outside the sweep's box
+    p = np.array([[1.0, 1e200, 1.0], [1.0, -3e180, 2.0]]); q = np.array([[0.0, 1e198, 0.0], [0.0, 1e179, 0.0]])
+    check(1, 1, p, q, b=[1.0], ncap=6000, tol=1e-280)
+    p = np.array([[1.0, 2.0, 1e-150], [1.0, 3.0, 1e150]]); q = np.array([[0.0, 0.3, 0.0], [0.0, -0.2, 0.0]])
+    check(1, 1, p, q, b=[1.0, 1.0], ncap=8000, tol=1e-250)
+    # other upper bandwidths, denominators, shifts, a right-hand side longer than a group, tiny chunks (a chunk boundary in every
+    # other group of 8 columns), 33 and 64 instances
+    for (u, batch, cgw, nb) in [(0, 33, 16, 1), (2, 64, 24, 11), (3, 5, 1000, 3), (1, 33, 12, 20)]:
+        nd = u + 2
+        p = rng.normal(size=(batch, nd)); p[:, u] += 5.0 * np.sign(p[:, u])
+        p[:, u + 1] = rng.choice([-1.0, 0.5, 2.0, 1.0], size=batch)
+        q = np.zeros((batch, nd)); q[:, u] = 0.03 * np.sign(p[:, u]) * rng.uniform(0.5, 2.0, size=batch)
+        r = np.ones((batch, nd)); r[:, u] = rng.uniform(0.5, 3.0, size=batch)
+        check(1, u, p, q, r, shift=rng.normal(size=batch) * 0.2, b=rng.normal(size=(batch, nb)), ncap=12000, colgrowth=cgw, tol=1e-30)
+    # capacity reached (status 3, nothing returned) next to instances that converge; NaN in an operator
+    z = np.array([200.0, 5000.0, 300.0])
+    p, q, r = ila.bessel_operator(z)
+    g = _solve_both_sweeps(ila, 1, 1, p, q, r, b=jv(1, z)[:, None], ncap=3000)
+    assert list(g["status"]) == [0, 3, 0] and g["ncols"][1] == 0
+    o = ob.qr_banded_solve(1, 1, p[[0, 2]], q[[0, 2]], r[[0, 2]], b=jv(1, z[[0, 2]])[:, None], ncap=3000)
+    assert np.array_equal(g["x"][0], o["x"][0, :int(o["ncols"][0])]) and np.array_equal(g["x"][2], o["x"][1, :int(o["ncols"][1])])
+    p2 = p.copy(); p2[1, 1] = np.nan
+    g = _solve_both_sweeps(ila, 1, 1, p2, q, r, b=jv(1, z)[:, None], ncap=9000)
+    assert g["status"][1] != 0 and g["status"][0] == 0 and g["status"][2] == 0
