@@ -27,3 +27,12 @@ print(f"forward {f:.3f} ms  longest {ncol} columns  {f*1e-3*clk/ncol:.1f} cycles
 if st is not None and (st == 0).all():
     b = t(plan.run_backsolve)
     print(f"backward {b:.3f} ms  {b*1e-3*clk/ncol:.1f} cycles/row")
+# the same back-substitution through the interleaved stream + compaction pass
+from ila_b200 import _lib
+_lib.check(_lib.lib().ila_qr_set_arith_mode(3))
+b3 = t(plan.run_backsolve)
+_lib.check(_lib.lib().ila_qr_set_arith_mode(2))
+print(f"backward (interleaved + compaction) {b3:.3f} ms")
+
+import json
+json.dump({"forward_ms": f, "backward_ms": b, "backward_interleaved_ms": b3, "columns": ncol}, open(os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "gpurun_out", "c2_cycles.json"), "w"))
