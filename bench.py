@@ -578,7 +578,7 @@ def run_ours(args, rank, local_rank, world):
                                            "columns_swept": cols, "columns_reference_datasize": cols_ref},
             "roofline": {"bound": "hbm", "achieved": gbs2, "peak": hbm_peak, "unit": "GB/s", "frac": gbs2 / hbm_peak,
                          "traffic": None, "peak_kind": peak_kind, "bytes_per_unit": BYTES_PER_COLUMN,
-                         "note": "latency bound: 4096 serial recurrences = 128 warps on 148 SMs"},
+                         "note": "latency bound: 4096 serial recurrences = 128 groups on 148 SMs; the time is the dependent chain of the longest instance (forward sweep on three warps per group: scout / verifier / clerk)"},
             "gpu_launches_per_step": launches2,
         }
         if world > 1:

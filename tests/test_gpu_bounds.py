@@ -32,7 +32,7 @@ plan.ncap = 4000             # (the checked pointer redirects the stray stores t
 plan.run_factor(); torch.cuda.synchronize()
 _lib.check(_lib.lib().ila_debug_bounds_report(ctypes.byref(c), ctypes.byref(s), ctypes.byref(i), ctypes.byref(e)))
 print("NEGATIVE", c.value, s.value, i.value, e.value)
-assert c.value > 0 and s.value == 1201
+assert c.value > 0 and s.value in (1201, 1205)   # the record pointer of the one-warp sweep / of the three-warp sweep's clerk
 print("bounds ok")
 '''
 
