@@ -172,9 +172,10 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
  * (direct ragged stores when the batch is at most two warps per SM, coalesced interleaved stream + compaction otherwise) /
  * always compaction / always direct — all three must give identical bits too.  Modes 5 / 6 select the loader of the
  * back-substitution ring: per-lane 16-byte cp.async (LDGSTS; default, the faster one on the latency-bound C2 batch) / one
- * cp.async.bulk per group completing on an mbarrier — same bits.  Modes 7 / 8 select the forward sweep of l = 1 operators
- * (plain solves: no factor export, no resumable state, no head table): one warp per group of 32 instances / three warps per
- * group (default) — a scout running a shortened dependent chain, a verifier that proves every candidate of the scout correctly
+ * cp.async.bulk per group completing on an mbarrier — same bits.  Modes 7 / 8 / 11 select the forward sweep of l = 1
+ * operators (plain solves: no factor export, no resumable state, no head table): one warp per group of 32 instances / three
+ * warps per group when the batch is at most one group per SM, the latency-bound regime (default) / three warps whatever the
+ * batch size — a scout running a shortened dependent chain, a verifier that proves every candidate of the scout correctly
  * rounded by exact residual tests before it is used, a clerk for Q'b, the adaptive test and the records — same bits again. */
 int ila_qr_set_arith_mode(int mode);
 

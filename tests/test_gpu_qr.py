@@ -177,11 +177,11 @@ def test_bulk_and_ldgsts_loaders_identical(ila):
 
 
 def _solve_both_sweeps(ila, *args, **kw):
-    """The same solve with the one-warp forward sweep (mode 7) and the scout / verifier / clerk sweep (mode 8, default)."""
+    """The same solve with the one-warp forward sweep (mode 7) and the scout / verifier / clerk sweep forced (mode 11)."""
     from ila_b200 import _lib
     outs = []
     try:
-        for mode in (7, 8):
+        for mode in (7, 11):
             _lib.check(_lib.lib().ila_qr_set_arith_mode(mode))
             o = ila.qr_banded_solve(*args, **kw)
             outs.append(o)
