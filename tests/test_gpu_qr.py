@@ -244,3 +244,41 @@ def test_three_warp_sweep_regimes_bit_exact(ila):
     p2 = p.copy(); p2[1, 1] = np.nan
     g = _solve_both_sweeps(ila, 1, 1, p2, q, r, b=jv(1, z)[:, None], ncap=9000)
     assert g["status"][1] != 0 and g["status"][0] == 0 and g["status"][2] == 0
+
+
+def test_three_warp_sweep_randomized_against_one_warp(ila):
+    """Random l = 1 operators (bandwidths, scales over six decades, slopes of either sign, denominators, shifts, right-hand
+    sides, chunk lengths, tolerances, batch sizes that leave ragged groups): the three-warp sweep must reproduce the one-warp
+    sweep bit for bit — solution, ncols, nconv, status — whatever happens on the way (re-seeds, IEEE columns, fallback groups,
+    instances that hit the capacity)."""
+    from oracle import banded as ob
+    rng = np.random.default_rng(2024)
+    statuses = set()
+    for trial in range(40):
+        u = int(rng.integers(0, 4))
+        nd = u + 2
+        batch = int(rng.integers(1, 71))
+        scale = 10.0 ** rng.uniform(-3, 3)
+        p = rng.normal(size=(batch, nd)) * scale
+        p[:, u] += 4.0 * scale * np.sign(p[:, u])
+        p[:, u + 1] = scale * rng.choice([-2.0, -1.0, 0.25, 1.0, 3.0], size=batch) * 10.0 ** rng.uniform(-2, 2)
+        q = np.zeros((batch, nd))
+        q[:, u] = scale * rng.choice([-1.0, 1.0], size=batch) * 10.0 ** rng.uniform(-3, 0, size=batch)
+        r = np.ones((batch, nd))
+        if rng.random() < 0.5:
+            r[:, u] = rng.uniform(0.3, 4.0, size=batch)
+        shift = rng.normal(size=batch) * scale if rng.random() < 0.7 else None
+        nb = int(rng.integers(1, 6))
+        b = rng.normal(size=(batch, nb)) * 10.0 ** rng.uniform(-5, 5)
+        kw = dict(shift=shift, b=b, ncap=int(rng.choice([700, 4000, 12000])), colgrowth=int(rng.choice([8, 50, 1000])),
+                  tol=float(rng.choice([1e-300, 1e-40, 1e-12])))
+        g = _solve_both_sweeps(ila, 1, u, p, q, r, **kw)
+        statuses.update(int(s) for s in g["status"])
+        if trial % 8 == 0:      # and the oracle, on a few of them
+            o = ob.qr_banded_solve(1, u, p, q, r, **kw)
+            assert np.array_equal(g["status"], o["status"])
+            ok = o["status"] == 0
+            assert np.array_equal(g["ncols"][ok], o["ncols"][ok]) and np.array_equal(g["nconv"][ok], o["nconv"][ok])
+            for i in np.nonzero(ok)[0]:
+                assert np.array_equal(g["x"][i], o["x"][i, :int(o["ncols"][i])])
+    assert 0 in statuses
