@@ -171,8 +171,8 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
  * (validation mode: both must give identical bits).  Modes 2 / 3 / 4 select how the back-substitution delivers x: auto
  * (direct ragged stores when the batch is at most two warps per SM, coalesced interleaved stream + compaction otherwise) /
  * always compaction / always direct — all three must give identical bits too.  Modes 5 / 6 select the loader of the
- * back-substitution ring: per-lane 16-byte cp.async (LDGSTS; default, the faster one on the latency-bound C2 batch) / one
- * cp.async.bulk per group completing on an mbarrier — same bits.  Modes 7 / 8 / 11 select the forward sweep of l = 1
+ * back-substitution ring: per-lane 16-byte cp.async (LDGSTS) / one cp.async.bulk per group completing on an mbarrier (TMA;
+ * default) — same bits.  Modes 7 / 8 / 11 select the forward sweep of l = 1
  * operators (plain solves: no factor export, no resumable state, no head table): one warp per group of 32 instances / three
  * warps per group when the batch is at most one group per SM, the latency-bound regime (default) / three warps whatever the
  * batch size — a scout running a shortened dependent chain, a verifier that proves every candidate of the scout correctly

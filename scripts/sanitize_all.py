@@ -18,7 +18,7 @@ o = ila_b200.qr_banded_solve(1, 1, p, q, r, b=jv(1, z)[:, None], ncap_per=ila_b2
 for mode in (5, 6):
     _lib.check(_lib.lib().ila_qr_set_arith_mode(mode))
     o = ila_b200.qr_banded_solve(1, 1, p, q, r, b=jv(1, z)[:, None], ncap_per=ila_b200.bessel_ncap(z)); print("K2 loader", mode, o["status"])
-_lib.check(_lib.lib().ila_qr_set_arith_mode(5))
+_lib.check(_lib.lib().ila_qr_set_arith_mode(6))
 plan = ila_b200.QrBandedPlan(1, 1, p, q, r, b=jv(1, z)[:, None], ncap=4000)
 plan.run_factor_resumable(1500, False); plan.run_factor_resumable(4000, True); plan.run_backsolve(); print("resume", plan.d_status.cpu().numpy())
 p4, q4 = ila_b200.pentadiagonal_operator(np.array([0.1, 3.0]), eps=1e-2)

@@ -28,5 +28,5 @@ for name, zs in (("C2 4096 z in [1e3,1e5]", 1e3 + (1e5 - 1e3) * np.arange(4096) 
     out[f"{name} / forward"] = float(np.median(ts))
     print(f"{name:28s} forward sweep {np.median(ts):8.3f} ms")
     del plan
-_lib.check(lib.ila_qr_set_arith_mode(5))
+_lib.check(lib.ila_qr_set_arith_mode(6))
 json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r02_c2_loader.json"), "w"), indent=1)

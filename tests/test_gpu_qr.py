@@ -169,7 +169,7 @@ def test_bulk_and_ldgsts_loaders_identical(ila):
             o5 = ila.qr_banded_solve(2, 2, [[1, 0, 3, 0, 1]] * 40, [[0] * 5] * 40, shift=np.linspace(-0.5, 0.5, 40), b=[3., 4, 5], ncap=9000)
             outs[(mode, "5band")] = (o5["xflat"].copy(), o5["ncols"].copy(), o5["status"].copy())
     finally:
-        _lib.check(_lib.lib().ila_qr_set_arith_mode(5))
+        _lib.check(_lib.lib().ila_qr_set_arith_mode(6))
     for key in (False, True, "5band"):
         a, b = outs[(5, key)], outs[(6, key)]
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
