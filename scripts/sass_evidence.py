@@ -5,7 +5,7 @@ import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "infinitelinearalgebra.jl_b200", "libila_b200.so")
 out_path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "profiles", "r02_sass_resource_usage.txt")
-HOT = ["ql_toeplitz_l11_kernelILi4ELb0ELb0", "qr_forward_trio_kernelILi1E", "qr_forward_kernelILi1ELi1ELb0ELb1", "qr_backsolve_kernelILi1ELi1E", "chol_forward_kernelILi2",
+HOT = ["ql_toeplitz_l11_kernelILi4ELb0ELb0", "qr_forward_trio_kernelILi1E", "qr_forward_kernelILi1ELi1ELb0ELb1", "qr_backsolve_kernelILi1ELi1ELb0ELb1ELb1ELi16E", "chol_forward_kernelILi2",
        "ql_blocktri_l11_kernelIdLi2", "triconj_bands_kernel", "qr_blockbanded_kernel", "qr_almostbanded_kernel", "ql_pert_head_kernelILb0"]
 ru = subprocess.run(["cuobjdump", "--dump-resource-usage", so], capture_output=True, text=True).stdout
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
