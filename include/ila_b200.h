@@ -176,7 +176,10 @@ int ila_qr_banded_solve_f64(int l, int u, int64_t batch, const double *p, const 
  * operators (plain solves: no factor export, no resumable state, no head table): one warp per group of 32 instances / three
  * warps per group when the batch is at most one group per SM, the latency-bound regime (default) / three warps whatever the
  * batch size — a scout running a shortened dependent chain, a verifier that proves every candidate of the scout correctly
- * rounded by exact residual tests before it is used, a clerk for Q'b, the adaptive test and the records — same bits again. */
+ * rounded by exact residual tests before it is used, a clerk for Q'b, the adaptive test and the records — same bits again.
+ * Modes 1000 + n are a test hook: the scout corrupts one candidate by an ulp every n columns (n = 0: off), which the verifier
+ * must catch, repair with the IEEE column and answer by re-seeding the scout (or, when that happens too often, by going on
+ * alone) — the results must not change. */
 int ila_qr_set_arith_mode(int mode);
 
 /* device-resident two-phase form (no host round trip between the phases; the caller owns all buffers):

@@ -1569,6 +1569,7 @@ int ila_qr_set_arith_mode(int mode)
     // 0 / 1: arithmetic of the sweeps; 2 / 3 / 4 (validation knobs): solution output auto / always compacted / always direct
     if (mode >= 2 && mode <= 4) { g_qr_direct_x = mode == 2 ? -1 : (mode == 3 ? 0 : 1); return 0; }
     if (mode == 5 || mode == 6) { qr_set_bulk_loader(mode == 6); return 0; }   // back-substitution loader: LDGSTS / cp.async.bulk
+    if (mode >= 1000) { qr_set_fwd_fault(mode - 1000); return 0; }   // test hook: the scout of the three-warp sweep misrounds a candidate every (mode - 1000) columns
     if (mode == 7 || mode == 8 || mode == 11) { qr_set_fwd_duo(mode == 7 ? 0 : (mode == 8 ? 1 : 2)); return 0; }   // forward sweep (l = 1): one warp / three warps for batches of at most one group per SM / three warps always
     if (mode != 0 && mode != 1) return set_error(ILA_ERR_ARG, "qr arith mode must be 0 (branch-free exact), 1 (IEEE intrinsics), 2-4 (output path), 5-6 (loader) or 7, 8, 11 (forward sweep warps)");
     qr_set_arith_mode(mode);

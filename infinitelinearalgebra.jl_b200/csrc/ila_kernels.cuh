@@ -43,6 +43,7 @@ struct QrFwdArgs {
     double *state = nullptr;   // optional resumable state, qr_state_doubles(l,u) per instance (see qr_forward_kernel)
     int resume = 0;            // continue from `state` instead of column 0
     int factor_only = 0;       // partialqr!(F, ncap): sweep to column ncap, no right-hand side / convergence test
+    int fault_every = 0;       // test hook of the three-warp sweep: the scout corrupts a candidate by one ulp every so many columns
 };
 int qr_state_doubles(int l, int u);
 struct QrBwdArgs {
@@ -59,6 +60,7 @@ int qr_record_doubles(int l, int u, bool refl);
 void qr_set_arith_mode(int mode);
 void qr_set_bulk_loader(int v);
 void qr_set_fwd_duo(int v);
+void qr_set_fwd_fault(int every);
 int qr_get_arith_mode();
 int launch_qr_forward(int l, int u, const QrFwdArgs &a, bool refl, cudaStream_t s);
 int launch_qr_scan(const int64_t *d_ncols, int64_t batch, int64_t *d_xoff, cudaStream_t s);

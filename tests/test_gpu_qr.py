@@ -282,3 +282,34 @@ def test_three_warp_sweep_randomized_against_one_warp(ila):
             for i in np.nonzero(ok)[0]:
                 assert np.array_equal(g["x"][i], o["x"][i, :int(o["ncols"][i])])
     assert 0 in statuses
+
+
+def test_three_warp_sweep_recovers_from_misrounded_candidates(ila):
+    """Fault injection (mode 1000 + n: the scout corrupts one candidate by an ulp every n columns): the verifier must reject
+    it, take the IEEE column for that lane, re-seed the scout — and, when faults come too often, go on alone.  Whatever the
+    rate, solution, ncols, nconv and status must equal the one-warp sweep's bit for bit."""
+    from ila_b200 import _lib
+    lib = _lib.lib()
+    z = np.concatenate([np.linspace(40.0, 2500.0, 37), [6000.0]])
+    p, q, r = ila.bessel_operator(z)
+    kw = dict(b=jv(1, z)[:, None], ncap_per=ila.bessel_ncap(z))
+    rng = np.random.default_rng(5)
+    p3 = rng.normal(size=(9, 5)); p3[:, 3] += 5.0; p3[:, 4] = 1.5
+    q3 = np.zeros((9, 5)); q3[:, 3] = 0.02
+    try:
+        _lib.check(lib.ila_qr_set_arith_mode(7))
+        ref = ila.qr_banded_solve(1, 1, p, q, r, **kw)
+        ref3 = ila.qr_banded_solve(1, 3, p3, q3, b=rng.normal(size=(9, 2)), ncap=9000, tol=1e-200)
+        rng = np.random.default_rng(5); rng.normal(size=(9, 5))
+        _lib.check(lib.ila_qr_set_arith_mode(11))
+        for every in (4001, 257, 31, 3, 1):      # rare -> every column (the verifier ends up alone)
+            _lib.check(lib.ila_qr_set_arith_mode(1000 + every))
+            g = ila.qr_banded_solve(1, 1, p, q, r, **kw)
+            assert np.array_equal(g["status"], ref["status"]) and np.array_equal(g["ncols"], ref["ncols"]) and np.array_equal(g["nconv"], ref["nconv"])
+            assert np.array_equal(g["xflat"].view(np.int64), ref["xflat"].view(np.int64)), every
+            rng2 = np.random.default_rng(5); rng2.normal(size=(9, 5))
+            g3 = ila.qr_banded_solve(1, 3, p3, q3, b=rng2.normal(size=(9, 2)), ncap=9000, tol=1e-200)
+            assert np.array_equal(g3["ncols"], ref3["ncols"]) and np.array_equal(g3["xflat"].view(np.int64), ref3["xflat"].view(np.int64)), every
+    finally:
+        _lib.check(lib.ila_qr_set_arith_mode(1000))
+        _lib.check(lib.ila_qr_set_arith_mode(8))
